@@ -1,0 +1,120 @@
+/* lion_b200 -- C ABI of the B200-native LION sampling hot path.
+ *
+ * Drop-in boundary.  Every entry point takes plain device pointers,
+ * sizes and a cudaStream_t (as void*), returns 0 on success or a negative code (never exits
+ * the process -- the reference's kernels exit(-1) on a launch error,
+ * third_party/pvcnn/functional/src/cuda_utils.cuh:28-37), allocates nothing on the stream
+ * path and is CUDA-graph capturable after one warm-up call.  lion_last_error() describes the
+ * last failure of the calling thread.  "reference" paths below are relative to
+ * /root/reference.
+ */
+#ifndef LION_B200_H
+#define LION_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct LionCtx LionCtx;       /* device + scratch arena                         */
+typedef struct LionModel LionModel;   /* packed weights of one network / one block      */
+
+int lion_version(void);
+const char* lion_last_error(void);
+int lion_ctx_create(int device, LionCtx** out);
+int lion_ctx_destroy(LionCtx* ctx);
+/* kernels launched by the last network-level call on this context (bench.py: gpu_launches) */
+int lion_ctx_last_launches(LionCtx* ctx);
+size_t lion_ctx_arena_bytes(LionCtx* ctx);
+
+/* ---------------------------------------------------------------------------------------
+ * The seven operators of third_party/pvcnn/functional (reference layouts: features [B,C,N]
+ * channel-major fp32, coords [B,3,N], flat voxel index x*r*r + y*r + z).  Outputs are
+ * caller-allocated (the reference's C++ wrappers allocate them with torch::zeros).
+ * ------------------------------------------------------------------------------------- */
+/* replaces avg_voxelize_forward, src/bindings.cpp:33 -> voxelization/vox.cpp:17-43.
+ * out [B,C,r^3] fp32, ind [B,N] int32, cnt [B,r^3] int32 (all written). */
+int lion_avg_voxelize(const float* features, const int* coords, float* out, int* ind, int* cnt,
+                      int B, int C, int N, int r, void* stream);
+/* replaces trilinear_devoxelize_forward, src/bindings.cpp:29 -> interpolate/trilinear_devox.cpp:18-55.
+ * grid [B,C,r^3], coords [B,3,N] fp32 in voxel units; out [B,C,N]; inds/wgts [B,8,N] written
+ * only when is_training (may be NULL otherwise). */
+int lion_trilinear_devoxelize(const float* grid, const float* coords, float* out, int* inds, float* wgts,
+                              int B, int C, int N, int r, int is_training, void* stream);
+/* replaces furthest_point_sampling, src/bindings.cpp:15 -> sampling/sampling.cpp:43-58. idx [B,M] int32. */
+int lion_furthest_point_sampling(const float* coords, int* idx, int B, int N, int M, void* stream);
+/* replaces gather_features_forward, src/bindings.cpp:11 -> sampling/sampling.cpp:6-24. out [B,C,M]. */
+int lion_gather(const float* features, const int* idx, float* out, int B, int C, int N, int M, void* stream);
+/* replaces ball_query, src/bindings.cpp:17 -> ball_query/ball_query.cpp:6-27. out [B,M,K] int32, K<=32. */
+int lion_ball_query(const float* centers, const float* points, int* out, int B, int N, int M, float radius, int K,
+                    void* stream);
+/* replaces grouping_forward, src/bindings.cpp:18 -> grouping/grouping.cpp:6-24. out [B,C,M,U]. */
+int lion_grouping(const float* features, const int* idx, float* out, int B, int C, int N, int M, int U, void* stream);
+/* replaces three_nearest_neighbors_interpolate_forward, src/bindings.cpp:22 ->
+ * interpolate/neighbor_interpolate.cpp:10-41. out [B,C,N], idx/wgt [B,3,N] (all written). */
+int lion_three_nn_interpolate(const float* points, const float* centers, const float* centers_features, float* out,
+                              int* idx, float* wgt, int B, int C, int N, int M, void* stream);
+/* the coordinate half of Voxelization.forward (models/pvcnn2_ada.py:173-188):
+ * norm_coords [B,3,N] fp32 in [0,r-1], vox [B,3,N] int32 = round-half-even. */
+int lion_voxel_coords(const float* coords, float* norm_coords, int* vox, int B, int N, int r, int normalize, float eps,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Networks and blocks.  A model is created from an int descriptor (architecture) and the
+ * module's parameters as device pointers in the reference's state_dict order; the pointers
+ * must stay valid (weights are re-packed into kernel layouts at creation).
+ * kinds: */
+enum { LION_KIND_UNET = 1, LION_KIND_PVCONV = 2, LION_KIND_SA = 3, LION_KIND_FP = 4, LION_KIND_ATTN = 5,
+       LION_KIND_SHARED_MLP = 6, LION_KIND_GLOBAL_PRIOR = 7 };
+int lion_model_create(LionCtx* ctx, int kind, const int* desc, int ndesc, const float* const* params, int nparams,
+                      LionModel** out);
+int lion_model_destroy(LionModel* m);
+/* re-pack after the parameter tensors changed in place (load_state_dict) */
+int lion_model_refresh(LionModel* m);
+
+/* PVCNN2Unet.forward (models/latent_points_ada.py:117-173) as called by PVCNN2Prior.forward
+ * (models/latent_points_ada_localprior.py:72-83) and LatentPointDecPVC.forward
+ * (models/latent_points_ada.py:255-272): x [B,N,D] point-major (= the reference's
+ * x.view(B,N,D) before its permute), t [B] or NULL, style [B,S], clip [B,clip_dim] or NULL,
+ * out [B,N,num_classes] point-major. */
+int lion_unet_forward(LionModel* m, const float* x, const float* t, const float* style, const float* clip, float* out,
+                      int B, int N, void* stream);
+/* PVConv.forward (models/pvcnn2_ada.py:235-280): features [B,Cin,N], coords [B,3,N] -> out [B,Cout,N] */
+int lion_pvconv_fwd(LionModel* m, const float* features, const float* coords, const float* style, float* out,
+                    int B, int N, void* stream);
+/* PointNetSAModule.forward (models/pvcnn2_ada.py:354-382): -> out_features [B,Cout,M], out_coords [B,3,M] */
+int lion_sa_module_fwd(LionModel* m, const float* features, const float* coords, const float* style,
+                       float* out_features, float* out_coords, int B, int N, void* stream);
+/* PointNetFPModule.forward (models/pvcnn2_ada.py:393-411): points_features may be NULL -> out [B,Cout,N] */
+int lion_fp_module_fwd(LionModel* m, const float* points_coords, const float* centers_coords,
+                       const float* centers_features, const float* points_features, const float* style, float* out,
+                       int B, int N, int M, void* stream);
+/* LinearAttention.forward (models/pvcnn2_ada.py:54-71): x [B,C,N] -> out [B,C,N] */
+int lion_linear_attention_fwd(LionModel* m, const float* x, float* out, int B, int N, void* stream);
+/* SharedMLP.forward (models/pvcnn2_ada.py:140-164): x [B,C,R] -> out [B,Cout,R] */
+int lion_shared_mlp_fwd(LionModel* m, const float* x, const float* style, float* out, int B, int R, void* stream);
+/* Prior.forward with SE cells (models/score_sde/resnet.py:195-218): x [B,D], t [B], clip [B,clip_dim] or NULL */
+int lion_global_prior_forward(LionModel* m, const float* x, const float* t, const float* clip, float* out, int B,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * One ancestral DDPM step (utils/diffusion_pvd.py:283-296 + :475-486), elementwise over n.
+ * The step index t (the reference's loop variable, T-1 .. 0) is read from *step_ptr on the
+ * device and selects row t of `tables` ([T][4] fp32), so a captured graph can be replayed:
+ *   t > 0 : row = {1/sqrt(alpha_t), beta_t, sqrt(1-abar_t), exp(0.5*log beta_t)}
+ *           x_out = row0 * (x - (row1*eps)/row2) + (row3*noise)*temp
+ *   t = 0 : row = {1/sqrt(abar_0), sqrt(1-abar_0), 1, 0}
+ *           x_out = row0 * (x - row1*eps)                       (noise unused)
+ * evaluated in the reference's operation order without FMA contraction.  x_out may alias x.
+ * hist (optional, [T][n]): the result is also stored at slot T-1-t (the reference keeps every
+ * intermediate in output_list['pred_x']).
+ * ------------------------------------------------------------------------------------- */
+int lion_ddpm_update(const float* x, const float* eps, const float* noise, float* x_out, const float* tables,
+                     const int* step_ptr, float temp, size_t n, float* hist, int T, void* stream);
+/* set / decrement the device-side step counter and write the model's timestep (t+1, 1..T) into t_out[B] */
+int lion_ddpm_set_step(int* step_ptr, float* t_out, int B, int t_index, void* stream);
+int lion_ddpm_next_step(int* step_ptr, float* t_out, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,179 @@
+"""ctypes binding of liblion_b200.so (the C ABI declared in include/lion_b200.h).
+
+There is no CPU or eager-PyTorch fallback: if the shared library is missing, or a call
+returns a non-zero code, an exception is raised.
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblion_b200.so")
+
+
+class LionError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+c_f = C.c_void_p   # device pointers travel as integers
+
+
+def _proto(lib):
+    i, f, sz, vp = C.c_int, C.c_float, C.c_size_t, C.c_void_p
+    P = lambda *a: list(a)
+    sig = {
+        "lion_version": ([], i),
+        "lion_last_error": ([], C.c_char_p),
+        "lion_ctx_create": (P(i, C.POINTER(vp)), i),
+        "lion_ctx_destroy": (P(vp), i),
+        "lion_ctx_last_launches": (P(vp), i),
+        "lion_ctx_arena_bytes": (P(vp), sz),
+        "lion_avg_voxelize": (P(vp, vp, vp, vp, vp, i, i, i, i, vp), i),
+        "lion_trilinear_devoxelize": (P(vp, vp, vp, vp, vp, i, i, i, i, i, vp), i),
+        "lion_furthest_point_sampling": (P(vp, vp, i, i, i, vp), i),
+        "lion_gather": (P(vp, vp, vp, i, i, i, i, vp), i),
+        "lion_ball_query": (P(vp, vp, vp, i, i, i, f, i, vp), i),
+        "lion_grouping": (P(vp, vp, vp, i, i, i, i, i, vp), i),
+        "lion_three_nn_interpolate": (P(vp, vp, vp, vp, vp, vp, i, i, i, i, vp), i),
+        "lion_voxel_coords": (P(vp, vp, vp, i, i, i, i, f, vp), i),
+        "lion_model_create": (P(vp, i, C.POINTER(i), i, C.POINTER(vp), i, C.POINTER(vp)), i),
+        "lion_model_destroy": (P(vp), i),
+        "lion_model_refresh": (P(vp), i),
+        "lion_unet_forward": (P(vp, vp, vp, vp, vp, vp, i, i, vp), i),
+        "lion_pvconv_fwd": (P(vp, vp, vp, vp, vp, i, i, vp), i),
+        "lion_sa_module_fwd": (P(vp, vp, vp, vp, vp, vp, i, i, vp), i),
+        "lion_fp_module_fwd": (P(vp, vp, vp, vp, vp, vp, vp, i, i, i, vp), i),
+        "lion_linear_attention_fwd": (P(vp, vp, vp, i, i, vp), i),
+        "lion_shared_mlp_fwd": (P(vp, vp, vp, vp, i, i, vp), i),
+        "lion_global_prior_forward": (P(vp, vp, vp, vp, vp, i, vp), i),
+        "lion_ddpm_update": (P(vp, vp, vp, vp, vp, vp, f, sz, vp, i, vp), i),
+        "lion_ddpm_set_step": (P(vp, vp, i, i, vp), i),
+        "lion_ddpm_next_step": (P(vp, vp, i, vp), i),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, name)      # AttributeError if the library does not export it
+        fn.argtypes = args
+        fn.restype = res
+    return sig
+
+
+EXPORTS = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises LionError when it is not built."""
+    global _lib, EXPORTS
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise LionError(
+                        "lion_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "or `make -C lion_b200/csrc`; there is no fallback path." % LIB_PATH)
+                l = C.CDLL(LIB_PATH)
+                EXPORTS = sorted(_proto(l).keys())
+                _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().lion_last_error()
+        raise LionError("lion_b200 %s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/int32 CUDA tensor (or None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise LionError("lion_b200 needs CUDA tensors (got %s); there is no CPU path" % t.device)
+    if not t.is_contiguous():
+        raise LionError("lion_b200 needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ctxs = {}
+
+
+def ctx(device=None):
+    """One context (scratch arena) per CUDA device."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    h = _ctxs.get(dev)
+    if h is None:
+        out = C.c_void_p()
+        check(lib().lion_ctx_create(dev, C.byref(out)), "ctx_create")
+        h = out
+        _ctxs[dev] = h
+    return h
+
+
+def last_launches(device=None):
+    return lib().lion_ctx_last_launches(ctx(device))
+
+
+KIND_UNET, KIND_PVCONV, KIND_SA, KIND_FP, KIND_ATTN, KIND_SHARED_MLP, KIND_GLOBAL_PRIOR = 1, 2, 3, 4, 5, 6, 7
+
+
+def float_bits(x):
+    import struct
+    return struct.unpack("i", struct.pack("f", float(x)))[0]
+
+
+class Model:
+    """A packed network/block living in the library.  Re-created when the parameter tensors
+    are replaced, re-packed (refresh) when they were modified in place."""
+
+    def __init__(self, kind, desc, params):
+        for p in params:
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                raise LionError("lion_b200: parameters must be contiguous fp32 CUDA tensors (move the module with "
+                                ".cuda() first); there is no CPU path")
+        self.kind = kind
+        self.device = params[0].device
+        self.params = [p.detach() for p in params]           # keep storage alive
+        self.sig = tuple(p.data_ptr() for p in self.params)
+        self.versions = tuple(p._version for p in params)
+        d = (C.c_int * len(desc))(*[int(v) for v in desc])
+        pp = (C.c_void_p * len(params))(*[p.data_ptr() for p in self.params])
+        out = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().lion_model_create(ctx(self.device), kind, d, len(desc), pp, len(params), C.byref(out)),
+                  "model_create(kind=%d)" % kind)
+        self.h = out
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) is not None and _lib is not None:
+                _lib.lion_model_destroy(self.h)
+        except Exception:
+            pass
+
+    def refresh(self):
+        with torch.cuda.device(self.device):
+            check(lib().lion_model_refresh(self.h), "model_refresh")
+
+
+def model_for(module, kind, desc, params):
+    """Cached Model of an nn.Module; tracks load_state_dict / .cuda() / in-place updates."""
+    m = module.__dict__.get("_lion_model")
+    sig = tuple(p.data_ptr() for p in params)
+    if m is None or m.sig != sig or m.kind != kind:
+        m = Model(kind, desc, params)
+        module.__dict__["_lion_model"] = m
+    else:
+        vers = tuple(p._version for p in params)
+        if vers != m.versions:
+            m.refresh()
+            m.versions = vers
+    return m

@@ -1,0 +1,138 @@
+// lion_b200 -- shared plumbing for the sm_100a kernels: error reporting, the per-context
+// bump arena (no allocation inside a forward), launch helpers, small device utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace lion {
+
+// ---------------------------------------------------------------------------------------
+// errors: every C-ABI entry returns 0 / negative code and never exits the process
+// (the reference's kernels exit(-1), third_party/pvcnn/functional/src/cuda_utils.cuh:28-37).
+// ---------------------------------------------------------------------------------------
+enum : int { LION_OK = 0, LION_ERR_CUDA = -1, LION_ERR_ARG = -2, LION_ERR_OOM = -3, LION_ERR_STATE = -4 };
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define LION_CHECK_CUDA(expr)                                                          \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      lion::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return lion::LION_ERR_CUDA;                                                      \
+    }                                                                                  \
+  } while (0)
+
+#define LION_REQUIRE(cond, ...)                                                        \
+  do {                                                                                 \
+    if (!(cond)) {                                                                     \
+      lion::set_error(__VA_ARGS__);                                                    \
+      return lion::LION_ERR_ARG;                                                       \
+    }                                                                                  \
+  } while (0)
+
+#define LION_TRY(expr)                                                                 \
+  do {                                                                                 \
+    int _r = (expr);                                                                   \
+    if (_r != 0) return _r;                                                            \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Context: device, stream of the current call, bump arena.
+// A forward is run twice: a dry pass (no launches) that measures the arena high-water mark,
+// then -- after growing the arena if needed, outside any graph capture -- the real pass.
+// ---------------------------------------------------------------------------------------
+struct Ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  char* base = nullptr;      // arena
+  size_t cap = 0;
+  size_t off = 0;
+  size_t peak = 0;
+  bool dry = false;
+  int launches = 0;          // kernels launched by the last real pass (gpu_launches evidence)
+
+  void reset() { off = 0; peak = 0; launches = 0; }
+  // 256-byte aligned sub-allocation; in dry mode returns a fake non-null pointer.
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    if (off > peak) peak = off;
+    if (dry) return (void*)(uintptr_t)(0x1000 + a);
+    return base + a;
+  }
+  template <typename T> T* alloc_n(size_t n) { return (T*)alloc(n * sizeof(T)); }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+int ctx_reserve(Ctx* c, size_t bytes);   // grow arena (sync; not capturable)
+
+// launch helper: skipped in dry mode; counts launches.
+#define LION_LAUNCH(ctx, kernel, grid, block, smem, ...)                               \
+  do {                                                                                 \
+    if (!(ctx)->dry) {                                                                 \
+      kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                 \
+      (ctx)->launches++;                                                               \
+    }                                                                                  \
+  } while (0)
+
+inline int memset_async(Ctx* c, void* p, int v, size_t bytes) {
+  if (c->dry || bytes == 0) return 0;
+  LION_CHECK_CUDA(cudaMemsetAsync(p, v, bytes, c->stream));
+  return 0;
+}
+inline int memcpy_d2d(Ctx* c, void* d, const void* s, size_t bytes) {
+  if (c->dry || bytes == 0) return 0;
+  LION_CHECK_CUDA(cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+inline int check_launch(Ctx* c, const char* what) {
+  if (c->dry) return 0;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("kernel launch failed in %s: %s", what, cudaGetErrorString(e));
+    return LION_ERR_CUDA;
+  }
+  return 0;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t cdivz(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------
+// device utilities
+// ---------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// squared distance with the FMA contraction nvcc applies to the reference's
+// dx*dx + dy*dy + dz*dz (t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t)); see oracle/point_ops.py.
+__device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+#endif
+
+}  // namespace lion

@@ -1,0 +1,71 @@
+// lion_b200 -- the per-step update of the ancestral DDPM sampler, one elementwise kernel.
+//
+// Reference: utils/diffusion_pvd.py:283-296 (noise, mean, x update) with
+// get_q_posterior_mean :475-486 and get_p_log_scales :155-168.  The reference evaluates, in
+// fp32 tensor ops on 0-dim scalars:
+//   t > 0:  mean = (1/sqrt(alpha_t)) * (x - (beta_t * eps) / sqrt(1 - abar_t))
+//           x'   = mean + exp(0.5*log(beta_t)) * z * temp
+//   t = 0:  x'   = (1/sqrt(abar_0)) * (x - sqrt(1 - abar_0) * eps)
+// The per-step scalars come from a device table row selected by a device-side step counter,
+// so the captured step graph is replayed without host-side parameter updates.
+//   table row t: { c0, c1, c2, c3 } =
+//     t > 0: { 1/sqrt(alpha_t), beta_t, sqrt(1-abar_t), exp(0.5*log beta_t) }
+//     t = 0: { 1/sqrt(abar_0),  sqrt(1-abar_0), 1, 0 }   (flagged by c3 == 0 and t == 0)
+// and the same operation order is replayed (no FMA contraction).
+#include "common.cuh"
+#include "../../include/lion_b200.h"
+
+namespace lion {
+
+__global__ void k_ddpm_update(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                              float* __restrict__ xo, const float4* __restrict__ tables, const int* __restrict__ step,
+                              float temp, size_t n, float* __restrict__ hist, int T) {
+  int t = *step;
+  float4 c = tables[t];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xv = x[i], e = eps[i];
+  float r;
+  if (t == 0) {
+    r = __fmul_rn(c.x, __fsub_rn(xv, __fmul_rn(c.y, e)));
+  } else {
+    float mean = __fmul_rn(c.x, __fsub_rn(xv, __fdiv_rn(__fmul_rn(c.y, e), c.z)));
+    r = __fadd_rn(mean, __fmul_rn(__fmul_rn(c.w, noise[i]), temp));
+  }
+  xo[i] = r;
+  if (hist) hist[(size_t)(T - 1 - t) * n + i] = r;   // trajectory slot of this step (pred_x)
+}
+
+__global__ void k_ddpm_set_step(int* step, float* t_out, int B, int t_index, int advance) {
+  int t = advance ? (*step - 1) : t_index;
+  __syncthreads();
+  if (threadIdx.x == 0) *step = t;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) t_out[b] = (float)(t + 1);
+}
+
+}  // namespace lion
+
+using namespace lion;
+
+extern "C" int lion_ddpm_update(const float* x, const float* eps, const float* noise, float* x_out, const float* tables,
+                                const int* step_ptr, float temp, size_t n, float* hist, int T, void* stream) {
+  LION_REQUIRE(x && eps && x_out && tables && step_ptr && n > 0, "lion_ddpm_update: bad arguments");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_ddpm_update, (unsigned)cdivz(n, 256), 256, 0, x, eps, noise ? noise : x, x_out, (const float4*)tables, step_ptr, temp, n, hist, T);
+  return check_launch(&c, "lion_ddpm_update");
+}
+extern "C" int lion_ddpm_set_step(int* step_ptr, float* t_out, int B, int t_index, void* stream) {
+  LION_REQUIRE(step_ptr && t_out && B > 0 && t_index >= 0, "lion_ddpm_set_step: bad arguments");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_ddpm_set_step, 1, 64, 0, step_ptr, t_out, B, t_index, 0);
+  return check_launch(&c, "lion_ddpm_set_step");
+}
+extern "C" int lion_ddpm_next_step(int* step_ptr, float* t_out, int B, void* stream) {
+  LION_REQUIRE(step_ptr && t_out && B > 0, "lion_ddpm_next_step: bad arguments");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_ddpm_set_step, 1, 64, 0, step_ptr, t_out, B, 0, 1);
+  return check_launch(&c, "lion_ddpm_next_step");
+}

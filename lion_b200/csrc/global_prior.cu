@@ -1,0 +1,188 @@
+// lion_b200 -- the global-latent prior (PriorSEDrop / PriorSEClip): a 2048-wide residual MLP
+// with squeeze-excite cells evaluated on a handful of rows (B <= 64 shapes).
+//
+// Reference: models/score_sde/resnet.py:195-218 (Prior.forward), :60-90 (ResBlockSEDrop),
+// :29-56 (ResBlockSEClip), :16-27 (SE), models/utils.py:16-31 (PositionalEmbedding).
+// The work is weight streaming (309 MB of fp32 weights per step for 0.15 GFLOP/shape), so the
+// kernel is a skinny GEMM: every weight is read once, coalesced, and applied to all B rows
+// held in shared memory; bias / ReLU / residual / SE gate are fused into the epilogue.
+#include "common.cuh"
+#include "model.cuh"
+#include "../../include/lion_b200.h"
+
+namespace lion {
+
+constexpr int GP_MAXB = 64;     // rows handled per launch
+constexpr int GP_KT = 256;      // K tile staged in shared memory
+constexpr int GP_CO_PER_WARP = 2;
+constexpr int GP_WARPS = 8;
+
+// out[b][o] = epi( sum_k W[o][k] * (x[b][k] + add[b][k]) + bias[o] )
+//   act: 0 none, 1 relu, 2 sigmoid
+//   mul: if given, result *= mul[b][o]           (SE gate application)
+//   res: if given, result += res[b][o]           (residual shortcut)
+// x/add/out/mul/res are row-major with the given strides; W is [O][K] row-major (1x1 conv weight).
+__global__ void __launch_bounds__(GP_WARPS * 32)
+k_gp_linear(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x, int x_stride,
+            const float* __restrict__ add, int add_stride, float* __restrict__ out, int out_stride,
+            const float* __restrict__ mul, int mul_stride, const float* __restrict__ res, int res_stride,
+            int B, int K, int O, int act) {
+  __shared__ float s_x[GP_MAXB / 2][GP_KT + 4];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int o0 = (blockIdx.x * GP_WARPS + wid) * GP_CO_PER_WARP;
+  float acc[GP_CO_PER_WARP][GP_MAXB / 2];      // B <= 32 per pass; two passes for B up to 64
+  for (int b0 = 0; b0 < B; b0 += GP_MAXB / 2) {
+    int nb = min(GP_MAXB / 2, B - b0);
+#pragma unroll
+    for (int c = 0; c < GP_CO_PER_WARP; ++c)
+#pragma unroll
+      for (int b = 0; b < GP_MAXB / 2; ++b) acc[c][b] = 0.0f;
+    for (int k0 = 0; k0 < K; k0 += GP_KT) {
+      int kt = min(GP_KT, K - k0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nb * kt; i += blockDim.x) {
+        int b = i / kt, k = i % kt;
+        float v = x[(size_t)(b0 + b) * x_stride + k0 + k];
+        if (add) v += add[(size_t)(b0 + b) * add_stride + k0 + k];
+        s_x[b][k] = v;
+      }
+      __syncthreads();
+      for (int k = lane; k < kt; k += 32) {
+        float w[GP_CO_PER_WARP];
+#pragma unroll
+        for (int c = 0; c < GP_CO_PER_WARP; ++c) w[c] = (o0 + c < O) ? __ldg(W + (size_t)(o0 + c) * K + k0 + k) : 0.0f;
+#pragma unroll
+        for (int b = 0; b < GP_MAXB / 2; ++b) {
+          if (b < nb) {
+            float xv = s_x[b][k];
+#pragma unroll
+            for (int c = 0; c < GP_CO_PER_WARP; ++c) acc[c][b] = fmaf(w[c], xv, acc[c][b]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < GP_CO_PER_WARP; ++c) {
+#pragma unroll
+      for (int b = 0; b < GP_MAXB / 2; ++b) {
+        if (b < nb) {                                   // warp-uniform
+          float v = warp_sum(acc[c][b]);
+          int o = o0 + c;
+          if (lane == 0 && o < O) {
+            v += bias ? bias[o] : 0.0f;
+            if (act == 1) v = fmaxf(v, 0.0f);
+            else if (act == 2) v = 1.0f / (1.0f + expf(-v));
+            if (mul) v *= mul[(size_t)(b0 + b) * mul_stride + o];
+            if (res) v += res[(size_t)(b0 + b) * res_stride + o];
+            out[(size_t)(b0 + b) * out_stride + o] = v;
+          }
+        }
+      }
+    }
+  }
+}
+
+// PositionalEmbedding (models/utils.py:16-31): fp32 frequencies exp(i * -log(1e4)/(half-1))
+__global__ void k_gp_posemb(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out,
+                            int half, float scale) {
+  int b = blockIdx.x, i = threadIdx.x;
+  if (i >= half) return;
+  float e = __fmul_rn(__fmul_rn(t[b], scale), freqs[i]);
+  out[(size_t)b * 2 * half + i] = sinf(e);
+  out[(size_t)b * 2 * half + half + i] = cosf(e);
+}
+
+struct GPLin { const float* w; const float* b; int K, O; };
+struct GlobalPriorBlk {
+  int D = 128, nf = 2048, emb = 128, ncell = 8, clip = 0, clip_dim = 512;
+  float scale = 1.0f;
+  float* d_freqs = nullptr;
+  GPLin t0, t1, cmap, in, outl;
+  struct Cell { GPLin c1, c2, se0, se2; };
+  std::vector<Cell> cells;
+};
+void global_prior_free(GlobalPriorBlk* g) { delete g; }
+
+// desc: [D, nf, emb_dim, ncell, clip, clip_dim, scale_bits]; params in state_dict order:
+//   [clip_feat_mapping.w,b] temb_layer.0.w,b temb_layer.1.w,b input_layer.w,b
+//   all_modules.k.{conv1.w,b conv2.w,b SE.fc.0.w SE.fc.2.w} output_layer.w,b
+int global_prior_build(Model* m, Cursor& cur) {
+  const std::vector<int>& d = m->desc;
+  if (d.size() < 7) { set_error("global prior descriptor: [D, nf, emb, ncell, clip, clip_dim, scale_bits]"); return LION_ERR_ARG; }
+  GlobalPriorBlk* g = new GlobalPriorBlk();
+  m->gp = g;
+  g->D = d[0]; g->nf = d[1]; g->emb = d[2]; g->ncell = d[3]; g->clip = d[4]; g->clip_dim = d[5];
+  memcpy(&g->scale, &d[6], 4);
+  auto lin = [&](GPLin& l, int K, int O, bool bias) { l.w = cur.next(); l.b = bias ? cur.next() : nullptr; l.K = K; l.O = O; };
+  if (g->clip) lin(g->cmap, g->clip_dim, g->nf, true);
+  lin(g->t0, g->emb, g->emb * 4, true);
+  lin(g->t1, g->emb * 4, g->nf, true);
+  lin(g->in, g->D, g->nf, true);
+  g->cells.resize(g->ncell);
+  for (auto& c : g->cells) {
+    lin(c.c1, g->clip ? 2 * g->nf : g->nf, g->nf, true);
+    lin(c.c2, g->nf, g->nf, true);
+    lin(c.se0, g->nf, g->nf / 8, false);
+    lin(c.se2, g->nf / 8, g->nf, false);
+  }
+  lin(g->outl, g->nf, g->D, true);
+  if (cur.bad) { set_error("global prior: parameter list too short (%d given)", cur.n); return LION_ERR_ARG; }
+  int half = g->emb / 2;
+  std::vector<float> fr(half);
+  float step = (float)(std::log(10000.0) / (half - 1));      // python float -> fp32 tensor multiply
+  for (int i = 0; i < half; ++i) fr[i] = expf((float)i * -step);
+  LION_TRY(m->dmalloc(&g->d_freqs, (size_t)half));
+  LION_CHECK_CUDA(cudaMemcpy(g->d_freqs, fr.data(), half * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int gp_linear(Ctx* c, const GPLin& l, const float* x, int xs, const float* add, int as, float* out, int os,
+                     const float* mul, int ms, const float* res, int rs, int B, int act) {
+  int grid = cdiv(l.O, GP_WARPS * GP_CO_PER_WARP);
+  LION_LAUNCH(c, k_gp_linear, grid, GP_WARPS * 32, 0, l.w, l.b, x, xs, add, as, out, os, mul, ms, res, rs, B, l.K, l.O, act);
+  return 0;
+}
+
+int global_prior_forward(Model* m, const float* x, const float* t, const float* clip, float* out, int B) {
+  GlobalPriorBlk* g = m->gp;
+  Ctx* c = m->ctx;
+  if (B > GP_MAXB) { set_error("global prior: B=%d exceeds %d rows per call", B, GP_MAXB); return LION_ERR_ARG; }
+  if (g->clip && !clip) { set_error("global prior: this network needs clip_feat"); return LION_ERR_ARG; }
+  int nf = g->nf, tw = g->clip ? 2 * nf : nf;
+  float* pe = c->alloc_n<float>((size_t)B * g->emb);
+  float* t0 = c->alloc_n<float>((size_t)B * g->emb * 4);
+  float* tadd = c->alloc_n<float>((size_t)B * tw);     // [temb | 0]: what is added to the cell input
+  float* cat = c->alloc_n<float>((size_t)B * tw);      // [h | clip-mapped] (clip variant only)
+  float* h = c->alloc_n<float>((size_t)B * nf);
+  float* h2 = c->alloc_n<float>((size_t)B * nf);
+  float* a = c->alloc_n<float>((size_t)B * nf);
+  float* bb = c->alloc_n<float>((size_t)B * nf);
+  float* s0 = c->alloc_n<float>((size_t)B * nf / 8);
+  LION_LAUNCH(c, k_gp_posemb, B, 64, 0, t, g->d_freqs, pe, g->emb / 2, g->scale);
+  // temb_layer: two 1x1 convs, no nonlinearity in between (resnet.py:181-184)
+  LION_TRY(gp_linear(c, g->t0, pe, g->emb, nullptr, 0, t0, g->emb * 4, nullptr, 0, nullptr, 0, B, 0));
+  if (g->clip) LION_TRY(memset_async(c, tadd, 0, sizeof(float) * B * tw));
+  LION_TRY(gp_linear(c, g->t1, t0, g->emb * 4, nullptr, 0, tadd, tw, nullptr, 0, nullptr, 0, B, 0));
+  // clip_feat_mapping output is concatenated behind temb (resnet.py:203-208) and reaches every
+  // cell's conv1 un-added (ResBlockSEClip.forward, resnet.py:41-46)
+  if (g->clip) LION_TRY(gp_linear(c, g->cmap, clip, g->clip_dim, nullptr, 0, cat + nf, tw, nullptr, 0, nullptr, 0, B, 0));
+  LION_TRY(gp_linear(c, g->in, x, g->D, nullptr, 0, h, nf, nullptr, 0, nullptr, 0, B, 0));
+  for (auto& cell : g->cells) {
+    // conv1(x + t [| clip]) -> ReLU -> (dropout: identity in eval) -> conv2 -> ReLU -> SE -> + x
+    if (g->clip) {
+      if (!c->dry)
+        LION_CHECK_CUDA(cudaMemcpy2DAsync(cat, tw * sizeof(float), h, nf * sizeof(float), nf * sizeof(float), B, cudaMemcpyDeviceToDevice, c->stream));
+      LION_TRY(gp_linear(c, cell.c1, cat, tw, tadd, tw, a, nf, nullptr, 0, nullptr, 0, B, 1));
+    } else {
+      LION_TRY(gp_linear(c, cell.c1, h, nf, tadd, tw, a, nf, nullptr, 0, nullptr, 0, B, 1));
+    }
+    LION_TRY(gp_linear(c, cell.c2, a, nf, nullptr, 0, bb, nf, nullptr, 0, nullptr, 0, B, 1));
+    LION_TRY(gp_linear(c, cell.se0, bb, nf, nullptr, 0, s0, nf / 8, nullptr, 0, nullptr, 0, B, 1));
+    LION_TRY(gp_linear(c, cell.se2, s0, nf / 8, nullptr, 0, h2, nf, bb, nf, h, nf, B, 2));   // sigmoid(.) * bb + h
+    float* tmp = h; h = h2; h2 = tmp;
+  }
+  LION_TRY(gp_linear(c, g->outl, h, nf, nullptr, 0, out, g->D, nullptr, 0, nullptr, 0, B, 0));
+  return check_launch(c, "global_prior_forward");
+}
+
+}  // namespace lion

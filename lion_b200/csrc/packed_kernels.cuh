@@ -1,0 +1,581 @@
+// lion_b200 -- kernels of the fused network path.
+//
+// Data layout in HBM (all fp32):
+//   PF  "packed features"  [B][G][R][4]   G = ceil(C/4) channel groups, R rows (points, or
+//                                         centre x neighbour pairs); one float4 = 4 channels of
+//                                         one row.  A latent x[B,N,4] *is* a PF with G=1.
+//   C4  coordinates        [B][N] float4  (x, y, z, 0)
+//   VG  voxel grid         [B][G][P][4]   P = (r+2)^3 zero-haloed positions,
+//                                         pos(x,y,z) = ((x+1)*(r+2) + (y+1))*(r+2) + (z+1)
+// Channel groups are the unit of concatenation (cat along C = adjacent groups) and every
+// global access is a coalesced float4 along rows.  The zero halo turns a 3x3x3 convolution
+// into 27 constant row offsets (implicit GEMM without im2col or bounds checks), which is what
+// the tcgen05 kernel (conv_tc.cu) exploits with shifted shared-memory operand descriptors.
+#pragma once
+#include "common.cuh"
+#include "point_core.cuh"
+#include "model.cuh"
+
+namespace lion {
+
+__device__ __forceinline__ float4 f4_affine(float4 v, float4 s, float4 t) {
+  return make_float4(fmaf(v.x, s.x, t.x), fmaf(v.y, s.y, t.y), fmaf(v.z, s.z, t.z), fmaf(v.w, s.w, t.w));
+}
+__device__ __forceinline__ float4 f4_swish(float4 v) {
+  return make_float4(swishf(v.x), swishf(v.y), swishf(v.z), swishf(v.w));
+}
+__device__ __forceinline__ float4 f4_max(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_fma(float4 a, float s, float4 c) {
+  return make_float4(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y), fmaf(a.z, s, c.z), fmaf(a.w, s, c.w));
+}
+
+// ------------------------------------------------------------------------------------
+// latent x[B][N][D] (D<=4 floats per point... here D==4) -> C4 coordinates
+// ------------------------------------------------------------------------------------
+__global__ void k_make_coords(const float4* __restrict__ x, float4* __restrict__ c4, int total) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float4 v = x[i];
+  v.w = 0.0f;
+  c4[i] = v;
+}
+
+// ------------------------------------------------------------------------------------
+// voxelisation prep, once per distinct (coords, r) of a forward (4 instead of 14 per step)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(VOX_THREADS)
+k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restrict__ vidx, int* __restrict__ ppos,
+           int* __restrict__ cnt, int N, int r) {
+  int b = blockIdx.x;
+  const float4* c = c4 + (size_t)b * N;
+  __shared__ float s_stat[4];
+  vox_stats_block([&](int k, float& x, float& y, float& z) { float4 v = c[k]; x = v.x; y = v.y; z = v.z; }, N, s_stat);
+  float mx = s_stat[0], my = s_stat[1], mz = s_stat[2], nrm = s_stat[3];
+  int rp = r + 2;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    float4 p = c[k];
+    float v[3];
+    vox_normalize(__fsub_rn(p.x, mx), __fsub_rn(p.y, my), __fsub_rn(p.z, mz), nrm, r, 1, 0.0f, v);
+    int xi = (int)rintf(v[0]), yi = (int)rintf(v[1]), zi = (int)rintf(v[2]);   // half-to-even, like torch.round
+    int flat = xi * r * r + yi * r + zi;
+    nc[(size_t)b * N + k] = make_float4(v[0], v[1], v[2], 0.0f);
+    vidx[(size_t)b * N + k] = flat;
+    ppos[(size_t)b * N + k] = ((xi + 1) * rp + (yi + 1)) * rp + (zi + 1);
+    atomicAdd(cnt + (size_t)b * r * r * r + flat, 1);
+  }
+}
+
+__global__ void k_vox_invcnt(const int* __restrict__ vidx, const int* __restrict__ cnt, float* __restrict__ inv,
+                             int N, int r3) {
+  int b = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int k = cnt[(size_t)b * r3 + vidx[(size_t)b * N + i]];
+  inv[(size_t)b * N + i] = 1.0f / (float)k;     // vox.cu:65
+}
+
+// scatter-mean of PF rows into a (pre-zeroed) VG; 16-byte vector atomics (sm_90+)
+__global__ void k_scatter(const float4* __restrict__ feat, const int* __restrict__ ppos, const float* __restrict__ inv,
+                          float4* __restrict__ grid, int G, int N, int P) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float4 v = feat[((size_t)b * G + g) * N + i];
+  float s = inv[(size_t)b * N + i];
+  v = f4_scale(v, s);
+  atomicAdd(grid + ((size_t)b * G + g) * P + ppos[(size_t)b * N + i], v);
+}
+
+// ------------------------------------------------------------------------------------
+// SIMT reference convolution (3x3x3 over a VG, or 1x1 over a PF with ntaps == 1).
+// Correctness scaffold and small-shape fallback; the tensor-core kernel (conv_tc.cu) has the
+// same contract:
+//   out[b][co/4][p] = bias + sum_taps sum_ci W[tap][ci][co] * in[b][ci/4][p + off[tap]]
+//   for p in [p_begin, p_end); rows whose (y,z) lie in the halo are written as zeros and
+//   excluded from the statistics;  ssum/ssq[b][co] += sum / sum of squares over valid rows.
+// ------------------------------------------------------------------------------------
+// ConvGeom: model.cuh
+
+template <int COT>
+__global__ void __launch_bounds__(128)
+k_conv_simt(const float4* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
+            float4* __restrict__ out, double* __restrict__ ssum, double* __restrict__ ssq,
+            int Gin, int cin_pad, int cout_pad, int Gout_store, ConvGeom geo) {
+  extern __shared__ float s_w[];   // [ntaps][4][COT]
+  int b = blockIdx.z;
+  int co0 = blockIdx.y * COT;
+  int p = geo.p_begin + blockIdx.x * 128 + threadIdx.x;
+  bool inrange = p < geo.p_end;
+  bool valid = inrange;
+  if (geo.rp > 0 && inrange) {
+    int z = p % geo.rp, y = (p / geo.rp) % geo.rp;
+    valid = (z >= 1 && z <= geo.rp - 2 && y >= 1 && y <= geo.rp - 2);
+  }
+  float acc[COT];
+#pragma unroll
+  for (int o = 0; o < COT; ++o) acc[o] = 0.0f;
+  const float4* inb = in + (size_t)b * Gin * geo.rows;
+  for (int g = 0; g < Gin; ++g) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < geo.ntaps * 4 * COT; i += 128) {
+      int o = i % COT, j = (i / COT) % 4, t = i / (4 * COT);
+      s_w[i] = Wt[((size_t)t * cin_pad + g * 4 + j) * cout_pad + co0 + o];
+    }
+    __syncthreads();
+    if (valid) {
+      const float4* ig = inb + (size_t)g * geo.rows + p;
+      for (int t = 0; t < geo.ntaps; ++t) {
+        float4 v = __ldg(ig + geo.off[t]);
+        const float* w = s_w + t * 4 * COT;
+#pragma unroll
+        for (int o = 0; o < COT; ++o) {
+          acc[o] = fmaf(v.x, w[o], acc[o]);
+          acc[o] = fmaf(v.y, w[COT + o], acc[o]);
+          acc[o] = fmaf(v.z, w[2 * COT + o], acc[o]);
+          acc[o] = fmaf(v.w, w[3 * COT + o], acc[o]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < COT; ++o) acc[o] = valid ? acc[o] + (bias ? bias[co0 + o] : 0.0f) : 0.0f;
+  if (inrange) {
+#pragma unroll
+    for (int q = 0; q < COT / 4; ++q) {
+      int g = co0 / 4 + q;
+      if (g < Gout_store)
+        out[((size_t)b * Gout_store + g) * geo.rows + p] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+  }
+  if (ssum) {
+    int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 0; o < COT; ++o) {
+      float s = warp_sum(acc[o]);
+      float q = warp_sum(acc[o] * acc[o]);
+      if (lane == 0) {
+        atomicAdd(ssum + (size_t)b * cout_pad + co0 + o, (double)s);
+        atomicAdd(ssq + (size_t)b * cout_pad + co0 + o, (double)q);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// AdaGN folding: GroupNorm(8, C, eps 1e-5, affine) followed by *factor + bias
+// (models/adagn.py:45-65) collapses to y = scale[b][c] * x + shift[b][c] once the (b, group)
+// statistics are known; SE3d (models/pvcnn2_ada.py:27-41) needs only the per-channel mean of
+// y, which is affine in the per-channel mean of x, so its gate folds in as well.
+//   grid = B, block = C (<= 512; C multiple of 8)
+// ------------------------------------------------------------------------------------
+__global__ void k_affine_prep(const double* __restrict__ ssum, const double* __restrict__ ssq, int stat_stride,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              const float* __restrict__ style_fb /*[B][2C] for this layer*/, int fb_stride,
+                              const float* __restrict__ se_w1 /*[C/8][C] or null*/, const float* __restrict__ se_w2 /*[C][C/8]*/,
+                              float* __restrict__ scale, float* __restrict__ shift, int C, double count) {
+  extern __shared__ float s_f[];   // [C] se input, [C/8] hidden
+  __shared__ double s_gs[8], s_gq[8];
+  int b = blockIdx.x, c = threadIdx.x;
+  int cpg = C / 8;
+  if (c < 8) { s_gs[c] = 0; s_gq[c] = 0; }
+  __syncthreads();
+  double s = ssum[(size_t)b * stat_stride + c], q = ssq[(size_t)b * stat_stride + c];
+  atomicAdd(&s_gs[c / cpg], s);
+  atomicAdd(&s_gq[c / cpg], q);
+  __syncthreads();
+  double n = count * cpg;
+  double mean = s_gs[c / cpg] / n;
+  double var = s_gq[c / cpg] / n - mean * mean;
+  if (var < 0) var = 0;
+  float rstd = (float)(1.0 / sqrt(var + 1e-5));
+  float f = style_fb[(size_t)b * fb_stride + c], bb = style_fb[(size_t)b * fb_stride + C + c];
+  float ga = gamma[c], be = beta[c];
+  float sc = rstd * ga * f;
+  float sh = (be - (float)mean * rstd * ga) * f + bb;
+  if (se_w1) {
+    int H = C / 8;
+    float* s_h = s_f + C;
+    s_f[c] = sc * (float)(s / count) + sh;     // mean over voxels of the AdaGN output
+    __syncthreads();
+    if (c < H) {
+      float a = 0.0f;
+      for (int k = 0; k < C; ++k) a = fmaf(se_w1[c * C + k], s_f[k], a);
+      s_h[c] = fmaxf(a, 0.0f);
+    }
+    __syncthreads();
+    float a = 0.0f;
+    for (int k = 0; k < H; ++k) a = fmaf(se_w2[c * H + k], s_h[k], a);
+    float gate = 1.0f / (1.0f + expf(-a));
+    sc *= gate;
+    sh *= gate;
+  }
+  scale[(size_t)b * C + c] = sc;
+  shift[(size_t)b * C + c] = sh;
+}
+
+// all AdaGN style Linears of a network in one launch: out[b][off_l + o] = W_l[o] . style[b] + bias_l[o]
+__global__ void k_style_linear(const StyleLayer* __restrict__ layers, const float* __restrict__ style, int S,
+                               float* __restrict__ out, int out_stride) {
+  extern __shared__ float s_style[];
+  StyleLayer L = layers[blockIdx.x];
+  int b = blockIdx.y;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) s_style[i] = style[(size_t)b * S + i];
+  __syncthreads();
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = wid; o < L.n_out; o += nw) {
+    float a = 0.0f;
+    for (int k = lane; k < S; k += 32) a = fmaf(L.w[(size_t)o * S + k], s_style[k], a);
+    a = warp_sum(a);
+    if (lane == 0) out[(size_t)b * out_stride + L.out_off + o] = a + L.b[o];
+  }
+}
+
+// generic small dense layer on [B][K] rows: out = act(W x + b); act 0 none, 1 leaky(0.1)
+__global__ void k_small_linear(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
+                               int x_stride, float* __restrict__ out, int out_stride, int K, int O, int act) {
+  extern __shared__ float s_x[];
+  int b = blockIdx.x;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) s_x[i] = x[(size_t)b * x_stride + i];
+  __syncthreads();
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int o = wid; o < O; o += nw) {
+    float a = 0.0f;
+    for (int k = lane; k < K; k += 32) a = fmaf(W[(size_t)o * K + k], s_x[k], a);
+    a = warp_sum(a);
+    if (lane == 0) {
+      a += bias ? bias[o] : 0.0f;
+      if (act == 1) a = a > 0.0f ? a : 0.1f * a;
+      out[(size_t)b * out_stride + o] = a;
+    }
+  }
+}
+
+// sinusoidal timestep embedding (models/latent_points_ada.py:101-115); freqs computed on the
+// host in float64 and rounded to fp32 exactly like the reference
+__global__ void k_time_sinusoid(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out,
+                                int half, float scale) {
+  int b = blockIdx.x, i = threadIdx.x;
+  if (i >= half) return;
+  float e = __fmul_rn(__fmul_rn(t[b], scale), freqs[i]);
+  out[(size_t)b * 2 * half + i] = sinf(e);
+  out[(size_t)b * 2 * half + half + i] = cosf(e);
+}
+
+// ------------------------------------------------------------------------------------
+// elementwise passes
+// ------------------------------------------------------------------------------------
+// VG: y = swish(scale*x + shift) on interior voxels, 0 on every halo position (incl. x planes)
+__global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
+                           const float* __restrict__ shift, int G, int C, int rp, int P) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  int z = p % rp, y = (p / rp) % rp, x = p / (rp * rp);
+  bool interior = z >= 1 && z <= rp - 2 && y >= 1 && y <= rp - 2 && x >= 1 && x <= rp - 2;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (interior) {
+    float4 v = in[((size_t)b * G + g) * P + p];
+    float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
+    float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
+    r = f4_swish(f4_affine(v, s, t));
+  }
+  out[((size_t)b * G + g) * P + p] = r;
+}
+
+// PF: y = swish(scale*x + shift); written at group offset g_off of a destination with Gd groups.
+// POOL > 1: max over POOL consecutive rows (neighbours of one centre) after the activation.
+template <int POOL>
+__global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
+                           const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R_out) return;
+  float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
+  float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
+  const float4* src = in + ((size_t)b * G + g) * (size_t)R_out * POOL + (size_t)i * POOL;
+  float4 r = f4_swish(f4_affine(src[0], s, t));
+#pragma unroll 4
+  for (int k = 1; k < POOL; ++k) r = f4_max(r, f4_swish(f4_affine(src[k], s, t)));
+  out[((size_t)b * Gd + g_off + g) * R_out + i] = r;
+}
+
+// copy groups of a PF into another PF at a group offset (channel concatenation)
+__global__ void k_copy_groups(const float4* __restrict__ src, float4* __restrict__ dst, int Gs, int Gd, int g_off, int R) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  dst[((size_t)b * Gd + g_off + g) * R + i] = src[((size_t)b * Gs + g) * R + i];
+}
+
+// broadcast a per-shape vector v[b][4*Gv] over all rows (the time embedding "expand")
+__global__ void k_fill_groups(const float* __restrict__ v, int v_stride, float4* __restrict__ dst, int Gd, int g_off, int R) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  dst[((size_t)b * Gd + g_off + g) * R + i] = *reinterpret_cast<const float4*>(v + (size_t)b * v_stride + g * 4);
+}
+
+// ------------------------------------------------------------------------------------
+// trilinear devoxelisation fused with: AdaGN-2 + SE affine of the raw second conv output,
+// + the point branch swish(AdaGN(conv1x1)) (PVConv.forward, models/pvcnn2_ada.py:267-277)
+// ------------------------------------------------------------------------------------
+__global__ void k_devox_fuse(const float4* __restrict__ raw, const float4* __restrict__ nc, const float* __restrict__ scale,
+                             const float* __restrict__ shift, const float4* __restrict__ rawp,
+                             const float* __restrict__ scale_p, const float* __restrict__ shift_p,
+                             float4* __restrict__ out, int G, int C, int N, int r, int P, int Gd, int g_off) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float4 c = nc[(size_t)b * N + i];
+  int rp = r + 2;
+  float xl = floorf(c.x), yl = floorf(c.y), zl = floorf(c.z);
+  float x1 = c.x - xl, y1 = c.y - yl, z1 = c.z - zl;
+  float x0 = 1.0f - x1, y0 = 1.0f - y1, z0 = 1.0f - z1;
+  float w[8] = {x0 * y0 * z0, x0 * y0 * z1, x0 * y1 * z0, x0 * y1 * z1, x1 * y0 * z0, x1 * y0 * z1, x1 * y1 * z0, x1 * y1 * z1};
+  int hx = (x1 > 0.0f) ? rp * rp : 0, hy = (y1 > 0.0f) ? rp : 0, hz = (z1 > 0.0f) ? 1 : 0;
+  int i0 = (((int)xl + 1) * rp + ((int)yl + 1)) * rp + ((int)zl + 1);
+  int idx[8] = {i0, i0 + hz, i0 + hy, i0 + hy + hz, i0 + hx, i0 + hx + hz, i0 + hx + hy, i0 + hx + hy + hz};
+  float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
+  float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
+  const float4* rg = raw + ((size_t)b * G + g) * P;
+  float4 acc = f4_scale(f4_affine(__ldg(rg + idx[0]), s, t), w[0]);
+#pragma unroll
+  for (int k = 1; k < 8; ++k) acc = f4_fma(f4_affine(__ldg(rg + idx[k]), s, t), w[k], acc);
+  if (rawp) {
+    float4 sp = *reinterpret_cast<const float4*>(scale_p + (size_t)b * C + g * 4);
+    float4 tp = *reinterpret_cast<const float4*>(shift_p + (size_t)b * C + g * 4);
+    acc = f4_add(acc, f4_swish(f4_affine(rawp[((size_t)b * G + g) * N + i], sp, tp)));
+  }
+  out[((size_t)b * Gd + g_off + g) * N + i] = acc;
+}
+
+// ------------------------------------------------------------------------------------
+// set abstraction: FPS (+ centre coordinates), ball query, grouped input assembly
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FPS_THREADS)
+k_fps_c4(const float4* __restrict__ c4, int* __restrict__ idx, float4* __restrict__ centers, int N, int M) {
+  int b = blockIdx.x;
+  const float4* c = c4 + (size_t)b * N;
+  int* io = idx + (size_t)b * M;
+  float4* co = centers + (size_t)b * M;
+  fps_block_emit([&](int k, float& x, float& y, float& z) { float4 v = c[k]; x = v.x; y = v.y; z = v.z; },
+                 [&](int j, int k, float x, float y, float z) { io[j] = k; co[j] = make_float4(x, y, z, 0.0f); }, N, M);
+}
+
+__global__ void k_ball_query_c4(const float4* __restrict__ centers, const float4* __restrict__ points, int* __restrict__ out,
+                                int N, int M, float r2, int K) {
+  int b = blockIdx.y;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= M) return;
+  float4 ce = centers[(size_t)b * M + warp];
+  const float4* pt = points + (size_t)b * N;
+  ball_query_warp([&](int k, float& x, float& y, float& z) { float4 v = __ldg(pt + k); x = v.x; y = v.y; z = v.z; },
+                  ce.x, ce.y, ce.z, r2, N, K, out + ((size_t)b * M + warp) * K);
+}
+
+// grouped SA input: group 0 = neighbour xyz - centre xyz (BallQuery.forward, pvcnn2_ada.py:104-113),
+// groups 1..Gf = neighbour features.  rows = M*U pairs.
+__global__ void k_group_gather(const float4* __restrict__ feat, const float4* __restrict__ points,
+                               const float4* __restrict__ centers, const int* __restrict__ nidx, float4* __restrict__ out,
+                               int Gf, int N, int M, int U) {
+  int b = blockIdx.z, g = blockIdx.y;    // g == 0: coordinates; g >= 1: features group g-1
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int MU = M * U;
+  if (i >= MU) return;
+  int k = nidx[(size_t)b * MU + i];
+  float4 v;
+  if (g == 0) {
+    float4 p = points[(size_t)b * N + k], c = centers[(size_t)b * M + i / U];
+    v = make_float4(p.x - c.x, p.y - c.y, p.z - c.z, 0.0f);
+  } else {
+    v = feat[((size_t)b * Gf + (g - 1)) * N + k];
+  }
+  out[((size_t)b * (Gf + 1) + g) * MU + i] = v;
+}
+
+// ------------------------------------------------------------------------------------
+// feature propagation: 3-NN search + interpolation into a destination PF at a group offset
+// ------------------------------------------------------------------------------------
+__global__ void k_three_nn_c4(const float4* __restrict__ points, const float4* __restrict__ centers, int* __restrict__ idx,
+                              float* __restrict__ wgt, int N, int M) {
+  int b = blockIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float4 s_c4[];
+  const float4* ce = centers + (size_t)b * M;
+  float4 u = make_float4(0, 0, 0, 0);
+  if (j < N) u = points[(size_t)b * N + j];
+  ThreeNN st;
+  st.init();
+  const int TILE = 1024;
+  for (int k0 = 0; k0 < M; k0 += TILE) {
+    int n = min(TILE, M - k0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) s_c4[t] = ce[k0 + t];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+      float4 c = s_c4[k];
+      st.push(sqdist_ref(u.x - c.x, u.y - c.y, u.z - c.z), k0 + k);
+    }
+  }
+  if (j >= N) return;
+  float w0, w1, w2;
+  st.weights(w0, w1, w2);
+  size_t o = ((size_t)b * N + j) * 3;
+  idx[o] = st.i0; idx[o + 1] = st.i1; idx[o + 2] = st.i2;
+  wgt[o] = w0; wgt[o + 1] = w1; wgt[o + 2] = w2;
+}
+
+__global__ void k_interp_rows(const float4* __restrict__ cf, const int* __restrict__ idx, const float* __restrict__ wgt,
+                              float4* __restrict__ dst, int Gs, int M, int N, int Gd, int g_off) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  size_t o = ((size_t)b * N + j) * 3;
+  const float4* f = cf + ((size_t)b * Gs + g) * M;
+  float4 a = f4_scale(f[idx[o]], wgt[o]);                      // f[i1]*w1 + f[i2]*w2 + f[i3]*w3
+  a = f4_fma(f[idx[o + 1]], wgt[o + 1], a);
+  a = f4_fma(f[idx[o + 2]], wgt[o + 2], a);
+  dst[((size_t)b * Gd + g_off + g) * N + j] = a;
+}
+
+// ------------------------------------------------------------------------------------
+// linear attention (models/pvcnn2_ada.py:54-71).  qkv PF has 3*H*32 channels ordered
+// (qkv, head, c).  ctx[b][h][d][e] = sum_n softmax_n(k[d])[n] * v[e][n];  out[e][n] = sum_d ctx[d][e] q[d][n]
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_attn_ctx(const float4* __restrict__ qkv, float* __restrict__ ctx, int H, int N) {
+  int h = blockIdx.x, b = blockIdx.y;
+  int Gq = 3 * H * 8;                       // groups in qkv
+  const float4* kb = qkv + ((size_t)b * Gq + (H + h) * 8) * N;       // k: 8 groups x N
+  const float4* vb = qkv + ((size_t)b * Gq + (2 * H + h) * 8) * N;   // v
+  __shared__ float s_max[32], s_sum[32];
+  __shared__ float s_k[32][65], s_v[32][65];
+  int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // pass 1: per-channel max and sum(exp) over N; warp w handles channels 4w..4w+3 (one group)
+  {
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int n = lane; n < N; n += 32) {
+      float4 v = kb[(size_t)wid * N + n];
+      m[0] = fmaxf(m[0], v.x); m[1] = fmaxf(m[1], v.y); m[2] = fmaxf(m[2], v.z); m[3] = fmaxf(m[3], v.w);
+    }
+    float s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m[j] = warp_max(m[j]);
+    for (int n = lane; n < N; n += 32) {
+      float4 v = kb[(size_t)wid * N + n];
+      s[0] += expf(v.x - m[0]); s[1] += expf(v.y - m[1]); s[2] += expf(v.z - m[2]); s[3] += expf(v.w - m[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = warp_sum(s[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s_max[wid * 4 + j] = m[j]; s_sum[wid * 4 + j] = s[j]; }
+    }
+  }
+  __syncthreads();
+  // pass 2: thread (d = tid/8, e in 4*(tid%8)..+3) accumulates over tiles of 64 points
+  int d = tid >> 3, e0 = (tid & 7) * 4;
+  float acc[4] = {0, 0, 0, 0};
+  for (int n0 = 0; n0 < N; n0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 8 * 64; i += 256) {
+      int g = i / 64, n = i % 64;
+      float4 kv = make_float4(0, 0, 0, 0), vv = kv;
+      bool ok = n0 + n < N;
+      if (ok) { kv = kb[(size_t)g * N + n0 + n]; vv = vb[(size_t)g * N + n0 + n]; }
+      s_k[g * 4 + 0][n] = ok ? expf(kv.x - s_max[g * 4 + 0]) : 0.f;
+      s_k[g * 4 + 1][n] = ok ? expf(kv.y - s_max[g * 4 + 1]) : 0.f;
+      s_k[g * 4 + 2][n] = ok ? expf(kv.z - s_max[g * 4 + 2]) : 0.f;
+      s_k[g * 4 + 3][n] = ok ? expf(kv.w - s_max[g * 4 + 3]) : 0.f;
+      s_v[g * 4 + 0][n] = vv.x; s_v[g * 4 + 1][n] = vv.y; s_v[g * 4 + 2][n] = vv.z; s_v[g * 4 + 3][n] = vv.w;
+    }
+    __syncthreads();
+    for (int n = 0; n < 64; ++n) {
+      float kk = s_k[d][n];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(kk, s_v[e0 + j][n], acc[j]);
+    }
+  }
+  float inv = 1.0f / s_sum[d];
+  float* o = ctx + (((size_t)b * H + h) * 32 + d) * 32 + e0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = acc[j] * inv;
+}
+
+__global__ void __launch_bounds__(128)
+k_attn_apply(const float4* __restrict__ qkv, const float* __restrict__ ctx, float4* __restrict__ out, int H, int N) {
+  int h = blockIdx.y, b = blockIdx.z;
+  __shared__ float s_ctx[32 * 32];
+  for (int i = threadIdx.x; i < 1024; i += 128) s_ctx[i] = ctx[((size_t)b * H + h) * 1024 + i];
+  __syncthreads();
+  int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= N) return;
+  int Gq = 3 * H * 8;
+  const float4* qb = qkv + ((size_t)b * Gq + h * 8) * N;
+  float acc[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) acc[e] = 0.0f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float4 q = qb[(size_t)g * N + n];
+    float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* c = s_ctx + (g * 4 + j) * 32;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) acc[e] = fmaf(c[e], qq[j], acc[e]);
+    }
+  }
+  float4* ob = out + ((size_t)b * (H * 8) + h * 8) * N;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) ob[(size_t)g * N + n] = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+}
+
+// ------------------------------------------------------------------------------------
+// layout conversion at the module-level C ABI: [B][C][R] channel-major <-> PF
+// ------------------------------------------------------------------------------------
+__global__ void k_cm_to_pf(const float* __restrict__ src, float4* __restrict__ dst, int C, int G, int R) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = g * 4 + j;
+    v[j] = c < C ? src[((size_t)b * C + c) * R + i] : 0.0f;
+  }
+  dst[((size_t)b * G + g) * R + i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+__global__ void k_pf_to_cm(const float4* __restrict__ src, float* __restrict__ dst, int C, int G, int R) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  float4 v = src[((size_t)b * G + g) * R + i];
+  float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = g * 4 + j;
+    if (c < C) dst[((size_t)b * C + c) * R + i] = vv[j];
+  }
+}
+__global__ void k_cm_to_c4(const float* __restrict__ src, float4* __restrict__ dst, int N) {
+  int b = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float* s = src + (size_t)b * 3 * N;
+  dst[(size_t)b * N + i] = make_float4(s[i], s[i + N], s[i + 2 * N], 0.0f);
+}
+__global__ void k_c4_to_cm(const float4* __restrict__ src, float* __restrict__ dst, int N) {
+  int b = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float4 v = src[(size_t)b * N + i];
+  float* d = dst + (size_t)b * 3 * N;
+  d[i] = v.x; d[i + N] = v.y; d[i + 2 * N] = v.z;
+}
+
+}  // namespace lion

@@ -1,0 +1,247 @@
+// lion_b200 -- device-side cores of the index-producing operators, shared by the
+// reference-layout entry points (point_ops.cu) and the fused network path (unet.cu) so that
+// both produce bit-identical indices.  Each core is templated on a coordinate loader
+// `load(k, x, y, z)` so it works on [3,N] planes and on packed float4 points alike.
+//
+// Semantics follow the reference kernels exactly (citations into
+// /root/reference/third_party/pvcnn/functional/src/); only the parallel decomposition differs.
+#pragma once
+#include "common.cuh"
+
+namespace lion {
+
+// ---------------------------------------------------------------------------------------
+// trilinear corners (interpolate/trilinear_devox.cu:38-76): floor / frac, the hi-corner
+// offset is 0 when frac == 0, corner order 000,001,010,011,100,101,110,111 (x major).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void trilinear_corners(float x, float y, float z, int r, int idx[8], float w[8]) {
+  float xl = floorf(x), yl = floorf(y), zl = floorf(z);
+  float x1 = x - xl, y1 = y - yl, z1 = z - zl;
+  float x0 = 1.0f - x1, y0 = 1.0f - y1, z0 = 1.0f - z1;
+  w[0] = x0 * y0 * z0; w[1] = x0 * y0 * z1; w[2] = x0 * y1 * z0; w[3] = x0 * y1 * z1;
+  w[4] = x1 * y0 * z0; w[5] = x1 * y0 * z1; w[6] = x1 * y1 * z0; w[7] = x1 * y1 * z1;
+  int hx = (x1 > 0.0f) ? r * r : 0;
+  int hy = (y1 > 0.0f) ? r : 0;
+  int hz = (z1 > 0.0f) ? 1 : 0;
+  int i0 = (int)xl * r * r + (int)yl * r + (int)zl;
+  idx[0] = i0;           idx[1] = i0 + hz;
+  idx[2] = i0 + hy;      idx[3] = i0 + hy + hz;
+  idx[4] = i0 + hx;      idx[5] = i0 + hx + hz;
+  idx[6] = i0 + hx + hy; idx[7] = i0 + hx + hy + hz;
+}
+
+// ---------------------------------------------------------------------------------------
+// Voxelization.forward (models/pvcnn2_ada.py:173-188): statistics + normalisation.
+// Every fp32 operation is a separate torch op in the reference, so nothing may be contracted
+// into an FMA here: explicit _rn intrinsics.
+// ---------------------------------------------------------------------------------------
+constexpr int VOX_THREADS = 256;
+
+// s_out[0..2] = mean over points (double accumulation, rounded once), s_out[3] = max_k ||c_k - mean||_2
+template <typename Load>
+__device__ __forceinline__ void vox_stats_block(Load load, int N, float* s_out) {
+  __shared__ double s_red[3][VOX_THREADS / 32];
+  __shared__ float s_max[VOX_THREADS / 32];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double sx = 0, sy = 0, sz = 0;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    float x, y, z;
+    load(k, x, y, z);
+    sx += x; sy += y; sz += z;
+  }
+  sx = warp_sum_d(sx); sy = warp_sum_d(sy); sz = warp_sum_d(sz);
+  if (lane == 0) { s_red[0][wid] = sx; s_red[1][wid] = sy; s_red[2][wid] = sz; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[threadIdx.x][w];
+    s_out[threadIdx.x] = (float)(t / (double)N);
+  }
+  __syncthreads();
+  float mx = s_out[0], my = s_out[1], mz = s_out[2];
+  float best = 0.0f;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    float x, y, z;
+    load(k, x, y, z);
+    float dx = __fsub_rn(x, mx), dy = __fsub_rn(y, my), dz = __fsub_rn(z, mz);
+    float n2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    best = fmaxf(best, __fsqrt_rn(n2));
+  }
+  best = warp_max(best);
+  if (lane == 0) s_max[wid] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, s_max[w]);
+    s_out[3] = t;
+  }
+  __syncthreads();
+}
+
+// (dx,dy,dz) already centred.  v in voxel units, clamped to [0, r-1] (not yet rounded).
+__device__ __forceinline__ void vox_normalize(float dx, float dy, float dz, float nrm, int r, int normalize,
+                                              float eps, float v[3]) {
+  float d[3] = {dx, dy, dz};
+  float rf = (float)r;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float t;
+    if (normalize) {
+      float den = __fadd_rn(__fmul_rn(nrm, 2.0f), eps);
+      t = __fadd_rn(__fdiv_rn(d[a], den), 0.5f);
+    } else {
+      t = __fdiv_rn(__fadd_rn(d[a], 1.0f), 2.0f);
+    }
+    t = __fmul_rn(t, rf);
+    v[a] = fminf(fmaxf(t, 0.0f), rf - 1.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// furthest point sampling (sampling/sampling.cu:86-167).
+// One CTA per shape; thread t owns points t, t+T, t+2T, ... (T = 512, the reference's block
+// size, so the reference's tie-breaking -- max distance, then lowest thread, then lowest
+// index within the thread -- is reproduced by construction), coordinates and running
+// min-distances live in registers, the arg-max is a shuffle butterfly + one shared-memory
+// exchange with a single __syncthreads per round (the reference: 9 barriers + global-memory
+// distance traffic per round).
+// ---------------------------------------------------------------------------------------
+constexpr int FPS_THREADS = 512;
+constexpr int FPS_MAX_PER_THREAD = 8;   // N <= 4096
+
+struct FpsBest {
+  float v; int tid; int k;
+};
+__device__ __forceinline__ FpsBest fps_better(FpsBest a, FpsBest b) {
+  // keep a unless b is strictly larger, or equal with a lower owning thread (lower slot wins ties)
+  bool take_b = (b.v > a.v) || (b.v == a.v && b.tid < a.tid);
+  return take_b ? b : a;
+}
+__device__ __forceinline__ FpsBest fps_shfl_xor(FpsBest a, int o) {
+  FpsBest b;
+  b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+  b.tid = __shfl_xor_sync(0xffffffffu, a.tid, o);
+  b.k = __shfl_xor_sync(0xffffffffu, a.k, o);
+  return b;
+}
+
+// Emit(j, k, x, y, z) is called by one thread for every selected point j=0..M-1.
+template <typename Load, typename Emit>
+__device__ __forceinline__ void fps_block_emit(Load load, Emit emit, int N, int M) {
+  constexpr int NW = FPS_THREADS / 32;
+  __shared__ float s_v[2][NW];
+  __shared__ int s_t[2][NW];
+  __shared__ int s_k[2][NW];
+  __shared__ float s_xyz[2][NW][3];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float px[FPS_MAX_PER_THREAD], py[FPS_MAX_PER_THREAD], pz[FPS_MAX_PER_THREAD], pd[FPS_MAX_PER_THREAD];
+#pragma unroll
+  for (int i = 0; i < FPS_MAX_PER_THREAD; ++i) {
+    int k = tid + i * FPS_THREADS;
+    px[i] = py[i] = pz[i] = 0.0f;
+    pd[i] = 1e38f;                         // sampling.cpp:54
+    if (k < N) load(k, px[i], py[i], pz[i]);
+  }
+  float lx, ly, lz;
+  load(0, lx, ly, lz);                     // first pick is point 0 (sampling.cu:104-106)
+  if (tid == 0) emit(0, 0, lx, ly, lz);
+  for (int j = 1; j < M; ++j) {
+    FpsBest b;
+    b.v = -1.0f; b.tid = tid; b.k = 0;     // threads without points never win (sampling.cu:117-118)
+    float bx = 0, by = 0, bz = 0;
+#pragma unroll
+    for (int i = 0; i < FPS_MAX_PER_THREAD; ++i) {
+      int k = tid + i * FPS_THREADS;
+      if (k < N) {
+        float d = sqdist_ref(px[i] - lx, py[i] - ly, pz[i] - lz);
+        float d2 = fminf(d, pd[i]);
+        pd[i] = d2;
+        if (d2 > b.v) { b.v = d2; b.k = k; bx = px[i]; by = py[i]; bz = pz[i]; }
+      }
+    }
+    FpsBest w = b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = fps_better(w, fps_shfl_xor(w, o));
+    int buf = j & 1;
+    if (w.tid == tid) {                    // exactly one lane per warp owns the warp's winner
+      s_v[buf][wid] = w.v; s_t[buf][wid] = w.tid; s_k[buf][wid] = w.k;
+      s_xyz[buf][wid][0] = bx; s_xyz[buf][wid][1] = by; s_xyz[buf][wid][2] = bz;
+    }
+    __syncthreads();
+    FpsBest g;
+    if (lane < NW) { g.v = s_v[buf][lane]; g.tid = s_t[buf][lane]; g.k = s_k[buf][lane]; }
+    else { g.v = -2.0f; g.tid = 1 << 30; g.k = 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) g = fps_better(g, fps_shfl_xor(g, o));
+    int ww = g.tid >> 5;
+    lx = s_xyz[buf][ww][0]; ly = s_xyz[buf][ww][1]; lz = s_xyz[buf][ww][2];
+    if (tid == 0) emit(j, g.k, lx, ly, lz);
+  }
+}
+
+template <typename Load>
+__device__ __forceinline__ void fps_block(Load load, int* idx_out, int N, int M) {
+  fps_block_emit(load, [&](int j, int k, float, float, float) { idx_out[j] = k; }, N, M);
+}
+
+// ---------------------------------------------------------------------------------------
+// ball query (ball_query/ball_query.cu:19-50): first K point indices in ascending order with
+// d^2 < r^2 (strict), padded with the first hit, all zeros when there is no hit.
+// One warp per centre: 32 candidates per step, ballot + prefix popcount keeps the order.
+// ---------------------------------------------------------------------------------------
+template <typename Load>
+__device__ __forceinline__ void ball_query_warp(Load load, float cx, float cy, float cz, float r2, int N, int K,
+                                                int* out) {
+  int lane = threadIdx.x & 31;
+  int cnt = 0, first = 0;
+  for (int k0 = 0; k0 < N && cnt < K; k0 += 32) {
+    int k = k0 + lane;
+    bool hit = false;
+    if (k < N) {
+      float x, y, z;
+      load(k, x, y, z);
+      hit = sqdist_ref(cx - x, cy - y, cz - z) < r2;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {
+      if (cnt == 0) first = k0 + __ffs(m) - 1;
+      int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (hit && pos < K) out[pos] = k;
+      cnt += __popc(m);
+    }
+  }
+  if (cnt > K) cnt = K;
+  if (lane >= cnt && lane < K) out[lane] = (cnt > 0) ? first : 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// 3 nearest centres (interpolate/neighbor_interpolate.cu:36-73): strict '<' cascade over
+// centres in index order; weights from distances clamped to [1e-10, 1e10].
+// ---------------------------------------------------------------------------------------
+struct ThreeNN {
+  float b0, b1, b2;
+  int i0, i1, i2;
+  __device__ __forceinline__ void init() {
+    b0 = b1 = b2 = __int_as_float(0x7f800000);   // the reference starts at 1e40 (double): > any float
+    i0 = i1 = i2 = 0;
+  }
+  __device__ __forceinline__ void push(float d, int k) {
+    if (d < b2) {
+      b2 = d; i2 = k;
+      if (d < b1) {
+        b2 = b1; i2 = i1; b1 = d; i1 = k;
+        if (d < b0) { b1 = b0; i1 = i0; b0 = d; i0 = k; }
+      }
+    }
+  }
+  __device__ __forceinline__ void weights(float& w0, float& w1, float& w2) const {
+    float c0 = fmaxf(fminf(1e10f, b0), 1e-10f);
+    float c1 = fmaxf(fminf(1e10f, b1), 1e-10f);
+    float c2 = fmaxf(fminf(1e10f, b2), 1e-10f);
+    float d0d1 = __fmul_rn(c0, c1), d0d2 = __fmul_rn(c0, c2), d1d2 = __fmul_rn(c1, c2);
+    float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(d0d1, d0d2), d1d2));
+    w0 = __fmul_rn(d1d2, inv); w1 = __fmul_rn(d0d2, inv); w2 = __fmul_rn(d0d1, inv);
+  }
+};
+
+}  // namespace lion

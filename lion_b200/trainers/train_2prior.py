@@ -1,0 +1,54 @@
+"""Sampling entry point of the two-prior trainer -- mirror of the reference's
+trainers/train_2prior.py:49-127 (`generate_samples_vada_2prior`, same signature and 5-tuple
+return).  Training (`Trainer.train_iter`, optimisers, resume, visualisation) is out of scope.
+"""
+from timeit import default_timer as timer
+
+import torch
+
+from ..utils.diffusion_pvd import DiffusionDiscretized
+
+
+@torch.no_grad()
+def generate_samples_vada_2prior(shape, dae, diffusion, vae, num_samples, enable_autocast, ode_eps=0.00001,
+                                 ode_solver_tol=1e-5, ode_sample=False, prior_var=1.0, temp=1.0, vae_temp=1.0, noise=None,
+                                 need_denoise=False, ddim_step=0, clip_feat=None, cls_emb=None, ddim_skip_type='uniform',
+                                 ddim_kappa=1.0):
+    output = {}
+    if ode_sample == 1:
+        raise NotImplementedError("lion_b200: ODE sampling is off in every shipped config (sde.ode_sample=0)")
+    assert isinstance(diffusion, DiffusionDiscretized), 'Regular sampling requires disc. diffusion!'
+    assert noise is None, 'Noise is not used in ancestral sampling.'
+    assert cls_emb is None, 'lion_b200: class-conditional sampling (cls_emb) is not part of the shipped prior configs'
+    nfe = diffusion._diffusion_steps
+    time_ode_solve = 999.999
+    start = timer()
+    condition_input = None
+    all_eps = []
+    eps_list = None
+    for i in range(len(dae)):
+        if ddim_step > 0:
+            eps, eps_list = diffusion.run_ddim(dae[i], num_samples, shape[i], temp, enable_autocast, is_image=False,
+                                               prior_var=prior_var, ddim_step=ddim_step, condition_input=condition_input,
+                                               clip_feat=clip_feat, skip_type=ddim_skip_type, kappa=ddim_kappa)
+        else:
+            eps, eps_list = diffusion.run_denoising_diffusion(dae[i], num_samples, shape[i], temp, enable_autocast,
+                                                              is_image=False, prior_var=prior_var,
+                                                              condition_input=condition_input, clip_feat=clip_feat)
+        condition_input = eps
+        if i == 0:
+            condition_input = vae.global2style(condition_input)
+        all_eps.append(eps)
+        output['sampled_eps'] = eps
+    eps = vae.compose_eps(all_eps)
+    output['eps_list'] = eps_list
+    output['print/sample_mean_global'] = eps.view(num_samples, -1).mean(-1).mean()
+    output['print/sample_var_global'] = eps.view(num_samples, -1).var(-1).mean()
+    decomposed_eps = vae.decompose_eps(eps)
+    image = vae.sample(num_samples=num_samples, decomposed_eps=decomposed_eps, cls_emb=cls_emb)
+    end = timer()
+    sampling_time = end - start
+    nfe_torch = torch.tensor(nfe * 1.0, device='cuda')
+    sampling_time_torch = torch.tensor(sampling_time * 1.0, device='cuda')
+    time_ode_solve_torch = torch.tensor(time_ode_solve * 1.0, device='cuda')
+    return image, nfe_torch, time_ode_solve_torch, sampling_time_torch, output

@@ -1,0 +1,84 @@
+"""Module-level parity: each block of pvcnn2_ada through the C ABI against the CPU oracle,
+on the reference's channel-major layouts, with key-seeded synthetic weights."""
+import pytest
+import torch
+
+from oracle import net as ON
+from tests.synth import synth_state_dict
+from tests.util import assert_close, gen
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-3   # convolutions run in TF32 on the tensor cores (the reference's cuDNN path does too)
+
+
+def _cfg():
+    from lion_b200.config import default_prior_cfg
+    return default_prior_cfg()
+
+
+def _load(mod, seed):
+    sd = synth_state_dict({k: list(v.shape) for k, v in mod.state_dict().items()}, seed)
+    mod.load_state_dict(sd)
+    return mod.cuda().eval(), sd
+
+
+@pytest.mark.parametrize("cin,outs,R", [(35, [32, 64], 4096), (320, [128, 128], 300), (193, [128, 128, 64], 2048), (64, [128], 777)])
+def test_shared_mlp(cin, outs, R):
+    from lion_b200.models.pvcnn2_ada import SharedMLP
+    m, sd = _load(SharedMLP(cin, outs, dim=1, cfg=_cfg()), 21)
+    x, style = gen(1, 2, cin, R), gen(2, 2, 128)
+    out = m(x.cuda(), style.cuda())
+    assert_close(out, ON.shared_mlp(sd, "", x, style, len(outs)), TOL, "SharedMLP")
+
+
+@pytest.mark.parametrize("C,heads,N", [(64, 4, 1024), (128, 8, 16), (64, 4, 100)])
+def test_linear_attention(C, heads, N):
+    from lion_b200.models.pvcnn2_ada import LinearAttention
+    m, sd = _load(LinearAttention(C, heads), 22)
+    x = gen(3, 2, C, N)
+    assert_close(m(x.cuda()), ON.linear_attention(sd, "", x, heads), TOL, "LinearAttention")
+
+
+@pytest.mark.parametrize("cin,cout,r,N,attn", [(4, 32, 32, 2048, False), (128, 64, 16, 1024, True), (192, 128, 8, 256, False),
+                                               (128, 128, 8, 64, False), (64, 64, 32, 2048, False)])
+def test_pvconv(cin, cout, r, N, attn):
+    from lion_b200.models.pvcnn2_ada import PVConv
+    m, sd = _load(PVConv(cin, cout, 3, r, with_se=True, attention=attn, cfg=_cfg()), 23)
+    B = 2
+    feats, coords, style = gen(4, B, cin, N), gen(5, B, 3, N, scale=0.4), gen(6, B, 128)
+    out, *_ = m((feats.cuda(), coords.cuda(), None, style.cuda()))
+    blk = dict(kind="pvconv", cin=cin, cout=cout, r=r, attn=attn)
+    assert_close(out, ON.pvconv(sd, "", blk, feats, coords, style), TOL, "PVConv")
+
+
+@pytest.mark.parametrize("cfeat,m,radius,outs,N", [(32, 1024, 0.1, [32, 64], 2048), (64, 256, 0.2, [64, 128], 1024),
+                                                   (192, 16, 0.8, [128, 128, 128], 64)])
+def test_sa_module(cfeat, m, radius, outs, N):
+    from lion_b200.models.pvcnn2_ada import PointNetSAModule
+    mod, sd = _load(PointNetSAModule(m, radius, 32, cfeat, outs, cfg=_cfg()), 24)
+    B = 2
+    feats, coords, style = gen(7, B, cfeat, N), gen(8, B, 3, N, scale=0.3), gen(9, B, 128)
+    out, centers, _, _ = mod((feats.cuda(), coords.cuda(), None, style.cuda()))
+    blk = dict(kind="sa", m=m, radius=radius, k=32, cin=cfeat + 3, mlp=outs)
+    o_feat, o_centers, _ = ON.sa_module(sd, "", blk, feats, coords, None, style)
+    assert torch.equal(centers.cpu(), o_centers)
+    assert_close(out, o_feat, TOL, "SA module")
+
+
+@pytest.mark.parametrize("cc,cp,outs,N,M", [(192, 128, [128, 128], 64, 16), (192, 1, [128, 128, 64], 2048, 1024), (128, 0, [64], 256, 64)])
+def test_fp_module(cc, cp, outs, N, M):
+    from lion_b200.models.pvcnn2_ada import PointNetFPModule
+    mod, sd = _load(PointNetFPModule(cc + cp, outs, cfg=_cfg()), 25)
+    B = 2
+    pc = gen(10, B, 3, N, scale=0.3)
+    cctr = pc[:, :, :M].contiguous()
+    cf, style = gen(11, B, cc, M), gen(12, B, 128)
+    pf = gen(13, B, cp, N) if cp else None
+    if pf is not None:
+        out, *_ = mod((pc.cuda(), cctr.cuda(), cf.cuda(), pf.cuda(), None, style.cuda()))
+    else:
+        out, *_ = mod((pc.cuda(), cctr.cuda(), cf.cuda(), None, style.cuda()))
+    blk = dict(kind="fp", cin=cc + cp, mlp=outs)
+    o, _ = ON.fp_module(sd, "", blk, pc, cctr, cf, pf, None, style)
+    assert_close(out, o, TOL, "FP module")

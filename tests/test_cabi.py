@@ -1,0 +1,63 @@
+"""CPU-side checks of the C-ABI boundary: the library builds/loads and exports every symbol
+declared in include/lion_b200.h (no compute calls without a GPU)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "lion_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lion_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lion_b200 import _lib
+    lib = _lib.lib()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "liblion_b200.so does not export %s" % n
+    assert set(names) == set(_lib.EXPORTS), (set(names) ^ set(_lib.EXPORTS))
+    assert lib.lion_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA tensors -- never fall back."""
+    import torch
+    from lion_b200 import _lib
+    from lion_b200.third_party.pvcnn import functional as F
+    with pytest.raises(_lib.LionError):
+        F.ball_query(torch.zeros(1, 3, 4), torch.zeros(1, 3, 8), 0.1, 4)
+
+
+def test_product_path_does_not_import_oracle():
+    bad = []
+    for dp, _, fs in os.walk(os.path.join(ROOT, "lion_b200")):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                s = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|from\s+\.+oracle", s, flags=re.M):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_state_dict_key_contract():
+    """Module trees expose exactly the reference's parameter names and shapes (SURVEY.md App. E;
+    tests/golden/keys.json was dumped from the reference modules)."""
+    import json
+    from lion_b200.config import default_prior_cfg
+    from lion_b200.models.latent_points_ada_localprior import PVCNN2Prior
+    from lion_b200.models.score_sde.resnet import PriorSEDrop, PriorSEClip
+    from lion_b200.models.vae_adain import Model
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "keys.json")))
+    shp = lambda m: {k: list(v.shape) for k, v in m.state_dict().items()}
+    cfg, cc = default_prior_cfg(), default_prior_cfg(clip=True)
+    assert shp(PVCNN2Prior(cfg.sde, 1, cfg)) == keys["prior"]
+    assert shp(PVCNN2Prior(cc.sde, 1, cc)) == keys["prior_clip"]
+    assert shp(PriorSEDrop(cfg.sde, 128, cfg)) == keys["global"]
+    assert shp(PriorSEClip(cc.sde, 128, cc)) == keys["global_clip"]
+    assert shp(Model(cfg)) == keys["vae_decoder"]
