@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- shapes/sec of LION's sampling hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One bench "step" = one full pass of the hot path over one batch: `generate_samples_vada_2prior`
+= 1000 denoising steps of the global prior + 1000 of the latent-point prior (PVCNN2-AdaGN)
++ one VAE-decoder pass, for `--batch` shapes of 2048 latent points per GPU (BASELINE.json
+configs[1]; at N > 1 every rank samples its own 32 shapes -> weak scaling, and the finished
+point clouds are all-gathered once per pass, the path's only collective).  Weights are
+key-seeded synthetic tensors (no checkpoints offline), data is synthetic noise.
+
+Printed JSON line (rank 0): the base contract plus
+  roofline      the dominant kernel (3x3x3 voxel convolution 64->64 @ 32^3, tcgen05 TF32) timed
+                alone with CUDA events via lion_bench_conv; achieved = algorithmic FLOPs / time,
+                peak = MEASURED_PEAKS.json bf16 burst / 2 (TF32 runs at half the bf16 rate)
+  cpu_baseline  the CPU oracle (oracle/) on the host cores, bounded sample, extrapolated
+  e2e           the same pass with all noise supplied from pinned HOST memory (H2D inside the
+                timed region) and the point clouds copied back to pinned host memory
+--impl reference times the reference's own CPU implementation of the path (the oracle port,
+restated from the reference and pinned to its goldens) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_STEPS = 1000
+N_POINTS = 2048
+GFLOP_PER_SHAPE = 59.87e3      # 1000 x 59.658 + 58.534 + 1000 x 0.154 GFLOP
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="shapes per GPU")
+    ap.add_argument("--ddpm-steps", type=int, default=T_STEPS, help="(debug) DDPM steps; the metric is defined at 1000")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_models(cfg, device):
+    import torch
+    from lion_b200.models.latent_points_ada_localprior import PVCNN2Prior
+    from lion_b200.models.score_sde.resnet import PriorSEDrop
+    from lion_b200.models.vae_adain import Model
+    from tests.synth import synth_state_dict
+    shp = lambda m: {k: list(v.shape) for k, v in m.state_dict().items()}
+    gp = PriorSEDrop(cfg.sde, cfg.latent_pts.style_dim, cfg)
+    gp.load_state_dict(synth_state_dict(shp(gp), 14))
+    lp = PVCNN2Prior(cfg.sde, 1, cfg)
+    lp.load_state_dict(synth_state_dict(shp(lp), 11))
+    vae = Model(cfg)
+    vae.decoder.load_state_dict(synth_state_dict(shp(vae.decoder), 13))
+    dae = torch.nn.ModuleList([gp, lp]).to(device).eval()
+    return dae, vae.to(device).eval()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(B=1, local_steps=2, global_steps=4, threads=None):
+    """Bounded sample of the reference's CPU path (oracle port): a few denoising steps of both
+    priors + one decoder pass at batch B; returns (shapes_per_sec_extrapolated, detail)."""
+    import torch
+    from oracle import net as ON
+    from tests.synth import synth_state_dict
+    import json as _json
+    if threads:
+        torch.set_num_threads(threads)
+    keys = _json.load(open(os.path.join(ROOT, "tests", "golden", "keys.json")))
+    sd_l, sd_g, sd_d = synth_state_dict(keys["prior"], 11), synth_state_dict(keys["global"], 14), synth_state_dict(keys["decoder"], 13)
+    spec, dspec = ON.prior_spec(), ON.decoder_spec()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, 8192, 1, 1, generator=g)
+    style = torch.randn(B, 128, 1, 1, generator=g)
+    t = torch.full((B,), 500.0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for _ in range(local_steps):
+            ON.prior_forward(sd_l, spec, x, t, style)
+        tl = (time.perf_counter() - t0) / local_steps
+        t0 = time.perf_counter()
+        for _ in range(global_steps):
+            ON.global_prior_forward(sd_g, style, t)
+        tg = (time.perf_counter() - t0) / global_steps
+        t0 = time.perf_counter()
+        ON.decoder_forward(sd_d, dspec, x.view(B, -1), style.view(B, -1))
+        td = time.perf_counter() - t0
+    total = T_STEPS * (tl + tg) + td           # seconds per batch of B shapes
+    return B / total, {"s_per_local_step": tl, "s_per_global_step": tg, "s_decoder": td}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, detail = cpu_reference_sample(B=1, local_steps=1, global_steps=2)
+        if i >= args.warmup:
+            vals.append(v)
+    v = sum(vals) / len(vals)
+    sample = "per step: 1 PVCNN2Prior + 2 global-prior denoising steps + 1 decoder pass at B=1, extrapolated to 1000+1000+1"
+    line = {"impl": "reference", "metric": "shapes/sec (1000-step DDPM, 2048 latent pts, B=32)", "value": v, "unit": "shapes/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 32 / v,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "airplane prior, batch 32, 1000 DDPM steps, 2048 latent pts (configs[1])",
+                       "timed_on": "host CPU, oracle port of the reference's PyTorch path"},
+            "cpu_baseline": {"value": v, "unit": "shapes/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    import torch
+    import torch.distributed as dist
+    from lion_b200 import _lib as L
+    from lion_b200.config import default_prior_cfg
+    from lion_b200.utils.diffusion_pvd import DiffusionDiscretized
+    from lion_b200.trainers.train_2prior import generate_samples_vada_2prior
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path for --impl ours)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()
+    B, T = args.batch, args.ddpm_steps
+    cfg = default_prior_cfg(num_steps=T)
+    dae, vae = build_models(cfg, dev)
+    diff = DiffusionDiscretized(cfg.sde, None, cfg)
+    shape = vae.latent_shape()
+    gathered = [torch.empty(B, N_POINTS, 3, device=dev) for _ in range(world)] if world > 1 else None
+    launches = {"n": 0}
+
+    def one_pass(seed):
+        torch.manual_seed(seed * 1000 + rank)             # distinct noise per rank
+        img, *_ = generate_samples_vada_2prior(shape, dae, diff, vae, B, False)
+        launches["n"] += L.last_launches(dev)             # decoder pass (the sampling loops count themselves)
+        if world > 1:
+            dist.all_gather(gathered, img.contiguous())   # the single collective of the path
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing: K passes, CUDA events, max over ranks --------------------------
+    for i in range(args.warmup):
+        one_pass(i)
+    barrier()
+    launches["n"] = 0
+    diff.total_gpu_launches = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        img = one_pass(100 + i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    tms = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = tms.item()
+    value = world * B * args.steps / (ms / 1000.0)
+    n_launch = launches["n"] + diff.total_gpu_launches
+    assert torch.isfinite(img).all()
+
+    # ---- end to end: all noise from pinned host memory, result back to pinned host --------------
+    e2e = None
+    if not args.no_e2e:
+        g = torch.Generator().manual_seed(1234 + rank)
+        hn_g = torch.randn(T + 1, B, 128, 1, 1, generator=g).pin_memory()
+        hn_l = torch.randn(T + 1, B, 8192, 1, 1, generator=g).pin_memory()
+        hout = torch.empty(B, N_POINTS, 3).pin_memory()
+        h2d = (hn_g.numel() + hn_l.numel()) * 4
+        d2h = hout.numel() * 4
+
+        def e2e_pass():
+            dg = hn_g.to(dev, non_blocking=True)
+            dl = hn_l.to(dev, non_blocking=True)
+            z_g, _ = diff.run_denoising_diffusion(dae[0], B, shape[0], given_noise=(dg[0], dg[1:]))
+            z_l, _ = diff.run_denoising_diffusion(dae[1], B, shape[1], condition_input=vae.global2style(z_g),
+                                                  given_noise=(dl[0], dl[1:]))
+            pts = vae.sample(num_samples=B, decomposed_eps=vae.decompose_eps(vae.compose_eps([z_g, z_l])))
+            if world > 1:
+                dist.all_gather(gathered, pts.contiguous())
+            hout.copy_(pts, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        e2e_pass()                                          # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 2))
+        for _ in range(n_e2e):
+            e2e_pass()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * n_e2e / dt.item(), "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "note": "x_T and every per-step noise tensor of both priors come from pinned host memory; generated points are read back"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (measured alone, CUDA events on its stream) -------------
+    import ctypes as C
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops (burst) / 2: kind::tf32 UMMA issues at half the bf16 rate" if peaks \
+        else "fallback 1.59 PFLOP/s bf16 (B200_PROFILING.md) / 2"
+    ms_k, fl = C.c_float(), C.c_double()
+    L.check(L.lib().lion_bench_conv(L.ctx(dev), 27, 64, 64, 32, B, 20, 3, C.byref(ms_k), C.byref(fl), L.stream()), "bench_conv")
+    achieved = fl.value / (ms_k.value * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "lion::tc::k_conv_tc (3x3x3 conv 64->64 @ 32^3, B=%d; 4 launches / denoising step, 49%% of FLOPs)" % B,
+                "achieved": achieved, "peak": bf16_peak / 2.0, "unit": "TFLOP/s", "frac": achieved / (bf16_peak / 2.0),
+                "ms_per_launch": ms_k.value, "flops_per_launch": fl.value, "peak_source": peak_src, "traffic": None}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, detail = cpu_reference_sample(B=1, local_steps=2, global_steps=4, threads=os.cpu_count())
+        cpu = {"value": v, "unit": "shapes/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "2 PVCNN2Prior + 4 global-prior denoising steps + 1 decoder pass at B=1 on the CPU oracle, extrapolated to 1000+1000+1",
+               "detail": detail}
+
+    line = {"metric": "shapes/sec (1000-step DDPM, 2048 latent pts, B=32)", "value": value, "unit": "shapes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage/accumulate)",
+            "data": "synthetic",
+            "config": {"workload": "airplane prior, batch %d per GPU, %d DDPM steps x (global prior + PVCNN2 latent-point prior) + VAE decoder, 2048 latent pts (BASELINE configs[1])" % (B, T),
+                       "global_batch": B * world, "parallelism": "dp%d (independent shapes, one all_gather per pass)" % world,
+                       "l2": "per-step working set (303 MB voxel grids) exceeds the 126 MB L2; no flush needed",
+                       "weights": "key-seeded synthetic (tests/synth.py)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch,
+            "ms_per_denoise_step_pair": ms / args.steps / T,
+            "tensor_roofline_frac_whole_job": value * GFLOP_PER_SHAPE / 1e3 / world / (bf16_peak / 2.0),
+            "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,13 @@ int lion_ddpm_update(const float* x, const float* eps, const float* noise, float
 int lion_ddpm_set_step(int* step_ptr, float* t_out, int B, int t_index, void* stream);
 int lion_ddpm_next_step(int* step_ptr, float* t_out, int B, void* stream);
 
+/* measurement hook (bench.py roofline leg): average device time of `iters` launches of the
+ * convolution kernel alone (CUDA events on `stream`), on synthetic data: ntaps = 27 -> 3x3x3
+ * over [B, cin, r^3] (r_or_rows = r), ntaps = 1 -> 1x1 over r_or_rows rows.  flops_out = the
+ * algorithmic FLOPs of one launch (2*B*rows*ntaps*cin*cout, halo work not counted). */
+int lion_bench_conv(LionCtx* ctx, int ntaps, int cin, int cout, int r_or_rows, int B, int iters, int warmup,
+                    float* ms_out, double* flops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

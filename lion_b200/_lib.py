@@ -53,6 +53,7 @@ def _proto(lib):
         "lion_ddpm_update": (P(vp, vp, vp, vp, vp, vp, f, sz, vp, i, vp), i),
         "lion_ddpm_set_step": (P(vp, vp, i, i, vp), i),
         "lion_ddpm_next_step": (P(vp, vp, i, vp), i),
+        "lion_bench_conv": (P(vp, i, i, i, i, i, i, i, C.POINTER(f), C.POINTER(C.c_double), vp), i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)      # AttributeError if the library does not export it

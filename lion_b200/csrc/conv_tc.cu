@@ -1,9 +1,411 @@
-// placeholder until the tcgen05 kernel lands: every convolution uses the SIMT kernel
+// lion_b200 -- tensor-core convolution for sm_100a: tcgen05.mma (kind::tf32) with TMEM
+// accumulators, operands staged by cp.async.bulk + mbarrier pipelines, warp-specialised.
+//
+// One kernel serves the 3x3x3 voxel convolutions (reference: nn.Conv3d in
+// models/pvcnn2_ada.py:211-222 -> cuDNN, 98 % of the step's FLOPs) and the 1x1 point
+// convolutions (SharedMLP / attention projections, pvcnn2_ada.py:125-137, :51-52).
+//
+// Formulation (im2col-free implicit GEMM on the zero-haloed packed layouts, see
+// packed_kernels.cuh):  out[p][co] = sum_tap sum_ci in[p + off(tap)][ci] * W[tap][ci][co].
+//   * M = 128 consecutive rows p of one shape (voxel positions incl. y/z halo rows, masked at
+//     the store), N = output channels (<= 128 per CTA), K = 8 channels per UMMA.
+//   * A operand: the activation tensor is [C/4][rows][4] in HBM, i.e. for 4 channels all rows
+//     are contiguous at a 16-byte pitch.  That *is* the canonical no-swizzle K-major UMMA
+//     layout (core matrix = 8 rows x 16 B = 128 contiguous bytes, SBO = 128 B between 8-row
+//     groups, LBO = distance between channel groups), so one contiguous cp.async.bulk per
+//     channel group stages 128 + 2*halo rows, and every one of the 9 (dy,dz) taps of an x-plane
+//     is the SAME shared-memory bytes viewed through a descriptor whose start address is
+//     shifted by (dy*(r+2)+dz) rows.  L2->SM traffic per MAC drops 9x versus reloading per tap.
+//   * B operand: weights pre-packed [n-tile][chunk][x-plane][tap][C/4][co][4] so one bulk copy
+//     brings the 9 taps of a (channel chunk, x-plane); a CTA reuses it for up to 8 row tiles
+//     (8 x 64 fp32 accumulator columns = all 512 TMEM columns).
+//   * warp 0: bulk-copy producer, warp 1: single-thread MMA issuer, warps 2-5: epilogue
+//     (tcgen05.ld -> +bias -> halo mask -> coalesced float4 stores, GroupNorm sum / sum-of-squares
+//     reduced in registers/shared memory, one fp64 atomic per channel per CTA).
 #include "common.cuh"
 #include "model.cuh"
+#include <cstdlib>
+
 namespace lion {
-int conv_tc_prepare(Model*, ConvW&) { return 0; }
-int conv_tc_pack_job(const PackJob&) { return 0; }
-bool conv_tc_usable(const ConvW&, const ConvGeom&) { return false; }
-int conv_tc_run(Ctx*, const ConvW&, const float4*, int, float4*, int, double*, double*, const ConvGeom&, int) { return LION_ERR_STATE; }
+namespace tc {
+
+constexpr int THREADS = 192;
+constexpr int A_STAGES = 3;
+constexpr int B_STAGES = 2;
+constexpr int MAX_ACC = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (and surfaces as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct Params {
+  const float4* in; const float* w; const float* bias; float4* out; double* ssum; double* ssq;
+  int Gin, Gout_store, cout_pad;
+  int rows;              // rows per (b, group)
+  int p_begin, p_end;
+  int rp;                // r+2 (halo mask) or 0
+  int ntg, tpg;          // tap groups (x planes) and taps per group: (3,9) or (1,1)
+  int tg_off[3];         // row offset of each tap group (dx * rp^2)
+  int tap_off[9];        // row offset of each tap inside a group (dy*rp + dz)
+  int halo;              // rp+1 or 0
+  int KG, nchunk;        // channel groups per chunk, chunks
+  int NT;                // output channels per CTA (UMMA N)
+  int G;                 // row tiles (accumulators) per CTA
+  int a_stage_bytes, b_stage_bytes, stage_rows;
+};
+
+// per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
+// in: v[32] (this lane's row, 32 channels); cost 31 shuffles instead of 160.
+__device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float keep = upper ? v[i + half] : v[i];
+      float send = upper ? v[i] : v[i + half];
+      float got = __shfl_xor_sync(0xffffffffu, send, half);
+      v[i] = keep + got;
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // layout: [A stages][B stages][bias NT floats][stat NT*2*4 floats][barriers][tmem ptr]
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)A_STAGES * P.a_stage_bytes;
+  float* s_bias = (float*)(sB + (size_t)B_STAGES * P.b_stage_bytes);
+  float* s_stat = s_bias + 128;                 // [4 warps][2][128]
+  uint64_t* bars = (uint64_t*)(s_stat + 4 * 2 * 128);
+  uint32_t* s_tmem = (uint32_t*)(bars + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, nt = blockIdx.y;
+  const int n0 = nt * P.NT;
+  const int tile0 = blockIdx.x * P.G;
+  const int ntile_total = (P.p_end - P.p_begin + 127) / 128;
+  const int ntile = min(P.G, ntile_total - tile0);
+
+  uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + A_STAGES);
+  uint32_t bar_full_b = smem_u32(bars + 2 * A_STAGES), bar_empty_b = smem_u32(bars + 2 * A_STAGES + B_STAGES);
+  uint32_t bar_acc = smem_u32(bars + 2 * A_STAGES + 2 * B_STAGES);
+
+  // zero the A stages once: channel-group slots that a partial chunk does not load must hold
+  // finite values (their weights are zero)
+  for (int i = tid; i < A_STAGES * P.a_stage_bytes / 16; i += THREADS) ((float4*)sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < P.NT; i += THREADS) s_bias[i] = P.bias ? P.bias[n0 + i] : 0.0f;
+  if (tid == 0) {
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 1); }
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill -> async proxy readers
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+
+  const size_t in_b = (size_t)b * P.Gin * P.rows;           // float4 units
+  const size_t w_tile = (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);   // float units
+
+  if (warp == 0) {
+    // ===================== producer =====================
+    if (lane == 0) {
+      int ia = 0, ib = 0;          // running stage counters
+      for (int cc = 0; cc < P.nchunk; ++cc) {
+        int kg_real = min(P.KG, P.Gin - cc * P.KG);
+        for (int tg = 0; tg < P.ntg; ++tg) {
+          int sb = ib % B_STAGES;
+          mbar_wait(bar_empty_b + 8 * sb, ((ib / B_STAGES) & 1) ^ 1);
+          mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
+          bulk_g2s(smem_u32(sB + (size_t)sb * P.b_stage_bytes), P.w + w_tile + (size_t)(cc * P.ntg + tg) * (P.b_stage_bytes / 4),
+                   P.b_stage_bytes, bar_full_b + 8 * sb);
+          ++ib;
+          for (int j = 0; j < ntile; ++j) {
+            int sa = ia % A_STAGES;
+            mbar_wait(bar_empty_a + 8 * sa, ((ia / A_STAGES) & 1) ^ 1);
+            uint32_t bytes = (uint32_t)P.stage_rows * 16u;
+            mbar_expect_tx(bar_full_a + 8 * sa, bytes * kg_real);
+            long long row0 = (long long)P.p_begin + (long long)(tile0 + j) * 128 + P.tg_off[tg] - P.halo;
+            for (int kg = 0; kg < kg_real; ++kg) {
+              const float4* src = P.in + in_b + (size_t)(cc * P.KG + kg) * P.rows + row0;
+              bulk_g2s(smem_u32(sA + (size_t)sa * P.a_stage_bytes + (size_t)kg * bytes), src, bytes, bar_full_a + 8 * sa);
+            }
+            ++ia;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_pitch = (uint32_t)P.stage_rows * 16u;     // bytes between channel groups (LBO of A)
+      const uint32_t b_pitch = (uint32_t)P.NT * 16u;             // bytes between channel groups (LBO of B)
+      const uint32_t b_tap = (uint32_t)P.KG * b_pitch;
+      int ia = 0, ib = 0;
+      for (int cc = 0; cc < P.nchunk; ++cc) {
+        for (int tg = 0; tg < P.ntg; ++tg) {
+          int sb = ib % B_STAGES;
+          mbar_wait(bar_full_b + 8 * sb, (ib / B_STAGES) & 1);
+          uint32_t b_base = smem_u32(sB + (size_t)sb * P.b_stage_bytes);
+          for (int j = 0; j < ntile; ++j) {
+            int sa = ia % A_STAGES;
+            mbar_wait(bar_full_a + 8 * sa, (ia / A_STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t a_base = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
+            uint32_t d = tmem_base + (uint32_t)(j * P.NT);
+            for (int t = 0; t < P.tpg; ++t) {
+              uint32_t a_t = a_base + (uint32_t)(P.halo + P.tap_off[t]) * 16u;
+              uint32_t b_t = b_base + (uint32_t)t * b_tap;
+              for (int k2 = 0; k2 < P.KG; k2 += 2) {
+                uint64_t ad = make_desc(a_t + k2 * a_pitch, a_pitch, 128);
+                uint64_t bd = make_desc(b_t + k2 * b_pitch, b_pitch, 128);
+                uint32_t acc = (cc | tg | t | k2) != 0 ? 1u : 0u;
+                umma_tf32(d, ad, bd, idesc, acc);
+              }
+            }
+            umma_commit(bar_empty_a + 8 * sa);     // frees the A stage when these MMAs retire
+            ++ia;
+          }
+          umma_commit(bar_empty_b + 8 * sb);
+          ++ib;
+        }
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    mbar_wait(bar_acc, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // lane l: channels l, l+32, l+64, l+96
+    for (int j = 0; j < ntile; ++j) {
+      int p = P.p_begin + (tile0 + j) * 128 + q * 32 + lane;
+      bool inrange = p < P.p_end;
+      bool valid = inrange;
+      if (P.rp > 0 && inrange) {
+        int z = p % P.rp, y = (p / P.rp) % P.rp;
+        valid = (z >= 1 && z <= P.rp - 2 && y >= 1 && y <= P.rp - 2);
+      }
+      for (int c32 = 0; c32 < P.NT; c32 += 32) {
+        float v[32];
+        uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + c32);
+        tmem_ld16(taddr, v);
+        tmem_ld16(taddr + 16, v + 16);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + s_bias[c32 + i] : 0.0f;
+        if (inrange) {
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            int g = (n0 + c32) / 4 + g4;
+            if (g < P.Gout_store)
+              P.out[((size_t)b * P.Gout_store + g) * P.rows + p] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+          }
+        }
+        if (P.ssum) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+          run_s[c32 >> 5] += warp_transpose_sum(v, lane);
+          run_q[c32 >> 5] += warp_transpose_sum(sq, lane);
+        }
+      }
+    }
+    if (P.ssum) {
+      int ew = warp - 2;
+      for (int k = 0; k < P.NT / 32; ++k) {
+        s_stat[(ew * 2 + 0) * 128 + k * 32 + lane] = run_s[k];
+        s_stat[(ew * 2 + 1) * 128 + k * 32 + lane] = run_q[k];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+      int et = tid - 64;
+      if (et < P.NT) {
+        float s = 0.f, qq = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { s += s_stat[(w * 2 + 0) * 128 + et]; qq += s_stat[(w * 2 + 1) * 128 + et]; }
+        atomicAdd(P.ssum + (size_t)b * P.cout_pad + n0 + et, (double)s);
+        atomicAdd(P.ssq + (size_t)b * P.cout_pad + n0 + et, (double)qq);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// weights: from the SIMT packing wt[tap][cin_pad][cout_pad] to
+//   w[nt][chunk][tg][t][kg][n][4]  (tf32-rounded, round-to-nearest-away like cuDNN's conversion)
+__global__ void k_pack_tc(const float* __restrict__ wt, float* __restrict__ w, int ntaps, int cin_pad, int cout_pad,
+                          int NT, int nchunk, int ntg, int tpg, int KG) {
+  size_t total = (size_t)(cout_pad / NT) * nchunk * ntg * tpg * KG * NT * 4;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int jj = i % 4;
+  size_t r = i / 4;
+  int n = r % NT; r /= NT;
+  int kg = r % KG; r /= KG;
+  int t = r % tpg; r /= tpg;
+  int tg = r % ntg; r /= ntg;
+  int cc = r % nchunk; r /= nchunk;
+  int nt = (int)r;
+  int tap = tg * tpg + t;
+  int ci = (cc * KG + kg) * 4 + jj;
+  float v = 0.0f;
+  if (ci < cin_pad) v = wt[((size_t)tap * cin_pad + ci) * cout_pad + nt * NT + n];
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  w[i] = __uint_as_float(u);
+}
+
+}  // namespace tc
+
+static int tc_mode() {      // 1 = tensor cores (default), 0 = SIMT only (LION_CONV_IMPL=simt; bring-up/debug)
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LION_CONV_IMPL");
+    mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return mode;
+}
+
+static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, int& tpg) {
+  NT = w.cout_pad < 128 ? w.cout_pad : 128;
+  ntg = w.ntaps == 27 ? 3 : 1;
+  tpg = w.ntaps == 27 ? 9 : 1;
+  int G = w.cin_pad / 4;
+  if (w.ntaps == 27) KG = (NT > 64) ? 4 : 8;     // keep two 9-tap weight stages within shared memory
+  else KG = 8;
+  if (G < KG) KG = (G <= 2) ? 2 : ((G <= 4) ? 4 : 8);
+  nchunk = (G + KG - 1) / KG;
+}
+
+int conv_tc_prepare(Model* m, ConvW& w) {
+  w.tc = ConvTcW();
+  if (!(w.ntaps == 27 || w.ntaps == 1)) return 0;
+  if (w.cout_pad < 16 || w.cout_pad % 16) return 0;
+  int NT, KG, nchunk, ntg, tpg;
+  tc_shape(w, NT, KG, nchunk, ntg, tpg);
+  if (w.cout_pad % NT) return 0;
+  size_t total = (size_t)(w.cout_pad / NT) * nchunk * ntg * tpg * KG * NT * 4;
+  LION_TRY(m->dmalloc(&w.tc.w, total));
+  w.tc.ck = KG * 4; w.tc.nchunk = nchunk; w.tc.n = NT;
+  PackJob j{2, w.wt, nullptr, w.tc.w, w.ntaps, w.cin_pad, w.cout_pad, NT, 0};
+  j.kmap = nullptr;
+  m->jobs.push_back(j);
+  return 0;
+}
+
+int conv_tc_pack_job(const PackJob& j) {
+  ConvW tmp;
+  tmp.ntaps = j.a; tmp.cin_pad = j.b; tmp.cout_pad = j.c;
+  int NT, KG, nchunk, ntg, tpg;
+  tc_shape(tmp, NT, KG, nchunk, ntg, tpg);
+  size_t total = (size_t)(j.c / NT) * nchunk * ntg * tpg * KG * NT * 4;
+  tc::k_pack_tc<<<(unsigned)cdivz(total, 256), 256>>>(j.src, j.dst, j.a, j.b, j.c, NT, nchunk, ntg, tpg, KG);
+  return 0;
+}
+
+bool conv_tc_usable(const ConvW& w, const ConvGeom& geo) {
+  if (!tc_mode() || !w.tc.w) return false;
+  if (geo.ntaps != w.ntaps) return false;
+  return true;
+}
+
+int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum, double* ssq,
+                const ConvGeom& geo, int B) {
+  tc::Params P{};
+  int NT, KG, nchunk, ntg, tpg;
+  tc_shape(w, NT, KG, nchunk, ntg, tpg);
+  P.in = in; P.w = w.tc.w; P.bias = w.bias; P.out = out; P.ssum = ssum; P.ssq = ssq;
+  P.Gin = Gin; P.Gout_store = Gout_store; P.cout_pad = w.cout_pad;
+  P.rows = geo.rows; P.p_begin = geo.p_begin; P.p_end = geo.p_end; P.rp = geo.rp;
+  P.ntg = ntg; P.tpg = tpg; P.KG = KG; P.nchunk = nchunk; P.NT = NT;
+  if (w.ntaps == 27) {
+    int rp = geo.rp;
+    for (int dx = 0; dx < 3; ++dx) P.tg_off[dx] = (dx - 1) * rp * rp;
+    for (int dy = 0; dy < 3; ++dy) for (int dz = 0; dz < 3; ++dz) P.tap_off[dy * 3 + dz] = (dy - 1) * rp + (dz - 1);
+    P.halo = rp + 1;
+  } else {
+    P.tg_off[0] = 0; P.tap_off[0] = 0; P.halo = 0;
+  }
+  P.stage_rows = 128 + 2 * P.halo;
+  P.a_stage_bytes = KG * P.stage_rows * 16;
+  P.b_stage_bytes = tpg * KG * NT * 16;
+  int ntile = cdiv(geo.p_end - geo.p_begin, 128);
+  int n_tiles_n = w.cout_pad / NT;
+  int gmax = 512 / NT;
+  if (gmax > tc::MAX_ACC) gmax = tc::MAX_ACC;
+  // enough CTAs to fill the machine about twice when the problem allows it
+  long long want = 2LL * c->num_sms;
+  int G = gmax;
+  while (G > 1 && (long long)cdiv(ntile, G) * n_tiles_n * B < want) G >>= 1;
+  P.G = G;
+  size_t smem = (size_t)tc::A_STAGES * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 4 * 2 * 128 * 4 + 16 * 8 + 16;
+  if (smem > 227 * 1024) { set_error("conv_tc: %zu bytes of shared memory needed", smem); return LION_ERR_ARG; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    LION_CHECK_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(cdiv(ntile, G), n_tiles_n, B);
+  LION_LAUNCH(c, tc::k_conv_tc, grid, tc::THREADS, smem, P);
+  return check_launch(c, "conv_tc");
+}
+
+}  // namespace lion

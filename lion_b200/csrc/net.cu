@@ -894,3 +894,62 @@ extern "C" int lion_global_prior_forward(LionModel* h, const float* x, const flo
   Model* m = &h->m;
   return two_pass(m, stream, B, [&](Fwd& f) { (void)f; return global_prior_forward(m, x, t, clip, out, B); });
 }
+
+// ---- measurement hook: time the convolution kernel alone (bench.py roofline leg) ------------
+__global__ void k_fill_pattern(float* p, size_t n, float scale) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { unsigned h = (unsigned)(i * 2654435761u) ^ 0x9e3779b9u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+               p[i] = scale * ((float)(h & 0xffff) / 32768.0f - 1.0f); }
+}
+extern "C" int lion_bench_conv(LionCtx* ctx, int ntaps, int cin, int cout, int r_or_rows, int B, int iters, int warmup,
+                               float* ms_out, double* flops_out, void* stream) {
+  LION_REQUIRE(ctx && ms_out && flops_out && (ntaps == 27 || ntaps == 1) && cin % 4 == 0 && cout % 8 == 0 && B > 0 && iters > 0,
+               "lion_bench_conv: bad arguments");
+  LION_CHECK_CUDA(cudaSetDevice(ctx->c.device));
+  LionModel h;
+  Model* m = &h.m;
+  m->ctx = &ctx->c;
+  float *wref = nullptr, *bref = nullptr;
+  size_t nw = (size_t)cout * cin * ntaps;
+  LION_TRY(m->dmalloc(&wref, nw));
+  LION_TRY(m->dmalloc(&bref, (size_t)cout));
+  k_fill_pattern<<<(unsigned)cdivz(nw, 256), 256>>>(wref, nw, 0.05f);
+  k_fill_pattern<<<cdiv(cout, 256), 256>>>(bref, cout, 0.1f);
+  ConvW w;
+  LION_TRY(make_conv(m, w, wref, bref, ntaps, cin, cout, ident_map(cin)));
+  LION_TRY(run_jobs(m));
+  ConvGeom geo = ntaps == 27 ? geom_grid(r_or_rows) : geom_rows(r_or_rows);
+  size_t guard = ntaps == 27 ? (size_t)(r_or_rows + 2) * (r_or_rows + 2) + (r_or_rows + 2) + 8 : 256;
+  size_t n_in = (size_t)B * (cin / 4) * geo.rows + 2 * guard, n_out = (size_t)B * (cout / 4) * geo.rows + 2 * guard;
+  float4 *din = nullptr, *dout = nullptr;
+  double* stats = nullptr;
+  LION_TRY(m->dmalloc(&din, n_in));
+  LION_TRY(m->dmalloc(&dout, n_out));
+  LION_TRY(m->dmalloc(&stats, (size_t)2 * B * w.cout_pad));
+  k_fill_pattern<<<(unsigned)cdivz(n_in * 4, 256), 256>>>((float*)din, n_in * 4, 1.0f);
+  LION_CHECK_CUDA(cudaMemset(stats, 0, sizeof(double) * 2 * B * w.cout_pad));
+  LION_CHECK_CUDA(cudaDeviceSynchronize());
+  Ctx* c = &ctx->c;
+  c->stream = (cudaStream_t)stream;
+  c->dry = false;
+  Fwd f{c, m, B};
+  cudaEvent_t e0, e1;
+  LION_CHECK_CUDA(cudaEventCreate(&e0));
+  LION_CHECK_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < warmup; ++i)
+    LION_TRY(run_conv(f, w, din + guard, cin / 4, dout + guard, cout / 4, stats, stats + (size_t)B * w.cout_pad, geo));
+  LION_CHECK_CUDA(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < iters; ++i)
+    LION_TRY(run_conv(f, w, din + guard, cin / 4, dout + guard, cout / 4, stats, stats + (size_t)B * w.cout_pad, geo));
+  LION_CHECK_CUDA(cudaEventRecord(e1, c->stream));
+  LION_CHECK_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  LION_CHECK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms / iters;
+  // algorithmic FLOPs of the dense convolution (interior voxels / rows only, no halo work counted)
+  double rows = ntaps == 27 ? (double)r_or_rows * r_or_rows * r_or_rows : (double)r_or_rows;
+  *flops_out = 2.0 * B * rows * ntaps * (double)cin * cout;
+  return 0;
+}

@@ -33,6 +33,7 @@ class DiffusionDiscretized(object):
         self._tables = None
         self.use_cuda_graph = True
         self.last_gpu_launches = 0
+        self.total_gpu_launches = 0      # kernels of this library launched by all sampling loops so far
 
     def _generate_base_constants(self, diffusion_steps):
         """float64 numpy -> fp32 tensors (diffusion_pvd.py:118-142)"""
@@ -149,6 +150,7 @@ class DiffusionDiscretized(object):
                     body(given_noise is None)
                 launches += per_step
         self.last_gpu_launches = launches
+        self.total_gpu_launches += launches
         # the reference appends x_noisy after every step, and at t == 0 x_noisy is not updated
         # (diffusion_pvd.py:292-298), so the last entry repeats the one before it
         pred_x = [hist[k] for k in range(T - 1)] + [hist[T - 2] if T > 1 else x0]
