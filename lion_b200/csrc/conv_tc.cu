@@ -97,7 +97,8 @@ struct Params {
   int halo;              // rp+1 or 0
   int KG, nchunk;        // channel groups per chunk, chunks
   int NT;                // output channels per CTA (UMMA N)
-  int G;                 // row tiles (accumulators) per CTA
+  int G;                 // row tiles (accumulators) per work item
+  int B;                 // shapes
   int a_stage_bytes, b_stage_bytes, stage_rows;
 };
 
@@ -118,34 +119,31 @@ __device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
   return v[0];
 }
 
+template <int KG, int TPG>
 __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  // layout: [A stages][B stages][bias NT floats][stat NT*2*4 floats][barriers][tmem ptr]
+  // layout: [A stages][B stages][bias NT floats][stat 4*2*128 floats][barriers][tmem ptr]
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)A_STAGES * P.a_stage_bytes;
   float* s_bias = (float*)(sB + (size_t)B_STAGES * P.b_stage_bytes);
   float* s_stat = s_bias + 128;                 // [4 warps][2][128]
   uint64_t* bars = (uint64_t*)(s_stat + 4 * 2 * 128);
-  uint32_t* s_tmem = (uint32_t*)(bars + 16);
+  uint32_t* s_tmem = (uint32_t*)(bars + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z, nt = blockIdx.y;
-  const int n0 = nt * P.NT;
-  const int tile0 = blockIdx.x * P.G;
-  const int ntile_total = (P.p_end - P.p_begin + 127) / 128;
-  const int ntile = min(P.G, ntile_total - tile0);
 
-  uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + A_STAGES);
-  uint32_t bar_full_b = smem_u32(bars + 2 * A_STAGES), bar_empty_b = smem_u32(bars + 2 * A_STAGES + B_STAGES);
-  uint32_t bar_acc = smem_u32(bars + 2 * A_STAGES + 2 * B_STAGES);
+  const uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + A_STAGES);
+  const uint32_t bar_full_b = smem_u32(bars + 2 * A_STAGES), bar_empty_b = smem_u32(bars + 2 * A_STAGES + B_STAGES);
+  const uint32_t bar_acc = smem_u32(bars + 2 * A_STAGES + 2 * B_STAGES);
+  const uint32_t bar_tfree = bar_acc + 8;       // MAX_ACC barriers: accumulator j drained by the epilogue
 
   // zero the A stages once: channel-group slots that a partial chunk does not load must hold
   // finite values (their weights are zero)
   for (int i = tid; i < A_STAGES * P.a_stage_bytes / 16; i += THREADS) ((float4*)sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = tid; i < P.NT; i += THREADS) s_bias[i] = P.bias ? P.bias[n0 + i] : 0.0f;
   if (tid == 0) {
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 1); }
     mbar_init(bar_acc, 1);
+    for (int i = 0; i < MAX_ACC; ++i) mbar_init(bar_tfree + 8 * i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill -> async proxy readers
@@ -158,33 +156,45 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
 
-  const size_t in_b = (size_t)b * P.Gin * P.rows;           // float4 units
-  const size_t w_tile = (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);   // float units
+  const int ntile_total = (P.p_end - P.p_begin + 127) / 128;
+  const int ngrp = (ntile_total + P.G - 1) / P.G;
+  const int n_nt = P.cout_pad / P.NT;
+  const int n_items = ngrp * n_nt * P.B;
+  // work item w -> (b, n-tile, row-tile group); consecutive items share weights (L2 locality)
+#define ITEM_DECODE(w)                                                  \
+  const int grp = (w) % ngrp; const int nt = ((w) / ngrp) % n_nt; const int b = (w) / (ngrp * n_nt); \
+  const int tile0 = grp * P.G; const int ntile = min(P.G, ntile_total - tile0); const int n0 = nt * P.NT;
 
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
-      int ia = 0, ib = 0;          // running stage counters
-      for (int cc = 0; cc < P.nchunk; ++cc) {
-        int kg_real = min(P.KG, P.Gin - cc * P.KG);
-        for (int tg = 0; tg < P.ntg; ++tg) {
-          int sb = ib % B_STAGES;
-          mbar_wait(bar_empty_b + 8 * sb, ((ib / B_STAGES) & 1) ^ 1);
-          mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
-          bulk_g2s(smem_u32(sB + (size_t)sb * P.b_stage_bytes), P.w + w_tile + (size_t)(cc * P.ntg + tg) * (P.b_stage_bytes / 4),
-                   P.b_stage_bytes, bar_full_b + 8 * sb);
-          ++ib;
-          for (int j = 0; j < ntile; ++j) {
-            int sa = ia % A_STAGES;
-            mbar_wait(bar_empty_a + 8 * sa, ((ia / A_STAGES) & 1) ^ 1);
-            uint32_t bytes = (uint32_t)P.stage_rows * 16u;
-            mbar_expect_tx(bar_full_a + 8 * sa, bytes * kg_real);
-            long long row0 = (long long)P.p_begin + (long long)(tile0 + j) * 128 + P.tg_off[tg] - P.halo;
-            for (int kg = 0; kg < kg_real; ++kg) {
-              const float4* src = P.in + in_b + (size_t)(cc * P.KG + kg) * P.rows + row0;
-              bulk_g2s(smem_u32(sA + (size_t)sa * P.a_stage_bytes + (size_t)kg * bytes), src, bytes, bar_full_a + 8 * sa);
+      uint32_t ia = 0, ib = 0;          // running stage counters
+      const uint32_t bytes = (uint32_t)P.stage_rows * 16u;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        ITEM_DECODE(w)
+        (void)n0;
+        const size_t in_b = (size_t)b * P.Gin * P.rows;
+        const float* wsrc = P.w + (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);
+        for (int cc = 0; cc < P.nchunk; ++cc) {
+          int kg_real = min(KG, P.Gin - cc * KG);
+          for (int tg = 0; tg < P.ntg; ++tg) {
+            uint32_t sb = ib % B_STAGES;
+            mbar_wait(bar_empty_b + 8 * sb, ((ib / B_STAGES) & 1) ^ 1);
+            mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
+            bulk_g2s(smem_u32(sB + (size_t)sb * P.b_stage_bytes), wsrc + (size_t)(cc * P.ntg + tg) * (P.b_stage_bytes / 4),
+                     P.b_stage_bytes, bar_full_b + 8 * sb);
+            ++ib;
+            for (int j = 0; j < ntile; ++j) {
+              uint32_t sa = ia % A_STAGES;
+              mbar_wait(bar_empty_a + 8 * sa, ((ia / A_STAGES) & 1) ^ 1);
+              mbar_expect_tx(bar_full_a + 8 * sa, bytes * kg_real);
+              long long row0 = (long long)P.p_begin + (long long)(tile0 + j) * 128 + P.tg_off[tg] - P.halo;
+              const float4* src = P.in + in_b + (size_t)(cc * KG) * P.rows + row0;
+              uint32_t dst = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
+              for (int kg = 0; kg < kg_real; ++kg)
+                bulk_g2s(dst + kg * bytes, src + (size_t)kg * P.rows, bytes, bar_full_a + 8 * sa);
+              ++ia;
             }
-            ++ia;
           }
         }
       }
@@ -193,95 +203,125 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_pitch = (uint32_t)P.stage_rows * 16u;     // bytes between channel groups (LBO of A)
-      const uint32_t b_pitch = (uint32_t)P.NT * 16u;             // bytes between channel groups (LBO of B)
-      const uint32_t b_tap = (uint32_t)P.KG * b_pitch;
-      int ia = 0, ib = 0;
-      for (int cc = 0; cc < P.nchunk; ++cc) {
-        for (int tg = 0; tg < P.ntg; ++tg) {
-          int sb = ib % B_STAGES;
-          mbar_wait(bar_full_b + 8 * sb, (ib / B_STAGES) & 1);
-          uint32_t b_base = smem_u32(sB + (size_t)sb * P.b_stage_bytes);
-          for (int j = 0; j < ntile; ++j) {
-            int sa = ia % A_STAGES;
-            mbar_wait(bar_full_a + 8 * sa, (ia / A_STAGES) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t a_base = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
-            uint32_t d = tmem_base + (uint32_t)(j * P.NT);
-            for (int t = 0; t < P.tpg; ++t) {
-              uint32_t a_t = a_base + (uint32_t)(P.halo + P.tap_off[t]) * 16u;
-              uint32_t b_t = b_base + (uint32_t)t * b_tap;
-              for (int k2 = 0; k2 < P.KG; k2 += 2) {
-                uint64_t ad = make_desc(a_t + k2 * a_pitch, a_pitch, 128);
-                uint64_t bd = make_desc(b_t + k2 * b_pitch, b_pitch, 128);
-                uint32_t acc = (cc | tg | t | k2) != 0 ? 1u : 0u;
-                umma_tf32(d, ad, bd, idesc, acc);
+      const uint32_t a_pitch16 = (uint32_t)P.stage_rows;             // (bytes between channel groups) >> 4
+      const uint32_t b_pitch16 = (uint32_t)P.NT;
+      const uint32_t b_tap16 = (uint32_t)KG * b_pitch16;
+      // descriptor high words are constant: LBO = group pitch, SBO = 128 B, version 1, no swizzle
+      const uint32_t a_hi = (128u >> 4) | (1u << 14);
+      const uint32_t b_hi = a_hi;
+      const uint32_t a_lo_c = (a_pitch16 & 0x3fff) << 16, b_lo_c = (b_pitch16 & 0x3fff) << 16;
+      uint32_t a_off16[TPG];
+#pragma unroll
+      for (int t = 0; t < TPG; ++t) a_off16[t] = (uint32_t)(P.halo + P.tap_off[t]);
+      uint32_t ia = 0, ib = 0, it = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+        ITEM_DECODE(w)
+        (void)b; (void)n0;
+        for (int cc = 0; cc < P.nchunk; ++cc) {
+          for (int tg = 0; tg < P.ntg; ++tg) {
+            uint32_t sb = ib % B_STAGES;
+            mbar_wait(bar_full_b + 8 * sb, (ib / B_STAGES) & 1);
+            const uint32_t b_base16 = smem_u32(sB + (size_t)sb * P.b_stage_bytes) >> 4;
+            const bool first = (cc | tg) == 0;
+            for (int j = 0; j < ntile; ++j) {
+              if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);     // accumulator j drained (previous item)
+              uint32_t sa = ia % A_STAGES;
+              mbar_wait(bar_full_a + 8 * sa, (ia / A_STAGES) & 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t a_base16 = smem_u32(sA + (size_t)sa * P.a_stage_bytes) >> 4;
+              const uint32_t d = tmem_base + (uint32_t)(j * P.NT);
+#pragma unroll
+              for (int t = 0; t < TPG; ++t) {
+#pragma unroll
+                for (int k2 = 0; k2 < KG; k2 += 2) {
+                  uint32_t alo = a_lo_c | ((a_base16 + a_off16[t] + k2 * a_pitch16) & 0x3fff);
+                  uint32_t blo = b_lo_c | ((b_base16 + t * b_tap16 + k2 * b_pitch16) & 0x3fff);
+                  uint64_t ad = ((uint64_t)a_hi << 32) | alo, bd = ((uint64_t)b_hi << 32) | blo;
+                  umma_tf32(d, ad, bd, idesc, (first && t == 0 && k2 == 0) ? 0u : 1u);
+                }
               }
+              umma_commit(bar_empty_a + 8 * sa);     // frees the A stage when these MMAs retire
+              ++ia;
             }
-            umma_commit(bar_empty_a + 8 * sa);     // frees the A stage when these MMAs retire
-            ++ia;
+            umma_commit(bar_empty_b + 8 * sb);
+            ++ib;
           }
-          umma_commit(bar_empty_b + 8 * sb);
-          ++ib;
         }
+        umma_commit(bar_acc);
       }
-      umma_commit(bar_acc);
     }
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    mbar_wait(bar_acc, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // lane l: channels l, l+32, l+64, l+96
-    for (int j = 0; j < ntile; ++j) {
-      int p = P.p_begin + (tile0 + j) * 128 + q * 32 + lane;
-      bool inrange = p < P.p_end;
-      bool valid = inrange;
-      if (P.rp > 0 && inrange) {
-        int z = p % P.rp, y = (p / P.rp) % P.rp;
-        valid = (z >= 1 && z <= P.rp - 2 && y >= 1 && y <= P.rp - 2);
-      }
-      for (int c32 = 0; c32 < P.NT; c32 += 32) {
-        float v[32];
-        uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + c32);
-        tmem_ld16(taddr, v);
-        tmem_ld16(taddr + 16, v + 16);
+    const int ew = warp - 2, et = tid - 64;
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      ITEM_DECODE(w)
+      asm volatile("bar.sync 1, 128;" ::: "memory");            // previous item's s_bias / s_stat readers are done
+      if (et < P.NT) s_bias[et] = P.bias ? P.bias[n0 + et] : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(bar_acc, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // lane l: channels l, l+32, l+64, l+96
+      for (int j = 0; j < ntile; ++j) {
+        int p = P.p_begin + (tile0 + j) * 128 + q * 32 + lane;
+        bool inrange = p < P.p_end;
+        bool valid = inrange;
+        if (P.rp > 0 && inrange) {
+          int z = p % P.rp, y = (p / P.rp) % P.rp;
+          valid = (z >= 1 && z <= P.rp - 2 && y >= 1 && y <= P.rp - 2);
+        }
+        for (int c32 = 0; c32 < P.NT; c32 += 32) {
+          float v[32];
+          uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + c32);
+          tmem_ld16(taddr, v);
+          tmem_ld16(taddr + 16, v + 16);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + s_bias[c32 + i] : 0.0f;
-        if (inrange) {
+          for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + s_bias[c32 + i] : 0.0f;
+          if (inrange) {
 #pragma unroll
-          for (int g4 = 0; g4 < 8; ++g4) {
-            int g = (n0 + c32) / 4 + g4;
-            if (g < P.Gout_store)
-              P.out[((size_t)b * P.Gout_store + g) * P.rows + p] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+            for (int g4 = 0; g4 < 8; ++g4) {
+              int g = (n0 + c32) / 4 + g4;
+              if (g < P.Gout_store)
+                P.out[((size_t)b * P.Gout_store + g) * P.rows + p] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+            }
+          }
+          if (P.ssum) {
+            float sq[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
+            run_s[c32 >> 5] += warp_transpose_sum(v, lane);
+            run_q[c32 >> 5] += warp_transpose_sum(sq, lane);
           }
         }
-        if (P.ssum) {
-          float sq[32];
+        // accumulator j is drained: let the MMA warp start the next item's tile j
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree + 8 * j) : "memory");
+      }
+      if (P.ssum) {
+        for (int k = 0; k < P.NT / 32; ++k) {
+          s_stat[(ew * 2 + 0) * 128 + k * 32 + lane] = run_s[k];
+          s_stat[(ew * 2 + 1) * 128 + k * 32 + lane] = run_q[k];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+        if (et < P.NT) {
+          float s = 0.f, qq = 0.f;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-          run_s[c32 >> 5] += warp_transpose_sum(v, lane);
-          run_q[c32 >> 5] += warp_transpose_sum(sq, lane);
+          for (int ww = 0; ww < 4; ++ww) { s += s_stat[(ww * 2 + 0) * 128 + et]; qq += s_stat[(ww * 2 + 1) * 128 + et]; }
+          atomicAdd(P.ssum + (size_t)b * P.cout_pad + n0 + et, (double)s);
+          atomicAdd(P.ssq + (size_t)b * P.cout_pad + n0 + et, (double)qq);
         }
       }
-    }
-    if (P.ssum) {
-      int ew = warp - 2;
-      for (int k = 0; k < P.NT / 32; ++k) {
-        s_stat[(ew * 2 + 0) * 128 + k * 32 + lane] = run_s[k];
-        s_stat[(ew * 2 + 1) * 128 + k * 32 + lane] = run_q[k];
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
-      int et = tid - 64;
-      if (et < P.NT) {
-        float s = 0.f, qq = 0.f;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) { s += s_stat[(w * 2 + 0) * 128 + et]; qq += s_stat[(w * 2 + 1) * 128 + et]; }
-        atomicAdd(P.ssum + (size_t)b * P.cout_pad + n0 + et, (double)s);
-        atomicAdd(P.ssq + (size_t)b * P.cout_pad + n0 + et, (double)qq);
+      // tiles beyond ntile of this item were never touched: release them too so the phase
+      // bookkeeping of bar_tfree stays in step with the item counter
+      for (int j = ntile; j < MAX_ACC; ++j) {
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree + 8 * j) : "memory");
       }
     }
   }
+#undef ITEM_DECODE
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -396,15 +436,22 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   int G = gmax;
   while (G > 1 && (long long)cdiv(ntile, G) * n_tiles_n * B < want) G >>= 1;
   P.G = G;
-  size_t smem = (size_t)tc::A_STAGES * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 4 * 2 * 128 * 4 + 16 * 8 + 16;
+  P.B = B;
+  size_t smem = (size_t)tc::A_STAGES * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 4 * 2 * 128 * 4 + 32 * 8 + 16;
   if (smem > 227 * 1024) { set_error("conv_tc: %zu bytes of shared memory needed", smem); return LION_ERR_ARG; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    LION_CHECK_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  long long n_items = (long long)cdiv(ntile, G) * n_tiles_n * B;
+  int grid = (int)(n_items < c->num_sms ? n_items : c->num_sms);      // persistent: one CTA per SM
+#define LION_TC_CASE(kg, tpg_)                                                                            \
+  if (KG == kg && tpg == tpg_) {                                                                          \
+    static bool attr_set = false;                                                                         \
+    if (!attr_set) {                                                                                      \
+      LION_CHECK_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<kg, tpg_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                    \
+    }                                                                                                     \
+    LION_LAUNCH(c, (tc::k_conv_tc<kg, tpg_>), grid, tc::THREADS, smem, P);                                \
   }
-  dim3 grid(cdiv(ntile, G), n_tiles_n, B);
-  LION_LAUNCH(c, tc::k_conv_tc, grid, tc::THREADS, smem, P);
+  LION_TC_CASE(2, 1) LION_TC_CASE(4, 1) LION_TC_CASE(8, 1) LION_TC_CASE(2, 9) LION_TC_CASE(4, 9) LION_TC_CASE(8, 9)
+#undef LION_TC_CASE
   return check_launch(c, "conv_tc");
 }
 

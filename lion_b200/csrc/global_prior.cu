@@ -12,71 +12,112 @@
 
 namespace lion {
 
-constexpr int GP_MAXB = 64;     // rows handled per launch
-constexpr int GP_KT = 256;      // K tile staged in shared memory
-constexpr int GP_CO_PER_WARP = 2;
+constexpr int GP_MAXB = 64;     // rows handled per call
+constexpr int GP_BT = 32;       // batch rows per pass (one accumulator per row and output)
+constexpr int GP_KT = 512;      // K tile staged in shared memory
+constexpr int GP_PITCH = GP_KT + 4;
+constexpr int GP_CO = 2;        // outputs per warp
 constexpr int GP_WARPS = 8;
 
+__device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float keep = upper ? v[i + half] : v[i];
+      float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
 // out[b][o] = epi( sum_k W[o][k] * (x[b][k] + add[b][k]) + bias[o] )
-//   act: 0 none, 1 relu, 2 sigmoid
-//   mul: if given, result *= mul[b][o]           (SE gate application)
-//   res: if given, result += res[b][o]           (residual shortcut)
-// x/add/out/mul/res are row-major with the given strides; W is [O][K] row-major (1x1 conv weight).
+//   act: 0 none, 1 relu, 2 sigmoid;  mul: result *= mul[b][o] (SE gate);  res: result += res[b][o]
+// W is [O][K] row-major (a 1x1 conv weight), K % 4 == 0.  Each warp owns GP_CO output rows and
+// streams them with 128-bit loads that are issued one K tile ahead (software pipelined, 8 loads
+// in flight per lane); the x tile of all <=32 batch rows sits in shared memory and every
+// 128-bit shared load feeds 8 FMAs.  Lane l ends up with the dot product of batch row l
+// (butterfly transpose-reduce), so the epilogue is one store per lane.
 __global__ void __launch_bounds__(GP_WARPS * 32)
 k_gp_linear(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x, int x_stride,
             const float* __restrict__ add, int add_stride, float* __restrict__ out, int out_stride,
             const float* __restrict__ mul, int mul_stride, const float* __restrict__ res, int res_stride,
             int B, int K, int O, int act) {
-  __shared__ float s_x[GP_MAXB / 2][GP_KT + 4];
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int o0 = (blockIdx.x * GP_WARPS + wid) * GP_CO_PER_WARP;
-  float acc[GP_CO_PER_WARP][GP_MAXB / 2];      // B <= 32 per pass; two passes for B up to 64
-  for (int b0 = 0; b0 < B; b0 += GP_MAXB / 2) {
-    int nb = min(GP_MAXB / 2, B - b0);
+  extern __shared__ __align__(16) float s_x[];      // [GP_BT][GP_PITCH]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int o0 = (blockIdx.x * GP_WARPS + wid) * GP_CO;
+  const int ntile = (K + GP_KT - 1) / GP_KT;
+  for (int b0 = 0; b0 < B; b0 += GP_BT) {
+    const int nb = min(GP_BT, B - b0);
+    float acc[GP_CO][GP_BT];
 #pragma unroll
-    for (int c = 0; c < GP_CO_PER_WARP; ++c)
+    for (int c = 0; c < GP_CO; ++c)
 #pragma unroll
-      for (int b = 0; b < GP_MAXB / 2; ++b) acc[c][b] = 0.0f;
-    for (int k0 = 0; k0 < K; k0 += GP_KT) {
-      int kt = min(GP_KT, K - k0);
+      for (int b = 0; b < GP_BT; ++b) acc[c][b] = 0.0f;
+    float4 wn[GP_CO][4];
+    auto load_w = [&](int tile) {
+#pragma unroll
+      for (int c = 0; c < GP_CO; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int k = tile * GP_KT + (lane + 32 * i) * 4;
+          wn[c][i] = (o0 + c < O && k < K) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + c) * K + k))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_w(0);
+    for (int tile = 0; tile < ntile; ++tile) {
+      const int k0 = tile * GP_KT, kt = min(GP_KT, K - k0);
       __syncthreads();
-      for (int i = threadIdx.x; i < nb * kt; i += blockDim.x) {
-        int b = i / kt, k = i % kt;
-        float v = x[(size_t)(b0 + b) * x_stride + k0 + k];
-        if (add) v += add[(size_t)(b0 + b) * add_stride + k0 + k];
-        s_x[b][k] = v;
+      for (int i = threadIdx.x; i < GP_BT * (GP_KT / 4); i += blockDim.x) {
+        int b = i / (GP_KT / 4), k4 = i % (GP_KT / 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < nb && k4 * 4 < kt) {
+          v = *reinterpret_cast<const float4*>(x + (size_t)(b0 + b) * x_stride + k0 + k4 * 4);
+          if (add) {
+            float4 a = *reinterpret_cast<const float4*>(add + (size_t)(b0 + b) * add_stride + k0 + k4 * 4);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+          }
+        }
+        *reinterpret_cast<float4*>(s_x + b * GP_PITCH + k4 * 4) = v;
       }
       __syncthreads();
-      for (int k = lane; k < kt; k += 32) {
-        float w[GP_CO_PER_WARP];
+      float4 wc[GP_CO][4];
 #pragma unroll
-        for (int c = 0; c < GP_CO_PER_WARP; ++c) w[c] = (o0 + c < O) ? __ldg(W + (size_t)(o0 + c) * K + k0 + k) : 0.0f;
+      for (int c = 0; c < GP_CO; ++c)
 #pragma unroll
-        for (int b = 0; b < GP_MAXB / 2; ++b) {
-          if (b < nb) {
-            float xv = s_x[b][k];
+        for (int i = 0; i < 4; ++i) wc[c][i] = wn[c][i];
+      if (tile + 1 < ntile) load_w(tile + 1);                 // in flight while this tile is consumed
 #pragma unroll
-            for (int c = 0; c < GP_CO_PER_WARP; ++c) acc[c][b] = fmaf(w[c], xv, acc[c][b]);
+      for (int i = 0; i < 4; ++i) {
+        const float* xr = s_x + (lane + 32 * i) * 4;
+#pragma unroll
+        for (int b = 0; b < GP_BT; ++b) {
+          float4 xv = *reinterpret_cast<const float4*>(xr + b * GP_PITCH);
+#pragma unroll
+          for (int c = 0; c < GP_CO; ++c) {
+            acc[c][b] = fmaf(wc[c][i].x, xv.x, acc[c][b]);
+            acc[c][b] = fmaf(wc[c][i].y, xv.y, acc[c][b]);
+            acc[c][b] = fmaf(wc[c][i].z, xv.z, acc[c][b]);
+            acc[c][b] = fmaf(wc[c][i].w, xv.w, acc[c][b]);
           }
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c < GP_CO_PER_WARP; ++c) {
-#pragma unroll
-      for (int b = 0; b < GP_MAXB / 2; ++b) {
-        if (b < nb) {                                   // warp-uniform
-          float v = warp_sum(acc[c][b]);
-          int o = o0 + c;
-          if (lane == 0 && o < O) {
-            v += bias ? bias[o] : 0.0f;
-            if (act == 1) v = fmaxf(v, 0.0f);
-            else if (act == 2) v = 1.0f / (1.0f + expf(-v));
-            if (mul) v *= mul[(size_t)(b0 + b) * mul_stride + o];
-            if (res) v += res[(size_t)(b0 + b) * res_stride + o];
-            out[(size_t)(b0 + b) * out_stride + o] = v;
-          }
-        }
+    for (int c = 0; c < GP_CO; ++c) {
+      float v = warp_transpose_sum32(acc[c], lane);            // lane l: batch row l
+      int o = o0 + c;
+      if (lane < nb && o < O) {
+        int b = b0 + lane;
+        v += bias ? bias[o] : 0.0f;
+        if (act == 1) v = fmaxf(v, 0.0f);
+        else if (act == 2) v = 1.0f / (1.0f + expf(-v));
+        if (mul) v *= mul[(size_t)b * mul_stride + o];
+        if (res) v += res[(size_t)b * res_stride + o];
+        out[(size_t)b * out_stride + o] = v;
       }
     }
   }
@@ -138,8 +179,14 @@ int global_prior_build(Model* m, Cursor& cur) {
 
 static int gp_linear(Ctx* c, const GPLin& l, const float* x, int xs, const float* add, int as, float* out, int os,
                      const float* mul, int ms, const float* res, int rs, int B, int act) {
-  int grid = cdiv(l.O, GP_WARPS * GP_CO_PER_WARP);
-  LION_LAUNCH(c, k_gp_linear, grid, GP_WARPS * 32, 0, l.w, l.b, x, xs, add, as, out, os, mul, ms, res, rs, B, l.K, l.O, act);
+  int grid = cdiv(l.O, GP_WARPS * GP_CO);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LION_CHECK_CUDA(cudaFuncSetAttribute(k_gp_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_BT * GP_PITCH * (int)sizeof(float)));
+    attr_set = true;
+  }
+  if (l.K % 4) { set_error("global prior: K=%d must be a multiple of 4", l.K); return LION_ERR_ARG; }
+  LION_LAUNCH(c, k_gp_linear, grid, GP_WARPS * 32, GP_BT * GP_PITCH * sizeof(float), l.w, l.b, x, xs, add, as, out, os, mul, ms, res, rs, B, l.K, l.O, act);
   return 0;
 }
 

@@ -200,7 +200,7 @@ int make_fp(Model* m, FPBlk& f, Cursor& cur, int cc, int cp, const std::vector<i
 // forward-time helpers
 // =====================================================================================
 struct PF { float4* p = nullptr; int G = 0; int R = 0; };
-struct VoxPrep { const float4* c4; int N, r; float4* nc; int* ppos; float* inv; };
+struct VoxPrep { const float4* c4; int N, r; float4* nc; int* order; int* ppos; int* len; };
 struct Fwd {
   Ctx* c; Model* m; int B;
   float* aff = nullptr;          // [B][style_total] all AdaGN (factor|bias) vectors of this forward
@@ -295,13 +295,13 @@ static int shared_mlp_fwd(Fwd& f, const SharedMLPBlk& m, PF in, int pool, float4
     if (last && pool > 1) {
       if (pool != 32 || cur.R % 32) { set_error("shared_mlp: unsupported pooling %d", pool); return LION_ERR_ARG; }
       int Ro = cur.R / 32;
-      LION_LAUNCH(f.c, k_act_rows<32>, dim3(cdiv(Ro, 64), Gout, f.B), 64, 0, raw.p, dst, a.scale, a.shift, Gout, w.cout, Ro, Gd, g_off);
+      LION_LAUNCH(f.c, k_act_rows<32>, dim3(cdiv(Ro, 64), Gout, f.B), 64, 0, raw.p, dst, a.scale, a.shift, Gout, w.cout, Ro, Gd, g_off, 0);
     } else {
       PF nxt;
       float4* o; int gd, go;
       if (last) { o = dst; gd = Gd; go = g_off; }
       else { nxt = alloc_pf(f, Gout, cur.R); o = nxt.p; gd = Gout; go = 0; }
-      LION_LAUNCH(f.c, k_act_rows<1>, dim3(cdiv(cur.R, 256), Gout, f.B), 256, 0, raw.p, o, a.scale, a.shift, Gout, w.cout, cur.R, gd, go);
+      LION_LAUNCH(f.c, k_act_rows<1>, dim3(cdiv(cur.R, 256), Gout, f.B), 256, 0, raw.p, o, a.scale, a.shift, Gout, w.cout, cur.R, gd, go, last ? 0 : 1);
       cur = nxt;
     }
     LION_TRY(check_launch(f.c, "shared_mlp act"));
@@ -324,16 +324,13 @@ static int attn_fwd(Fwd& f, const AttnBlk& a, PF x, float4* dst, int Gd, int g_o
 
 static int get_vox(Fwd& f, const float4* c4, int N, int r, VoxPrep** out) {
   for (auto& v : f.vox) if (v.c4 == c4 && v.N == N && v.r == r) { *out = &v; return 0; }
-  VoxPrep v{c4, N, r, nullptr, nullptr, nullptr};
-  size_t r3 = (size_t)r * r * r;
+  VoxPrep v{c4, N, r, nullptr, nullptr, nullptr, nullptr};
+  if (N > VOXP_MAXN || r > 32) { set_error("voxelisation: N=%d (max %d) or r=%d (max 32) unsupported", N, VOXP_MAXN, r); return LION_ERR_ARG; }
   v.nc = f.c->alloc_n<float4>((size_t)f.B * N);
+  v.order = f.c->alloc_n<int>((size_t)f.B * N);
   v.ppos = f.c->alloc_n<int>((size_t)f.B * N);
-  v.inv = f.c->alloc_n<float>((size_t)f.B * N);
-  int* vidx = f.c->alloc_n<int>((size_t)f.B * N);
-  int* cnt = f.c->alloc_n<int>((size_t)f.B * r3);
-  LION_TRY(memset_async(f.c, cnt, 0, sizeof(int) * f.B * r3));
-  LION_LAUNCH(f.c, k_vox_prep, f.B, VOX_THREADS, 0, c4, v.nc, vidx, v.ppos, cnt, N, r);
-  LION_LAUNCH(f.c, k_vox_invcnt, dim3(cdiv(N, 256), f.B), 256, 0, vidx, cnt, v.inv, N, (int)r3);
+  v.len = f.c->alloc_n<int>((size_t)f.B * N);
+  LION_LAUNCH(f.c, k_vox_prep, f.B, VOXP_THREADS, 0, c4, v.nc, v.order, v.ppos, v.len, N, r);
   LION_TRY(check_launch(f.c, "vox_prep"));
   f.vox.push_back(v);
   *out = &f.vox.back();
@@ -351,7 +348,7 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   // point -> voxel scatter-mean
   float4* g_in = alloc_vg(f, Gin, r);
   LION_TRY(memset_async(f.c, g_in, 0, sizeof(float4) * (size_t)f.B * Gin * P));
-  LION_LAUNCH(f.c, k_scatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, feat.p, vp->ppos, vp->inv, g_in, Gin, N, P);
+  LION_LAUNCH(f.c, k_scatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, feat.p, vp->order, vp->ppos, vp->len, g_in, Gin, N, P);
   // conv1 -> (stats) -> AdaGN + Swish
   float4* raw1 = alloc_vg(f, Gout, r);
   double *s1, *q1;

@@ -24,6 +24,15 @@ __device__ __forceinline__ float4 f4_affine(float4 v, float4 s, float4 t) {
 __device__ __forceinline__ float4 f4_swish(float4 v) {
   return make_float4(swishf(v.x), swishf(v.y), swishf(v.z), swishf(v.w));
 }
+// round-to-nearest(-away) to TF32, the unbiased conversion cuDNN applies to tensor-core operands;
+// used where the ONLY consumer of a tensor is a tcgen05 kind::tf32 convolution (which would
+// otherwise truncate the low 13 mantissa bits, a one-sided error that accumulates over layers)
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 f4_tf32(float4 v) { return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)); }
 __device__ __forceinline__ float4 f4_max(float4 a, float4 b) {
   return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
 }
@@ -45,49 +54,123 @@ __global__ void k_make_coords(const float4* __restrict__ x, float4* __restrict__
 }
 
 // ------------------------------------------------------------------------------------
-// voxelisation prep, once per distinct (coords, r) of a forward (4 instead of 14 per step)
+// voxelisation prep, once per distinct (coords, r) of a forward (4 instead of 14 per step).
+// One CTA per shape: statistics -> normalised coords -> voxel ids -> an in-shared-memory
+// bitonic sort of (voxel id, point id) keys, which yields for every occupied voxel the list of
+// its points in ascending point order.  The scatter-mean that follows is then a plain store
+// per voxel: no atomics, no count grid, and -- unlike the reference's float atomicAdd
+// (voxelization/vox.cu:66-68) -- bit-reproducible from run to run.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(VOX_THREADS)
-k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restrict__ vidx, int* __restrict__ ppos,
-           int* __restrict__ cnt, int N, int r) {
+constexpr int VOXP_THREADS = 1024;
+constexpr int VOXP_MAXN = 4096;
+
+__global__ void __launch_bounds__(VOXP_THREADS)
+k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restrict__ s_order, int* __restrict__ s_ppos,
+           int* __restrict__ s_len, int N, int r) {
   int b = blockIdx.x;
   const float4* c = c4 + (size_t)b * N;
   __shared__ float s_stat[4];
-  vox_stats_block([&](int k, float& x, float& y, float& z) { float4 v = c[k]; x = v.x; y = v.y; z = v.z; }, N, s_stat);
+  __shared__ unsigned s_key[VOXP_MAXN];
+  // statistics with the first VOX_THREADS threads' partition of the work (vox_stats_block uses blockDim)
+  {
+    __shared__ double s_red[3][VOXP_THREADS / 32];
+    __shared__ float s_max[VOXP_THREADS / 32];
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double sx = 0, sy = 0, sz = 0;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) { float4 v = c[k]; sx += v.x; sy += v.y; sz += v.z; }
+    sx = warp_sum_d(sx); sy = warp_sum_d(sy); sz = warp_sum_d(sz);
+    if (lane == 0) { s_red[0][wid] = sx; s_red[1][wid] = sy; s_red[2][wid] = sz; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[threadIdx.x][w];
+      s_stat[threadIdx.x] = (float)(t / (double)N);
+    }
+    __syncthreads();
+    float mx = s_stat[0], my = s_stat[1], mz = s_stat[2];
+    float best = 0.0f;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      float4 v = c[k];
+      float dx = __fsub_rn(v.x, mx), dy = __fsub_rn(v.y, my), dz = __fsub_rn(v.z, mz);
+      best = fmaxf(best, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
+    }
+    best = warp_max(best);
+    if (lane == 0) s_max[wid] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, s_max[w]);
+      s_stat[3] = t;
+    }
+    __syncthreads();
+  }
   float mx = s_stat[0], my = s_stat[1], mz = s_stat[2], nrm = s_stat[3];
+  int n2 = 1;
+  while (n2 < N) n2 <<= 1;
+  int bits = 0;
+  while ((1 << bits) < n2) ++bits;                 // point-id bits
+  for (int k = threadIdx.x; k < n2; k += blockDim.x) {
+    unsigned key = 0xffffffffu;
+    if (k < N) {
+      float4 p = c[k];
+      float v[3];
+      vox_normalize(__fsub_rn(p.x, mx), __fsub_rn(p.y, my), __fsub_rn(p.z, mz), nrm, r, 1, 0.0f, v);
+      int xi = (int)rintf(v[0]), yi = (int)rintf(v[1]), zi = (int)rintf(v[2]);   // half-to-even, like torch.round
+      nc[(size_t)b * N + k] = make_float4(v[0], v[1], v[2], 0.0f);
+      key = ((unsigned)(xi * r * r + yi * r + zi) << bits) | (unsigned)k;
+    }
+    s_key[k] = key;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= n2; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned a = s_key[i], bb = s_key[ixj];
+          bool up = (i & kk) == 0;
+          if ((a > bb) == up) { s_key[i] = bb; s_key[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
   int rp = r + 2;
-  for (int k = threadIdx.x; k < N; k += blockDim.x) {
-    float4 p = c[k];
-    float v[3];
-    vox_normalize(__fsub_rn(p.x, mx), __fsub_rn(p.y, my), __fsub_rn(p.z, mz), nrm, r, 1, 0.0f, v);
-    int xi = (int)rintf(v[0]), yi = (int)rintf(v[1]), zi = (int)rintf(v[2]);   // half-to-even, like torch.round
-    int flat = xi * r * r + yi * r + zi;
-    nc[(size_t)b * N + k] = make_float4(v[0], v[1], v[2], 0.0f);
-    vidx[(size_t)b * N + k] = flat;
-    ppos[(size_t)b * N + k] = ((xi + 1) * rp + (yi + 1)) * rp + (zi + 1);
-    atomicAdd(cnt + (size_t)b * r * r * r + flat, 1);
+  unsigned mask = (1u << bits) - 1u;
+  for (int s = threadIdx.x; s < N; s += blockDim.x) {
+    unsigned key = s_key[s];
+    int vox = (int)(key >> bits);
+    bool lead = (s == 0) || ((int)(s_key[s - 1] >> bits) != vox);
+    int len = 0, pp = -1;
+    if (lead) {
+      len = 1;
+      while (s + len < N && (int)(s_key[s + len] >> bits) == vox) ++len;
+      int xi = vox / (r * r), yi = (vox / r) % r, zi = vox % r;
+      pp = ((xi + 1) * rp + (yi + 1)) * rp + (zi + 1);
+    }
+    s_order[(size_t)b * N + s] = (int)(key & mask);
+    s_ppos[(size_t)b * N + s] = pp;
+    s_len[(size_t)b * N + s] = len;
   }
 }
 
-__global__ void k_vox_invcnt(const int* __restrict__ vidx, const int* __restrict__ cnt, float* __restrict__ inv,
-                             int N, int r3) {
-  int b = blockIdx.y;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  int k = cnt[(size_t)b * r3 + vidx[(size_t)b * N + i]];
-  inv[(size_t)b * N + i] = 1.0f / (float)k;     // vox.cu:65
-}
-
-// scatter-mean of PF rows into a (pre-zeroed) VG; 16-byte vector atomics (sm_90+)
-__global__ void k_scatter(const float4* __restrict__ feat, const int* __restrict__ ppos, const float* __restrict__ inv,
-                          float4* __restrict__ grid, int G, int N, int P) {
+// scatter-mean of PF rows into a (pre-zeroed) VG: one thread per (occupied voxel, channel group)
+// sums its points in ascending point order, each term scaled by 1/count first as the
+// reference does (vox.cu:65-68), and stores once.
+__global__ void k_scatter(const float4* __restrict__ feat, const int* __restrict__ s_order, const int* __restrict__ s_ppos,
+                          const int* __restrict__ s_len, float4* __restrict__ grid, int G, int N, int P) {
   int b = blockIdx.z, g = blockIdx.y;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  float4 v = feat[((size_t)b * G + g) * N + i];
-  float s = inv[(size_t)b * N + i];
-  v = f4_scale(v, s);
-  atomicAdd(grid + ((size_t)b * G + g) * P + ppos[(size_t)b * N + i], v);
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  int pp = s_ppos[(size_t)b * N + s];
+  if (pp < 0) return;
+  int len = s_len[(size_t)b * N + s];
+  float inv = 1.0f / (float)len;
+  const float4* f = feat + ((size_t)b * G + g) * N;
+  const int* ord = s_order + (size_t)b * N + s;
+  float4 acc = f4_scale(f[ord[0]], inv);
+  for (int k = 1; k < len; ++k) acc = f4_add(acc, f4_scale(f[ord[k]], inv));
+  grid[((size_t)b * G + g) * P + pp] = acc;
 }
 
 // ------------------------------------------------------------------------------------
@@ -281,7 +364,7 @@ __global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ o
     float4 v = in[((size_t)b * G + g) * P + p];
     float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
     float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
-    r = f4_swish(f4_affine(v, s, t));
+    r = f4_tf32(f4_swish(f4_affine(v, s, t)));   // sole consumer: the second 3x3x3 convolution
   }
   out[((size_t)b * G + g) * P + p] = r;
 }
@@ -290,7 +373,7 @@ __global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ o
 // POOL > 1: max over POOL consecutive rows (neighbours of one centre) after the activation.
 template <int POOL>
 __global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
-                           const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off) {
+                           const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off, int to_tf32) {
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R_out) return;
@@ -300,6 +383,7 @@ __global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ o
   float4 r = f4_swish(f4_affine(src[0], s, t));
 #pragma unroll 4
   for (int k = 1; k < POOL; ++k) r = f4_max(r, f4_swish(f4_affine(src[k], s, t)));
+  if (to_tf32) r = f4_tf32(r);
   out[((size_t)b * Gd + g_off + g) * R_out + i] = r;
 }
 

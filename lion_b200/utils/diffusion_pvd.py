@@ -10,6 +10,8 @@ calls per step from Python).  The per-step update replays the reference's fp32 o
 order; noise is drawn with torch.randn on the same generator in
 the same order (1 + T draws per prior, the t=0 draw included).
 """
+import os
+
 import numpy as np
 import torch
 from loguru import logger
@@ -31,7 +33,7 @@ class DiffusionDiscretized(object):
         self._betas_init, self._alphas, self._alpha_bars, self._betas_post_init, self.snr = \
             self._generate_base_constants(diffusion_steps=self._diffusion_steps)
         self._tables = None
-        self.use_cuda_graph = True
+        self.use_cuda_graph = os.environ.get('LION_NO_GRAPH', '0') != '1'   # eager loop for profilers
         self.last_gpu_launches = 0
         self.total_gpu_launches = 0      # kernels of this library launched by all sampling loops so far
 
