@@ -52,14 +52,19 @@ struct Ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t aux = nullptr;     // side stream for work that is independent of the main chain (FPS)
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* base = nullptr;      // arena
+  char* zgrid = nullptr;     // persistent all-zero voxel grid (scatter target; re-zeroed after use)
+  size_t zgrid_cap = 0, zgrid_need = 0;
   size_t cap = 0;
   size_t off = 0;
   size_t peak = 0;
   bool dry = false;
   int launches = 0;          // kernels launched by the last real pass (gpu_launches evidence)
 
-  void reset() { off = 0; peak = 0; launches = 0; }
+  void reset() { off = 0; peak = 0; launches = 0; zgrid_need = 0; }
   // 256-byte aligned sub-allocation; in dry mode returns a fake non-null pointer.
   void* alloc(size_t bytes) {
     size_t a = (off + 255) & ~size_t(255);

@@ -100,6 +100,8 @@ struct Params {
   int G;                 // row tiles (accumulators) per work item
   int B;                 // shapes
   int a_stage_bytes, b_stage_bytes, stage_rows;
+  const unsigned char* occ;   // 64-row occupancy flags of the input (sparse first conv of a PVConv) or null
+  int occ_stride;
 };
 
 // per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
@@ -129,12 +131,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   float* s_stat = s_bias + 128;                 // [4 warps][2][128]
   uint64_t* bars = (uint64_t*)(s_stat + 4 * 2 * 128);
   uint32_t* s_tmem = (uint32_t*)(bars + 32);
+  volatile uint32_t* s_skip = s_tmem + 1;        // [A_STAGES] stage holds no data (all-zero input slab)
+  volatile uint32_t* s_started = s_tmem + 1 + A_STAGES;   // per item: bit j = accumulator j received MMAs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + A_STAGES);
   const uint32_t bar_full_b = smem_u32(bars + 2 * A_STAGES), bar_empty_b = smem_u32(bars + 2 * A_STAGES + B_STAGES);
   const uint32_t bar_acc = smem_u32(bars + 2 * A_STAGES + 2 * B_STAGES);
   const uint32_t bar_tfree = bar_acc + 8;       // MAX_ACC barriers: accumulator j drained by the epilogue
+  const uint32_t bar_meta = bar_tfree + 8 * MAX_ACC;   // s_started published for the item
 
   // zero the A stages once: channel-group slots that a partial chunk does not load must hold
   // finite values (their weights are zero)
@@ -143,6 +148,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 1); }
     mbar_init(bar_acc, 1);
+    mbar_init(bar_meta, 1);
     for (int i = 0; i < MAX_ACC; ++i) mbar_init(bar_tfree + 8 * i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -187,12 +193,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             for (int j = 0; j < ntile; ++j) {
               uint32_t sa = ia % A_STAGES;
               mbar_wait(bar_empty_a + 8 * sa, ((ia / A_STAGES) & 1) ^ 1);
-              mbar_expect_tx(bar_full_a + 8 * sa, bytes * kg_real);
               long long row0 = (long long)P.p_begin + (long long)(tile0 + j) * 128 + P.tg_off[tg] - P.halo;
-              const float4* src = P.in + in_b + (size_t)(cc * KG) * P.rows + row0;
-              uint32_t dst = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
-              for (int kg = 0; kg < kg_real; ++kg)
-                bulk_g2s(dst + kg * bytes, src + (size_t)kg * P.rows, bytes, bar_full_a + 8 * sa);
+              bool empty = false;
+              if (P.occ) {
+                long long lo = row0 < 0 ? 0 : row0, hi = row0 + P.stage_rows - 1;
+                if (hi > P.rows - 1) hi = P.rows - 1;
+                unsigned any = 0;
+                const unsigned char* o = P.occ + (size_t)b * P.occ_stride;
+                for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(o + k);
+                empty = (any == 0);
+              }
+              s_skip[sa] = empty ? 1u : 0u;
+              if (empty) {
+                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar_full_a + 8 * sa) : "memory");
+              } else {
+                mbar_expect_tx(bar_full_a + 8 * sa, bytes * kg_real);
+                const float4* src = P.in + in_b + (size_t)(cc * KG) * P.rows + row0;
+                uint32_t dst = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
+                for (int kg = 0; kg < kg_real; ++kg)
+                  bulk_g2s(dst + kg * bytes, src + (size_t)kg * P.rows, bytes, bar_full_a + 8 * sa);
+              }
               ++ia;
             }
           }
@@ -217,6 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         ITEM_DECODE(w)
         (void)b; (void)n0;
+        uint32_t started = 0;
         for (int cc = 0; cc < P.nchunk; ++cc) {
           for (int tg = 0; tg < P.ntg; ++tg) {
             uint32_t sb = ib % B_STAGES;
@@ -227,9 +248,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
               if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);     // accumulator j drained (previous item)
               uint32_t sa = ia % A_STAGES;
               mbar_wait(bar_full_a + 8 * sa, (ia / A_STAGES) & 1);
+              if (s_skip[sa]) {
+                // all-zero input slab: nothing to accumulate, hand the stage straight back
+                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar_empty_a + 8 * sa) : "memory");
+                ++ia;
+                continue;
+              }
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint32_t a_base16 = smem_u32(sA + (size_t)sa * P.a_stage_bytes) >> 4;
               const uint32_t d = tmem_base + (uint32_t)(j * P.NT);
+              const bool fresh = ((started >> j) & 1u) == 0;
+              started |= 1u << j;
 #pragma unroll
               for (int t = 0; t < TPG; ++t) {
 #pragma unroll
@@ -237,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
                   uint32_t alo = a_lo_c | ((a_base16 + a_off16[t] + k2 * a_pitch16) & 0x3fff);
                   uint32_t blo = b_lo_c | ((b_base16 + t * b_tap16 + k2 * b_pitch16) & 0x3fff);
                   uint64_t ad = ((uint64_t)a_hi << 32) | alo, bd = ((uint64_t)b_hi << 32) | blo;
-                  umma_tf32(d, ad, bd, idesc, (first && t == 0 && k2 == 0) ? 0u : 1u);
+                  umma_tf32(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
                 }
               }
               umma_commit(bar_empty_a + 8 * sa);     // frees the A stage when these MMAs retire
@@ -247,6 +276,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             ++ib;
           }
         }
+        *s_started = started;
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar_meta) : "memory");
         umma_commit(bar_acc);
       }
     }
@@ -260,6 +291,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       asm volatile("bar.sync 1, 128;" ::: "memory");            // previous item's s_bias / s_stat readers are done
       if (et < P.NT) s_bias[et] = P.bias ? P.bias[n0 + et] : 0.0f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(bar_meta, it & 1);
+      const uint32_t started = *s_started;
       mbar_wait(bar_acc, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // lane l: channels l, l+32, l+64, l+96
@@ -274,8 +307,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
         for (int c32 = 0; c32 < P.NT; c32 += 32) {
           float v[32];
           uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + c32);
-          tmem_ld16(taddr, v);
-          tmem_ld16(taddr + 16, v + 16);
+          if ((started >> j) & 1u) {                 // warp-uniform
+            tmem_ld16(taddr, v);
+            tmem_ld16(taddr + 16, v + 16);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;     // no occupied input near this tile: the sum is exactly zero
+          }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + s_bias[c32 + i] : 0.0f;
           if (inrange) {
@@ -437,7 +475,8 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   while (G > 1 && (long long)cdiv(ntile, G) * n_tiles_n * B < want) G >>= 1;
   P.G = G;
   P.B = B;
-  size_t smem = (size_t)tc::A_STAGES * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 4 * 2 * 128 * 4 + 32 * 8 + 16;
+  P.occ = geo.occ; P.occ_stride = geo.occ_stride;
+  size_t smem = (size_t)tc::A_STAGES * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 4 * 2 * 128 * 4 + 32 * 8 + 64;
   if (smem > 227 * 1024) { set_error("conv_tc: %zu bytes of shared memory needed", smem); return LION_ERR_ARG; }
   long long n_items = (long long)cdiv(ntile, G) * n_tiles_n * B;
   int grid = (int)(n_items < c->num_sms ? n_items : c->num_sms);      // persistent: one CTA per SM

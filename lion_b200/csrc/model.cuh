@@ -136,6 +136,8 @@ struct ConvGeom {
   int rp;        // r+2 for a VG, 0 for a PF (no halo mask)
   int rows;      // rows per (b, group): P or R
   int p_begin, p_end;
+  const unsigned char* occ;   // optional 64-row occupancy flags of the INPUT ([B][occ_stride]); null = dense
+  int occ_stride;
 };
 
 // conv_tc.cu

@@ -60,6 +60,25 @@ int ctx_reserve(Ctx* c, size_t bytes) {
   return 0;
 }
 
+// persistent zero grid: (re)allocated and zeroed outside graph capture; users keep it all-zero
+int ctx_reserve_zgrid(Ctx* c, size_t bytes) {
+  if (bytes <= c->zgrid_cap) return 0;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(c->stream, &st);
+  if (st != cudaStreamCaptureStatusNone) {
+    set_error("zero grid too small during stream capture: run one eager warm-up call first");
+    return LION_ERR_STATE;
+  }
+  LION_CHECK_CUDA(cudaDeviceSynchronize());
+  if (c->zgrid) LION_CHECK_CUDA(cudaFree(c->zgrid));
+  c->zgrid = nullptr; c->zgrid_cap = 0;
+  cudaError_t e = cudaMalloc((void**)&c->zgrid, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) for the zero grid failed: %s", bytes, cudaGetErrorString(e)); return LION_ERR_OOM; }
+  LION_CHECK_CUDA(cudaMemset(c->zgrid, 0, bytes));
+  c->zgrid_cap = bytes;
+  return 0;
+}
+
 // weight packing kernels
 __global__ void k_pack_conv_w(const float* __restrict__ w_ref, const int* __restrict__ kmap, float* __restrict__ wt,
                               int ntaps, int cin_ref, int cin_pad, int cout, int cout_pad) {
@@ -200,7 +219,7 @@ int make_fp(Model* m, FPBlk& f, Cursor& cur, int cc, int cp, const std::vector<i
 // forward-time helpers
 // =====================================================================================
 struct PF { float4* p = nullptr; int G = 0; int R = 0; };
-struct VoxPrep { const float4* c4; int N, r; float4* nc; int* order; int* ppos; int* len; };
+struct VoxPrep { const float4* c4; int N, r; float4* nc; int* order; int* ppos; int* len; unsigned char* occ; int occ_stride; };
 struct Fwd {
   Ctx* c; Model* m; int B;
   float* aff = nullptr;          // [B][style_total] all AdaGN (factor|bias) vectors of this forward
@@ -232,6 +251,7 @@ static int style_affine_all(Fwd& f, const float* style) {
 static ConvGeom geom_rows(int R) {
   ConvGeom g{};
   g.ntaps = 1; g.off[0] = 0; g.rp = 0; g.rows = R; g.p_begin = 0; g.p_end = R;
+  g.occ = nullptr; g.occ_stride = 0;
   return g;
 }
 static ConvGeom geom_grid(int r) {
@@ -241,6 +261,7 @@ static ConvGeom geom_grid(int r) {
   for (int kx = 0; kx < 3; ++kx) for (int ky = 0; ky < 3; ++ky) for (int kz = 0; kz < 3; ++kz)
     g.off[(kx * 3 + ky) * 3 + kz] = (kx - 1) * rp * rp + (ky - 1) * rp + (kz - 1);
   g.p_begin = rp * rp; g.p_end = (rp - 1) * rp * rp;
+  g.occ = nullptr; g.occ_stride = 0;
   return g;
 }
 
@@ -324,13 +345,17 @@ static int attn_fwd(Fwd& f, const AttnBlk& a, PF x, float4* dst, int Gd, int g_o
 
 static int get_vox(Fwd& f, const float4* c4, int N, int r, VoxPrep** out) {
   for (auto& v : f.vox) if (v.c4 == c4 && v.N == N && v.r == r) { *out = &v; return 0; }
-  VoxPrep v{c4, N, r, nullptr, nullptr, nullptr, nullptr};
+  VoxPrep v{c4, N, r, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
   if (N > VOXP_MAXN || r > 32) { set_error("voxelisation: N=%d (max %d) or r=%d (max 32) unsupported", N, VOXP_MAXN, r); return LION_ERR_ARG; }
   v.nc = f.c->alloc_n<float4>((size_t)f.B * N);
   v.order = f.c->alloc_n<int>((size_t)f.B * N);
   v.ppos = f.c->alloc_n<int>((size_t)f.B * N);
   v.len = f.c->alloc_n<int>((size_t)f.B * N);
-  LION_LAUNCH(f.c, k_vox_prep, f.B, VOXP_THREADS, 0, c4, v.nc, v.order, v.ppos, v.len, N, r);
+  int P = (r + 2) * (r + 2) * (r + 2);
+  v.occ_stride = (P + 63) / 64 + 4;
+  v.occ = f.c->alloc_n<unsigned char>((size_t)f.B * v.occ_stride);
+  LION_TRY(memset_async(f.c, v.occ, 0, (size_t)f.B * v.occ_stride));
+  LION_LAUNCH(f.c, k_vox_prep, f.B, VOXP_THREADS, 0, c4, v.nc, v.order, v.ppos, v.len, v.occ, v.occ_stride, N, r);
   LION_TRY(check_launch(f.c, "vox_prep"));
   f.vox.push_back(v);
   *out = &f.vox.back();
@@ -345,15 +370,19 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   LION_TRY(get_vox(f, c4, N, r, &vp));
   size_t mk = f.c->mark();
   ConvGeom geo = geom_grid(r);
-  // point -> voxel scatter-mean
-  float4* g_in = alloc_vg(f, Gin, r);
-  LION_TRY(memset_async(f.c, g_in, 0, sizeof(float4) * (size_t)f.B * Gin * P));
+  // point -> voxel scatter-mean into the context's persistent all-zero grid (no per-call memset)
+  size_t zbytes = sizeof(float4) * ((size_t)f.B * Gin * P + 2 * ((size_t)rp * rp + rp + 8));
+  if (zbytes > f.c->zgrid_need) f.c->zgrid_need = zbytes;
+  float4* g_in = f.c->dry ? (float4*)(uintptr_t)0x1000 : (float4*)f.c->zgrid + ((size_t)rp * rp + rp + 8);
   LION_LAUNCH(f.c, k_scatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, feat.p, vp->order, vp->ppos, vp->len, g_in, Gin, N, P);
-  // conv1 -> (stats) -> AdaGN + Swish
+  // conv1 (sparse input: empty 64-row blocks are skipped) -> (stats) -> AdaGN + Swish
   float4* raw1 = alloc_vg(f, Gout, r);
   double *s1, *q1;
   LION_TRY(alloc_stats(f, p.c1.cout_pad, &s1, &q1));
-  LION_TRY(run_conv(f, p.c1, g_in, Gin, raw1, Gout, s1, q1, geo));
+  ConvGeom geo1 = geo;
+  geo1.occ = vp->occ; geo1.occ_stride = vp->occ_stride;
+  LION_TRY(run_conv(f, p.c1, g_in, Gin, raw1, Gout, s1, q1, geo1));
+  LION_LAUNCH(f.c, k_unscatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, vp->ppos, g_in, Gin, N, P);
   Affine a1;
   double V = (double)r * r * r;
   LION_TRY(run_affine(f, p.g1, s1, q1, p.c1.cout_pad, V, nullptr, nullptr, a1));
@@ -397,14 +426,20 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
 }
 
 // SA module: (features PF, coords) -> (dst PF with Gd groups at g_off, centres C4)
-static int sa_fwd(Fwd& f, const SABlk& s, PF feat, const float4* c4, float4* centers, float4* dst, int Gd, int g_off) {
+// pre_fps >= 0: the centres were already sampled on the side stream (event ev[pre_fps])
+static int sa_fwd(Fwd& f, const SABlk& s, PF feat, const float4* c4, float4* centers, float4* dst, int Gd, int g_off,
+                  int pre_fps = -1) {
   int N = feat.R, M = s.m, U = s.k, Gf = s.cfeat / 4;
   if (feat.G != Gf) { set_error("SA: got %d feature channels, expected %d", feat.G * 4, s.cfeat); return LION_ERR_ARG; }
   if (N > FPS_THREADS * FPS_MAX_PER_THREAD) { set_error("SA: N=%d too large for FPS", N); return LION_ERR_ARG; }
   if (M > N) { set_error("SA: more centres (%d) than points (%d)", M, N); return LION_ERR_ARG; }
   size_t mk = f.c->mark();
-  int* fidx = f.c->alloc_n<int>((size_t)f.B * M);
-  LION_LAUNCH(f.c, k_fps_c4, f.B, FPS_THREADS, 0, c4, fidx, centers, N, M);
+  if (pre_fps >= 0) {
+    if (!f.c->dry) LION_CHECK_CUDA(cudaStreamWaitEvent(f.c->stream, f.c->ev[pre_fps], 0));
+  } else {
+    int* fidx = f.c->alloc_n<int>((size_t)f.B * M);
+    LION_LAUNCH(f.c, k_fps_c4, f.B, FPS_THREADS, 0, c4, fidx, centers, N, M);
+  }
   int* nidx = f.c->alloc_n<int>((size_t)f.B * M * U);
   float r2 = s.radius * s.radius;
   LION_LAUNCH(f.c, k_ball_query_c4, dim3(cdiv(M * 32, 256), f.B), 256, 0, centers, c4, nidx, N, M, r2, U);
@@ -581,6 +616,30 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   float4* c0 = c->alloc_n<float4>((size_t)B * N);
   LION_LAUNCH(c, k_make_coords, cdiv(B * N, 256), 256, 0, (const float4*)x, c0, B * N);
   PF feat; feat.p = (float4*)x; feat.G = 1; feat.R = N;
+  // furthest-point sampling of all levels depends on coordinates only: a chain of 1360 latency-
+  // bound rounds on 32 SMs.  Fork it onto the side stream so it hides under the first PVConvs.
+  std::vector<float4*> fps_centers(n_sa, nullptr);
+  {
+    const float4* src = c0;
+    int ncur = N;
+    if (!c->dry) {
+      LION_CHECK_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+      LION_CHECK_CUDA(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+    }
+    for (int i = 0; i < n_sa && i < 8; ++i) {
+      const SABlk& sb = u.sa[i].back().sa;
+      if (ncur > FPS_THREADS * FPS_MAX_PER_THREAD || sb.m > ncur) { set_error("unet: FPS sizes unsupported"); return LION_ERR_ARG; }
+      fps_centers[i] = c->alloc_n<float4>((size_t)B * sb.m);
+      int* fidx = c->alloc_n<int>((size_t)B * sb.m);
+      if (!c->dry) {
+        k_fps_c4<<<B, FPS_THREADS, 0, c->aux>>>(src, fidx, fps_centers[i], ncur, sb.m);
+        c->launches++;
+        LION_CHECK_CUDA(cudaEventRecord(c->ev[i], c->aux));
+      }
+      src = fps_centers[i];
+      ncur = sb.m;
+    }
+  }
   const float4* coords = c0;
   int Ncur = N;
   bool has_t = temb != nullptr;
@@ -601,8 +660,8 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
         feat = o;
       } else {
         PF o = alloc_pf(f, blk.sa.mlp.cout() / 4, blk.sa.m);
-        float4* ctr = c->alloc_n<float4>((size_t)B * blk.sa.m);
-        LION_TRY(sa_fwd(f, blk.sa, feat, coords, ctr, o.p, o.G, 0));
+        float4* ctr = fps_centers[i];
+        LION_TRY(sa_fwd(f, blk.sa, feat, coords, ctr, o.p, o.G, 0, i));
         feat = o; coords = ctr; Ncur = blk.sa.m;
       }
     }
@@ -660,7 +719,10 @@ static int two_pass(Model* m, void* stream, int B, F body) {
     Fwd f{c, m, B};
     int rc = body(f);
     if (rc) { c->dry = false; return rc; }
-    if (pass == 0) LION_TRY(ctx_reserve(c, c->peak));
+    if (pass == 0) {
+      LION_TRY(ctx_reserve(c, c->peak));
+      LION_TRY(ctx_reserve_zgrid(c, c->zgrid_need));
+    }
   }
   return 0;
 }
@@ -686,6 +748,9 @@ extern "C" int lion_ctx_create(int device, LionCtx** out) {
   cudaDeviceProp prop;
   LION_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   h->c.num_sms = prop.multiProcessorCount;
+  LION_CHECK_CUDA(cudaStreamCreateWithFlags(&h->c.aux, cudaStreamNonBlocking));
+  LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev[i], cudaEventDisableTiming));
   if (prop.major != 10) {
     set_error("lion_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
     delete h;
@@ -697,6 +762,10 @@ extern "C" int lion_ctx_create(int device, LionCtx** out) {
 extern "C" int lion_ctx_destroy(LionCtx* h) {
   if (!h) return 0;
   if (h->c.base) cudaFree(h->c.base);
+  if (h->c.zgrid) cudaFree(h->c.zgrid);
+  if (h->c.aux) cudaStreamDestroy(h->c.aux);
+  if (h->c.ev_fork) cudaEventDestroy(h->c.ev_fork);
+  for (int i = 0; i < 8; ++i) if (h->c.ev[i]) cudaEventDestroy(h->c.ev[i]);
   delete h;
   return 0;
 }

@@ -66,7 +66,7 @@ constexpr int VOXP_MAXN = 4096;
 
 __global__ void __launch_bounds__(VOXP_THREADS)
 k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restrict__ s_order, int* __restrict__ s_ppos,
-           int* __restrict__ s_len, int N, int r) {
+           int* __restrict__ s_len, unsigned char* __restrict__ occ, int occ_stride, int N, int r) {
   int b = blockIdx.x;
   const float4* c = c4 + (size_t)b * N;
   __shared__ float s_stat[4];
@@ -147,6 +147,7 @@ k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restri
       while (s + len < N && (int)(s_key[s + len] >> bits) == vox) ++len;
       int xi = vox / (r * r), yi = (vox / r) % r, zi = vox % r;
       pp = ((xi + 1) * rp + (yi + 1)) * rp + (zi + 1);
+      occ[(size_t)b * occ_stride + (pp >> 6)] = 1;       // 64-row occupancy flags (pre-zeroed) for the sparse-input conv
     }
     s_order[(size_t)b * N + s] = (int)(key & mask);
     s_ppos[(size_t)b * N + s] = pp;
@@ -171,6 +172,16 @@ __global__ void k_scatter(const float4* __restrict__ feat, const int* __restrict
   float4 acc = f4_scale(f[ord[0]], inv);
   for (int k = 1; k < len; ++k) acc = f4_add(acc, f4_scale(f[ord[k]], inv));
   grid[((size_t)b * G + g) * P + pp] = acc;
+}
+
+// restore the all-zero invariant of the persistent scatter grid: zero exactly the voxels that
+// k_scatter wrote (N*G stores instead of a full-grid memset per PVConv)
+__global__ void k_unscatter(const int* __restrict__ s_ppos, float4* __restrict__ grid, int G, int N, int P) {
+  int b = blockIdx.z, g = blockIdx.y;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  int pp = s_ppos[(size_t)b * N + s];
+  if (pp >= 0) grid[((size_t)b * G + g) * P + pp] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------

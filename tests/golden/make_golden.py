@@ -145,6 +145,7 @@ def main():
             xT_l=noise_l[0].numpy(), z_l=torch.stack(noise_l[1]).numpy(),
             out_g=z_g.numpy(), out_l=z_l.numpy(), image=img.numpy(),
             traj_l=torch.stack(lst_l["pred_x"]).numpy()[:, 0, :64, 0, 0],
+            traj_full=torch.stack(lst_l["pred_x"]).numpy()[:, 0, :, 0, 0].astype(np.float32),
             betas=diff10._betas_init.numpy(), alpha_bars=diff10._alpha_bars.numpy())
         print("ddpm10", float(z_g.abs().mean()), float(z_l.abs().mean()), float(img.abs().mean()))
 
