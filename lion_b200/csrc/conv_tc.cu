@@ -29,8 +29,8 @@
 namespace lion {
 namespace tc {
 
-constexpr int THREADS = 192;
-constexpr int A_STAGES = 3;
+constexpr int THREADS = 224;       // warp 0 producer, warps 1-2 MMA issuers (even / odd row tiles), warps 3-6 epilogue
+constexpr int MAX_A_STAGES = 16;   // the A ring is as deep as shared memory allows (Params::a_stages)
 constexpr int B_STAGES = 2;
 constexpr int MAX_ACC = 8;
 
@@ -64,6 +64,23 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Warp-uniform issue: every lane executes these with identical operands and elect.sync picks
+// the issuing lane inside the asm.  Keeping the surrounding control flow warp-uniform lets the
+// compiler hold descriptors / loop counters in uniform registers (a divergent `if (lane == 0)`
+// around tcgen05 instructions costs an R2UR + ELECT/BRA.U.ANY sequence per MMA).
+__device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p, q;\nelect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"
+               "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t bar) {
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_w(uint32_t bar) {
+  asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
+               "@q mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n}" ::"r"(bar) : "memory");
 }
 // no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -100,6 +117,7 @@ struct Params {
   int G;                 // row tiles (accumulators) per work item
   int B;                 // shapes
   int a_stage_bytes, b_stage_bytes, stage_rows;
+  int a_stages;          // depth of the A ring
   const unsigned char* occ;   // 64-row occupancy flags of the input (sparse first conv of a PVConv) or null
   int occ_stride;
 };
@@ -126,18 +144,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   // layout: [A stages][B stages][bias NT floats][stat 4*2*128 floats][barriers][tmem ptr]
   uint8_t* sA = smem;
+  const int A_STAGES = P.a_stages;
   uint8_t* sB = sA + (size_t)A_STAGES * P.a_stage_bytes;
   float* s_bias = (float*)(sB + (size_t)B_STAGES * P.b_stage_bytes);
   float* s_stat = s_bias + 128;                 // [4 warps][2][128]
   uint64_t* bars = (uint64_t*)(s_stat + 4 * 2 * 128);
-  uint32_t* s_tmem = (uint32_t*)(bars + 32);
-  volatile uint32_t* s_skip = s_tmem + 1;        // [A_STAGES] stage holds no data (all-zero input slab)
-  volatile uint32_t* s_started = s_tmem + 1 + A_STAGES;   // per item: bit j = accumulator j received MMAs
+  uint32_t* s_tmem = (uint32_t*)(bars + 64);
+  volatile uint32_t* s_skip = s_tmem + 1;        // [MAX_A_STAGES] stage holds no data (all-zero input slab)
+  volatile uint32_t* s_started = s_tmem + 1 + MAX_A_STAGES;   // per item: bit j = accumulator j received MMAs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  const uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + A_STAGES);
-  const uint32_t bar_full_b = smem_u32(bars + 2 * A_STAGES), bar_empty_b = smem_u32(bars + 2 * A_STAGES + B_STAGES);
-  const uint32_t bar_acc = smem_u32(bars + 2 * A_STAGES + 2 * B_STAGES);
+  const uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + MAX_A_STAGES);
+  const uint32_t bar_full_b = smem_u32(bars + 2 * MAX_A_STAGES), bar_empty_b = smem_u32(bars + 2 * MAX_A_STAGES + B_STAGES);
+  const uint32_t bar_acc = smem_u32(bars + 2 * MAX_A_STAGES + 2 * B_STAGES);
   const uint32_t bar_tfree = bar_acc + 8;       // MAX_ACC barriers: accumulator j drained by the epilogue
   const uint32_t bar_meta = bar_tfree + 8 * MAX_ACC;   // s_started published for the item
 
@@ -146,9 +165,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   for (int i = tid; i < A_STAGES * P.a_stage_bytes / 16; i += THREADS) ((float4*)sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 1); }
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 1); }
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_meta, 1);
+    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 2); }
+    mbar_init(bar_acc, 2);
+    mbar_init(bar_meta, 2);
     for (int i = 0; i < MAX_ACC; ++i) mbar_init(bar_tfree + 8 * i, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -174,33 +193,31 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   if (warp == 0) {
     // ===================== producer =====================
     if (lane == 0) {
-      uint32_t ia = 0, ib = 0;          // running stage counters
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;          // ring positions and phase bits
       const uint32_t bytes = (uint32_t)P.stage_rows * 16u;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         ITEM_DECODE(w)
         (void)n0;
         const size_t in_b = (size_t)b * P.Gin * P.rows;
         const float* wsrc = P.w + (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);
+        const unsigned char* occ_b = P.occ ? P.occ + (size_t)b * P.occ_stride : nullptr;
         for (int cc = 0; cc < P.nchunk; ++cc) {
           int kg_real = min(KG, P.Gin - cc * KG);
           for (int tg = 0; tg < P.ntg; ++tg) {
-            uint32_t sb = ib % B_STAGES;
-            mbar_wait(bar_empty_b + 8 * sb, ((ib / B_STAGES) & 1) ^ 1);
+            mbar_wait(bar_empty_b + 8 * sb, pb ^ 1);
             mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
             bulk_g2s(smem_u32(sB + (size_t)sb * P.b_stage_bytes), wsrc + (size_t)(cc * P.ntg + tg) * (P.b_stage_bytes / 4),
                      P.b_stage_bytes, bar_full_b + 8 * sb);
-            ++ib;
-            for (int j = 0; j < ntile; ++j) {
-              uint32_t sa = ia % A_STAGES;
-              mbar_wait(bar_empty_a + 8 * sa, ((ia / A_STAGES) & 1) ^ 1);
-              long long row0 = (long long)P.p_begin + (long long)(tile0 + j) * 128 + P.tg_off[tg] - P.halo;
+            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+            long long row0 = (long long)P.p_begin + (long long)tile0 * 128 + P.tg_off[tg] - P.halo;
+            for (int j = 0; j < ntile; ++j, row0 += 128) {
+              mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
               bool empty = false;
-              if (P.occ) {
+              if (occ_b) {
                 long long lo = row0 < 0 ? 0 : row0, hi = row0 + P.stage_rows - 1;
                 if (hi > P.rows - 1) hi = P.rows - 1;
                 unsigned any = 0;
-                const unsigned char* o = P.occ + (size_t)b * P.occ_stride;
-                for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(o + k);
+                for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(occ_b + k);
                 empty = (any == 0);
               }
               s_skip[sa] = empty ? 1u : 0u;
@@ -213,78 +230,84 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
                 for (int kg = 0; kg < kg_real; ++kg)
                   bulk_g2s(dst + kg * bytes, src + (size_t)kg * P.rows, bytes, bar_full_a + 8 * sa);
               }
-              ++ia;
+              if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: warp 1 owns even row tiles, warp 2 odd ones ==========
+    // (each whole warp runs the loop; one elected lane issues).  Two issuers because a single
+    // thread cannot generate descriptors + issue one UMMA every 16-32 cycles (N <= 64).
+    {
+      const int me = warp - 1;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t a_pitch16 = (uint32_t)P.stage_rows;             // (bytes between channel groups) >> 4
       const uint32_t b_pitch16 = (uint32_t)P.NT;
       const uint32_t b_tap16 = (uint32_t)KG * b_pitch16;
-      // descriptor high words are constant: LBO = group pitch, SBO = 128 B, version 1, no swizzle
-      const uint32_t a_hi = (128u >> 4) | (1u << 14);
-      const uint32_t b_hi = a_hi;
+      // descriptor high words are constant: SBO = 128 B, version 1, no swizzle; LBO = group pitch
+      const uint32_t d_hi = (128u >> 4) | (1u << 14);
       const uint32_t a_lo_c = (a_pitch16 & 0x3fff) << 16, b_lo_c = (b_pitch16 & 0x3fff) << 16;
-      uint32_t a_off16[TPG];
-#pragma unroll
-      for (int t = 0; t < TPG; ++t) a_off16[t] = (uint32_t)(P.halo + P.tap_off[t]);
-      uint32_t ia = 0, ib = 0, it = 0;
+      const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4;
+      const uint32_t a_ring16 = (smem_u32(sA) >> 4) + (uint32_t)P.halo;
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
         ITEM_DECODE(w)
-        (void)b; (void)n0;
+        (void)b; (void)n0; (void)tile0;
         uint32_t started = 0;
         for (int cc = 0; cc < P.nchunk; ++cc) {
           for (int tg = 0; tg < P.ntg; ++tg) {
-            uint32_t sb = ib % B_STAGES;
-            mbar_wait(bar_full_b + 8 * sb, (ib / B_STAGES) & 1);
+            mbar_wait(bar_full_b + 8 * sb, pb);
             const uint32_t b_base16 = smem_u32(sB + (size_t)sb * P.b_stage_bytes) >> 4;
             const bool first = (cc | tg) == 0;
             for (int j = 0; j < ntile; ++j) {
+              const uint32_t my_sa = sa, my_pa = pa;
+              if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
+              if ((j & 1) != me) continue;                               // the other issuer's tile
               if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);     // accumulator j drained (previous item)
-              uint32_t sa = ia % A_STAGES;
-              mbar_wait(bar_full_a + 8 * sa, (ia / A_STAGES) & 1);
-              if (s_skip[sa]) {
+              mbar_wait(bar_full_a + 8 * my_sa, my_pa);
+              if (s_skip[my_sa]) {
                 // all-zero input slab: nothing to accumulate, hand the stage straight back
-                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar_empty_a + 8 * sa) : "memory");
-                ++ia;
+                mbar_arrive_w(bar_empty_a + 8 * my_sa);
                 continue;
               }
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t a_base16 = smem_u32(sA + (size_t)sa * P.a_stage_bytes) >> 4;
+              const uint32_t a_base16 = a_ring16 + my_sa * a_stage16;
               const uint32_t d = tmem_base + (uint32_t)(j * P.NT);
               const bool fresh = ((started >> j) & 1u) == 0;
               started |= 1u << j;
 #pragma unroll
               for (int t = 0; t < TPG; ++t) {
+                const uint32_t a_t = a_base16 + (uint32_t)P.tap_off[t];
+                const uint32_t b_t = b_base16 + t * b_tap16;
 #pragma unroll
                 for (int k2 = 0; k2 < KG; k2 += 2) {
-                  uint32_t alo = a_lo_c | ((a_base16 + a_off16[t] + k2 * a_pitch16) & 0x3fff);
-                  uint32_t blo = b_lo_c | ((b_base16 + t * b_tap16 + k2 * b_pitch16) & 0x3fff);
-                  uint64_t ad = ((uint64_t)a_hi << 32) | alo, bd = ((uint64_t)b_hi << 32) | blo;
-                  umma_tf32(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
+                  uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
+                  uint32_t blo = b_lo_c | ((b_t + k2 * b_pitch16) & 0x3fff);
+                  uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
+                  umma_tf32_w(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
                 }
               }
-              umma_commit(bar_empty_a + 8 * sa);     // frees the A stage when these MMAs retire
-              ++ia;
+              umma_commit_w(bar_empty_a + 8 * my_sa);     // frees the A stage when these MMAs retire
             }
-            umma_commit(bar_empty_b + 8 * sb);
-            ++ib;
+            umma_commit_w(bar_empty_b + 8 * sb);          // (count 2: both issuers)
+            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
           }
         }
-        *s_started = started;
-        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar_meta) : "memory");
-        umma_commit(bar_acc);
+        if (lane == 0) s_started[me] = started;
+        __syncwarp();
+        mbar_arrive_w(bar_meta);
+        umma_commit_w(bar_acc);
+        // keep the two issuers in the same item: the count-2 barriers above identify arrivals by
+        // number, not by warp, so an idle issuer must not run ahead into the next item
+        asm volatile("bar.sync 2, 64;" ::: "memory");
       }
     }
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    const int ew = warp - 2, et = tid - 64;
+    const int ew = warp - 3, et = tid - 96;
     uint32_t it = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       ITEM_DECODE(w)
@@ -292,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       if (et < P.NT) s_bias[et] = P.bias ? P.bias[n0 + et] : 0.0f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(bar_meta, it & 1);
-      const uint32_t started = *s_started;
+      const uint32_t started = s_started[0] | s_started[1];
       mbar_wait(bar_acc, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // lane l: channels l, l+32, l+64, l+96
@@ -407,7 +430,9 @@ static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, in
   ntg = w.ntaps == 27 ? 3 : 1;
   tpg = w.ntaps == 27 ? 9 : 1;
   int G = w.cin_pad / 4;
-  if (w.ntaps == 27) KG = (NT > 64) ? 4 : 8;     // keep two 9-tap weight stages within shared memory
+  // 16-channel chunks for the 3x3x3 case: a 9-tap weight slab is then <= 72 KB, two of them fit
+  // next to a deep (>= 6 stage) ring of activation slabs; the 1x1 case uses 32-channel chunks
+  if (w.ntaps == 27) KG = (NT >= 64) ? 4 : 8;
   else KG = 8;
   if (G < KG) KG = (G <= 2) ? 2 : ((G <= 4) ? 4 : 8);
   nchunk = (G + KG - 1) / KG;
@@ -476,7 +501,13 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   P.G = G;
   P.B = B;
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
-  size_t smem = (size_t)tc::A_STAGES * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 4 * 2 * 128 * 4 + 32 * 8 + 64;
+  const size_t fixed = 128 * 4 + 4 * 2 * 128 * 4 + 64 * 8 + 128;
+  long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
+  int a_stages = (int)(room / P.a_stage_bytes);
+  if (a_stages > tc::MAX_A_STAGES) a_stages = tc::MAX_A_STAGES;
+  if (a_stages < 2) { set_error("conv_tc: shared memory cannot hold the operand pipeline (N=%d, KG=%d)", NT, KG); return LION_ERR_ARG; }
+  P.a_stages = a_stages;
+  size_t smem = (size_t)a_stages * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 4 * 2 * 128 * 4 + 64 * 8 + 128;
   if (smem > 227 * 1024) { set_error("conv_tc: %zu bytes of shared memory needed", smem); return LION_ERR_ARG; }
   long long n_items = (long long)cdiv(ntile, G) * n_tiles_n * B;
   int grid = (int)(n_items < c->num_sms ? n_items : c->num_sms);      // persistent: one CTA per SM
