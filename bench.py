@@ -278,6 +278,21 @@ def main():
         e2e = {"value": world * B * n_e2e / dt.item(), "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "note": "x_T and every per-step noise tensor of both priors come from pinned host memory; generated points are read back"}
 
+    # ---- phase breakdown (one extra pass, CUDA events; diagnostic only) -------------------------
+    phases = None
+    if rank == 0 or world == 1:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.manual_seed(4242)
+        ev[0].record()
+        z_g, _ = diff.run_denoising_diffusion(dae[0], B, shape[0])
+        ev[1].record()
+        z_l, _ = diff.run_denoising_diffusion(dae[1], B, shape[1], condition_input=vae.global2style(z_g))
+        ev[2].record()
+        vae.sample(num_samples=B, decomposed_eps=vae.decompose_eps(vae.compose_eps([z_g, z_l])))
+        ev[3].record()
+        torch.cuda.synchronize(dev)
+        phases = {"global_prior_loop_ms": ev[0].elapsed_time(ev[1]), "local_prior_loop_ms": ev[1].elapsed_time(ev[2]),
+                  "decoder_ms": ev[2].elapsed_time(ev[3])}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -318,7 +333,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch,
             "ms_per_denoise_step_pair": ms / args.steps / T,
             "tensor_roofline_frac_whole_job": value * GFLOP_PER_SHAPE / 1e3 / world / (bf16_peak / 2.0),
-            "roofline": roofline, "cpu_baseline": cpu}
+            "phases": phases, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

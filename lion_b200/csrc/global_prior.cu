@@ -12,12 +12,14 @@
 
 namespace lion {
 
-constexpr int GP_MAXB = 64;     // rows handled per call
-constexpr int GP_BT = 32;       // batch rows per pass (one accumulator per row and output)
-constexpr int GP_KT = 512;      // K tile staged in shared memory
-constexpr int GP_PITCH = GP_KT + 4;
-constexpr int GP_CO = 2;        // outputs per warp
+constexpr int GP_MAXB = 32;     // rows (shapes) per call
+constexpr int GP_BT = 32;
+constexpr int GP_KS = 256;      // K slice per block (split-K)
+constexpr int GP_PITCH = GP_KS + 4;
 constexpr int GP_WARPS = 8;
+constexpr int GP_OW = 16;       // outputs per warp (processed two at a time)
+constexpr int GP_OB = GP_WARPS * GP_OW;   // 128 outputs per block
+constexpr int GP_MAXSPLIT = 16;
 
 __device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
 #pragma unroll
@@ -33,94 +35,110 @@ __device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
   return v[0];
 }
 
-// out[b][o] = epi( sum_k W[o][k] * (x[b][k] + add[b][k]) + bias[o] )
-//   act: 0 none, 1 relu, 2 sigmoid;  mul: result *= mul[b][o] (SE gate);  res: result += res[b][o]
-// W is [O][K] row-major (a 1x1 conv weight), K % 4 == 0.  Each warp owns GP_CO output rows and
-// streams them with 128-bit loads that are issued one K tile ahead (software pipelined, 8 loads
-// in flight per lane); the x tile of all <=32 batch rows sits in shared memory and every
-// 128-bit shared load feeds 8 FMAs.  Lane l ends up with the dot product of batch row l
-// (butterfly transpose-reduce), so the epilogue is one store per lane.
-__global__ void __launch_bounds__(GP_WARPS * 32)
-k_gp_linear(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x, int x_stride,
-            const float* __restrict__ add, int add_stride, float* __restrict__ out, int out_stride,
-            const float* __restrict__ mul, int mul_stride, const float* __restrict__ res, int res_stride,
-            int B, int K, int O, int act) {
-  extern __shared__ __align__(16) float s_x[];      // [GP_BT][GP_PITCH]
+// Split-K skinny GEMM, phase 1:  part[ks][b][o] = sum_{k in slice ks} W[o][k] * (x[b][k] + add[b][k])
+// grid = (O/128, K/256).  The block stages ITS 256-wide slice of all <=32 activation rows once
+// (32 KB; with one block per output group and the full K, 128 SMs re-read the same 256 KB of
+// activations from L2 per K tile, which is what bounded the first version), then every warp
+// streams 16 weight rows x 256 columns with 128-bit loads issued one row pair ahead; each
+// 128-bit shared-memory read of x feeds 8 FMAs.  Deterministic: partials are summed in a
+// fixed order by k_gp_reduce.
+__global__ void __launch_bounds__(GP_WARPS * 32, 2)
+k_gp_partial(const float* __restrict__ W, const float* __restrict__ x, int x_stride, const float* __restrict__ add,
+             int add_stride, float* __restrict__ part, int B, int K, int O) {
+  __shared__ __align__(16) float s_x[GP_BT * GP_PITCH];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int o0 = (blockIdx.x * GP_WARPS + wid) * GP_CO;
-  const int ntile = (K + GP_KT - 1) / GP_KT;
-  for (int b0 = 0; b0 < B; b0 += GP_BT) {
-    const int nb = min(GP_BT, B - b0);
-    float acc[GP_CO][GP_BT];
+  const int k0 = blockIdx.y * GP_KS, kt = min(GP_KS, K - k0);
+  const int o_base = blockIdx.x * GP_OB + wid * GP_OW;
+  // stage x slice (+ add): 8 independent 128-bit loads per thread
+  {
+    constexpr int PER_THREAD = GP_BT * (GP_KS / 4) / (GP_WARPS * 32);      // 8
+    float4 v[PER_THREAD];
 #pragma unroll
-    for (int c = 0; c < GP_CO; ++c)
-#pragma unroll
-      for (int b = 0; b < GP_BT; ++b) acc[c][b] = 0.0f;
-    float4 wn[GP_CO][4];
-    auto load_w = [&](int tile) {
-#pragma unroll
-      for (int c = 0; c < GP_CO; ++c)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int k = tile * GP_KT + (lane + 32 * i) * 4;
-          wn[c][i] = (o0 + c < O && k < K) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(o0 + c) * K + k))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    load_w(0);
-    for (int tile = 0; tile < ntile; ++tile) {
-      const int k0 = tile * GP_KT, kt = min(GP_KT, K - k0);
-      __syncthreads();
-      for (int i = threadIdx.x; i < GP_BT * (GP_KT / 4); i += blockDim.x) {
-        int b = i / (GP_KT / 4), k4 = i % (GP_KT / 4);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (b < nb && k4 * 4 < kt) {
-          v = *reinterpret_cast<const float4*>(x + (size_t)(b0 + b) * x_stride + k0 + k4 * 4);
-          if (add) {
-            float4 a = *reinterpret_cast<const float4*>(add + (size_t)(b0 + b) * add_stride + k0 + k4 * 4);
-            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-          }
-        }
-        *reinterpret_cast<float4*>(s_x + b * GP_PITCH + k4 * 4) = v;
-      }
-      __syncthreads();
-      float4 wc[GP_CO][4];
-#pragma unroll
-      for (int c = 0; c < GP_CO; ++c)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) wc[c][i] = wn[c][i];
-      if (tile + 1 < ntile) load_w(tile + 1);                 // in flight while this tile is consumed
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float* xr = s_x + (lane + 32 * i) * 4;
-#pragma unroll
-        for (int b = 0; b < GP_BT; ++b) {
-          float4 xv = *reinterpret_cast<const float4*>(xr + b * GP_PITCH);
-#pragma unroll
-          for (int c = 0; c < GP_CO; ++c) {
-            acc[c][b] = fmaf(wc[c][i].x, xv.x, acc[c][b]);
-            acc[c][b] = fmaf(wc[c][i].y, xv.y, acc[c][b]);
-            acc[c][b] = fmaf(wc[c][i].z, xv.z, acc[c][b]);
-            acc[c][b] = fmaf(wc[c][i].w, xv.w, acc[c][b]);
-          }
+    for (int u = 0; u < PER_THREAD; ++u) {
+      int i = threadIdx.x + u * (GP_WARPS * 32);
+      int b = i / (GP_KS / 4), k4 = i % (GP_KS / 4);
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < B && k4 * 4 < kt) {
+        v[u] = *reinterpret_cast<const float4*>(x + (size_t)b * x_stride + k0 + k4 * 4);
+        if (add) {
+          float4 a = *reinterpret_cast<const float4*>(add + (size_t)b * add_stride + k0 + k4 * 4);
+          v[u].x += a.x; v[u].y += a.y; v[u].z += a.z; v[u].w += a.w;
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c < GP_CO; ++c) {
-      float v = warp_transpose_sum32(acc[c], lane);            // lane l: batch row l
-      int o = o0 + c;
-      if (lane < nb && o < O) {
-        int b = b0 + lane;
-        v += bias ? bias[o] : 0.0f;
-        if (act == 1) v = fmaxf(v, 0.0f);
-        else if (act == 2) v = 1.0f / (1.0f + expf(-v));
-        if (mul) v *= mul[(size_t)b * mul_stride + o];
-        if (res) v += res[(size_t)b * res_stride + o];
-        out[(size_t)b * out_stride + o] = v;
-      }
+    for (int u = 0; u < PER_THREAD; ++u) {
+      int i = threadIdx.x + u * (GP_WARPS * 32);
+      int b = i / (GP_KS / 4), k4 = i % (GP_KS / 4);
+      *reinterpret_cast<float4*>(s_x + b * GP_PITCH + k4 * 4) = v[u];
     }
   }
+  float4 wn[2][2];
+  auto load_w = [&](int pair) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        int o = o_base + pair * 2 + c, k = (lane + 32 * i) * 4;
+        wn[c][i] = (o < O && k < kt) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)o * K + k0 + k))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  };
+  load_w(0);
+  __syncthreads();
+  float* pout = part + (size_t)blockIdx.y * B * O;
+  for (int pair = 0; pair < GP_OW / 2; ++pair) {
+    float4 wc[2][2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) wc[c][i] = wn[c][i];
+    if (pair + 1 < GP_OW / 2) load_w(pair + 1);
+    float acc[2][GP_BT];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int b = 0; b < GP_BT; ++b) acc[c][b] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float* xr = s_x + (lane + 32 * i) * 4;
+#pragma unroll
+      for (int b = 0; b < GP_BT; ++b) {
+        float4 xv = *reinterpret_cast<const float4*>(xr + b * GP_PITCH);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          acc[c][b] = fmaf(wc[c][i].x, xv.x, acc[c][b]);
+          acc[c][b] = fmaf(wc[c][i].y, xv.y, acc[c][b]);
+          acc[c][b] = fmaf(wc[c][i].z, xv.z, acc[c][b]);
+          acc[c][b] = fmaf(wc[c][i].w, xv.w, acc[c][b]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v = warp_transpose_sum32(acc[c], lane);            // lane l: batch row l
+      int o = o_base + pair * 2 + c;
+      if (lane < B && o < O) pout[(size_t)lane * O + o] = v;
+    }
+  }
+}
+
+// phase 2: out[b][o] = epi( sum_ks part[ks][b][o] + bias[o] );  act: 0 none, 1 relu, 2 sigmoid;
+// mul: result *= mul[b][o] (SE gate);  res: result += res[b][o] (residual shortcut)
+__global__ void k_gp_reduce(const float* __restrict__ part, int nsplit, const float* __restrict__ bias, float* __restrict__ out,
+                            int out_stride, const float* __restrict__ mul, int mul_stride, const float* __restrict__ res,
+                            int res_stride, int B, int O, int act) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * O) return;
+  int b = i / O, o = i % O;
+  float v = 0.0f;
+  for (int s = 0; s < nsplit; ++s) v += part[((size_t)s * B + b) * O + o];
+  v += bias ? bias[o] : 0.0f;
+  if (act == 1) v = fmaxf(v, 0.0f);
+  else if (act == 2) v = 1.0f / (1.0f + expf(-v));
+  if (mul) v *= mul[(size_t)b * mul_stride + o];
+  if (res) v += res[(size_t)b * res_stride + o];
+  out[(size_t)b * out_stride + o] = v;
 }
 
 // PositionalEmbedding (models/utils.py:16-31): fp32 frequencies exp(i * -log(1e4)/(half-1))
@@ -179,14 +197,14 @@ int global_prior_build(Model* m, Cursor& cur) {
 
 static int gp_linear(Ctx* c, const GPLin& l, const float* x, int xs, const float* add, int as, float* out, int os,
                      const float* mul, int ms, const float* res, int rs, int B, int act) {
-  int grid = cdiv(l.O, GP_WARPS * GP_CO);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LION_CHECK_CUDA(cudaFuncSetAttribute(k_gp_linear, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_BT * GP_PITCH * (int)sizeof(float)));
-    attr_set = true;
-  }
   if (l.K % 4) { set_error("global prior: K=%d must be a multiple of 4", l.K); return LION_ERR_ARG; }
-  LION_LAUNCH(c, k_gp_linear, grid, GP_WARPS * 32, GP_BT * GP_PITCH * sizeof(float), l.w, l.b, x, xs, add, as, out, os, mul, ms, res, rs, B, l.K, l.O, act);
+  int nsplit = cdiv(l.K, GP_KS);
+  if (nsplit > GP_MAXSPLIT) { set_error("global prior: K=%d too large", l.K); return LION_ERR_ARG; }
+  size_t mk = c->mark();
+  float* part = c->alloc_n<float>((size_t)nsplit * B * l.O);
+  LION_LAUNCH(c, k_gp_partial, dim3(cdiv(l.O, GP_OB), nsplit), GP_WARPS * 32, 0, l.w, x, xs, add, as, part, B, l.K, l.O);
+  LION_LAUNCH(c, k_gp_reduce, cdiv(B * l.O, 256), 256, 0, part, nsplit, l.b, out, os, mul, ms, res, rs, B, l.O, act);
+  c->release(mk);     // stream order makes reuse by the next layer safe
   return 0;
 }
 

@@ -222,6 +222,8 @@ struct PF { float4* p = nullptr; int G = 0; int R = 0; };
 struct VoxPrep { const float4* c4; int N, r; float4* nc; int* order; int* ppos; int* len; unsigned char* occ; int occ_stride; };
 struct Fwd {
   Ctx* c; Model* m; int B;
+  char* stat_pool = nullptr;     // all GroupNorm statistics of a forward: zeroed by ONE memset
+  size_t stat_off = 0, stat_cap = 0;
   float* aff = nullptr;          // [B][style_total] all AdaGN (factor|bias) vectors of this forward
   std::vector<VoxPrep> vox;
 };
@@ -292,10 +294,23 @@ static int run_affine(Fwd& f, const AdaGNW& g, const double* ssum, const double*
               f.m->style_total, se1, se2, a.scale, a.shift, g.C, count);
   return check_launch(f.c, "affine_prep");
 }
+static int stat_pool_begin(Fwd& f, size_t bytes) {
+  f.stat_pool = (char*)f.c->alloc(bytes);
+  f.stat_cap = bytes; f.stat_off = 0;
+  return memset_async(f.c, f.stat_pool, 0, bytes);
+}
 static int alloc_stats(Fwd& f, int stride, double** ssum, double** ssq) {
-  double* s = f.c->alloc_n<double>((size_t)2 * f.B * stride);
+  size_t bytes = sizeof(double) * 2 * f.B * stride;
+  double* s;
+  if (f.stat_pool && f.stat_off + bytes <= f.stat_cap) {        // pooled: already zero
+    s = (double*)(f.stat_pool + f.stat_off);
+    f.stat_off += bytes;
+    *ssum = s; *ssq = s + (size_t)f.B * stride;
+    return 0;
+  }
+  s = f.c->alloc_n<double>((size_t)2 * f.B * stride);
   *ssum = s; *ssq = s + (size_t)f.B * stride;
-  return memset_async(f.c, s, 0, sizeof(double) * 2 * f.B * stride);
+  return memset_async(f.c, s, 0, bytes);
 }
 
 // SharedMLP on a PF.  pool: 1, or 32 = max over neighbour rows after the last activation.
@@ -607,6 +622,7 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   }
   LION_TRY(check_launch(c, "unet prologue"));
   LION_TRY(style_affine_all(f, style));
+  LION_TRY(stat_pool_begin(f, (size_t)f.m->style_total * f.B * sizeof(double) + 4096));   // sum(2*C) doubles per shape
 
   int n_sa = (int)u.sa.size();
   std::vector<const float4*> coords_list(n_sa);
