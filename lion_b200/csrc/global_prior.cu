@@ -36,26 +36,54 @@ __device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
 }
 
 // Split-K skinny GEMM, phase 1:  part[ks][b][o] = sum_{k in slice ks} W[o][k] * (x[b][k] + add[b][k])
-// grid = (O/128, K/256).  The block stages ITS 256-wide slice of all <=32 activation rows once
-// (32 KB; with one block per output group and the full K, 128 SMs re-read the same 256 KB of
-// activations from L2 per K tile, which is what bounded the first version), then every warp
-// streams 16 weight rows x 256 columns with 128-bit loads issued one row pair ahead; each
-// 128-bit shared-memory read of x feeds 8 FMAs.  Deterministic: partials are summed in a
-// fixed order by k_gp_reduce.
-__global__ void __launch_bounds__(GP_WARPS * 32, 2)
+// grid = (O/128, K/256).  M = 32 shapes is far below a tcgen05 tile (M >= 128 rows of the SAME
+// operand), so this layer uses warp-level mma.sync.m16n8k8 TF32 (the reference's cuDNN 1x1
+// convolutions run TF32 as well): A = 16 weight rows x 8 k, B = 8 k x 8 shapes.
+//   * the block's weight tile [128 x 256] (128 KB) streams HBM -> shared memory with cp.async in
+//     four 64-column commit groups, so the tensor work on group g overlaps the arrival of g+1;
+//   * the activation slice [32 x 256] is staged once per block (rounded to TF32, round-to-nearest);
+//   * row pitch 260 floats makes every fragment load bank-conflict free (bank = 4*row + col).
+// Deterministic: partials are summed in a fixed order by k_gp_reduce.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__global__ void __launch_bounds__(GP_WARPS * 32, 1)
 k_gp_partial(const float* __restrict__ W, const float* __restrict__ x, int x_stride, const float* __restrict__ add,
              int add_stride, float* __restrict__ part, int B, int K, int O) {
-  __shared__ __align__(16) float s_x[GP_BT * GP_PITCH];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  extern __shared__ __align__(16) float s_mem[];
+  float* s_w = s_mem;                          // [GP_OB][GP_PITCH]
+  float* s_x = s_mem + GP_OB * GP_PITCH;       // [GP_BT][GP_PITCH]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int k0 = blockIdx.y * GP_KS, kt = min(GP_KS, K - k0);
-  const int o_base = blockIdx.x * GP_OB + wid * GP_OW;
-  // stage x slice (+ add): 8 independent 128-bit loads per thread
+  const int o0 = blockIdx.x * GP_OB;
+  // weights: 4 commit groups of 64 columns; chunk c of a group = (row, 16-byte column piece)
+  const uint32_t s_w_addr = (uint32_t)__cvta_generic_to_shared(s_w);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+#pragma unroll
+    for (int u = 0; u < (GP_OB * 16) / (GP_WARPS * 32); ++u) {       // 128 rows x 16 pieces / 256 threads = 8
+      int c = tid + u * (GP_WARPS * 32);
+      int row = c >> 4, piece = c & 15;
+      int col = g * 64 + piece * 4;
+      if (o0 + row < O && col < kt)
+        cp_async16(s_w_addr + (uint32_t)(row * GP_PITCH + col) * 4u, W + (size_t)(o0 + row) * K + k0 + col);
+      else   // keep out-of-range rows / columns finite: they meet zero activations or unused outputs
+        *reinterpret_cast<float4*>(s_w + row * GP_PITCH + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // activations (+ add), rounded to TF32
   {
     constexpr int PER_THREAD = GP_BT * (GP_KS / 4) / (GP_WARPS * 32);      // 8
     float4 v[PER_THREAD];
 #pragma unroll
     for (int u = 0; u < PER_THREAD; ++u) {
-      int i = threadIdx.x + u * (GP_WARPS * 32);
+      int i = tid + u * (GP_WARPS * 32);
       int b = i / (GP_KS / 4), k4 = i % (GP_KS / 4);
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (b < B && k4 * 4 < kt) {
@@ -68,57 +96,53 @@ k_gp_partial(const float* __restrict__ W, const float* __restrict__ x, int x_str
     }
 #pragma unroll
     for (int u = 0; u < PER_THREAD; ++u) {
-      int i = threadIdx.x + u * (GP_WARPS * 32);
+      int i = tid + u * (GP_WARPS * 32);
       int b = i / (GP_KS / 4), k4 = i % (GP_KS / 4);
-      *reinterpret_cast<float4*>(s_x + b * GP_PITCH + k4 * 4) = v[u];
+      float4 r = make_float4(__uint_as_float(tf32_bits(v[u].x)), __uint_as_float(tf32_bits(v[u].y)),
+                             __uint_as_float(tf32_bits(v[u].z)), __uint_as_float(tf32_bits(v[u].w)));
+      *reinterpret_cast<float4*>(s_x + b * GP_PITCH + k4 * 4) = r;
     }
   }
-  float4 wn[2][2];
-  auto load_w = [&](int pair) {
+  const int g8 = lane >> 2, t4 = lane & 3;
+  float acc[4][4];
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
+  for (int n = 0; n < 4; ++n)
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        int o = o_base + pair * 2 + c, k = (lane + 32 * i) * 4;
-        wn[c][i] = (o < O && k < kt) ? __ldg(reinterpret_cast<const float4*>(W + (size_t)o * K + k0 + k))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-  };
-  load_w(0);
-  __syncthreads();
-  float* pout = part + (size_t)blockIdx.y * B * O;
-  for (int pair = 0; pair < GP_OW / 2; ++pair) {
-    float4 wc[2][2];
+    for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
+  const float* wa = s_w + (wid * 16 + g8) * GP_PITCH + t4;       // rows g8 / g8+8 of this warp's 16 outputs
+  const float* xb = s_x + g8 * GP_PITCH + t4;                    // shape g8 of each 8-shape tile
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
+  for (int g = 0; g < 4; ++g) {
+    if (g == 0) asm volatile("cp.async.wait_group 3;" ::: "memory");
+    else if (g == 1) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else if (g == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (g * 64 < kt) {
 #pragma unroll
-      for (int i = 0; i < 2; ++i) wc[c][i] = wn[c][i];
-    if (pair + 1 < GP_OW / 2) load_w(pair + 1);
-    float acc[2][GP_BT];
+      for (int kk = 0; kk < 64; kk += 8) {
+        const int k = g * 64 + kk;
+        uint32_t a0 = __float_as_uint(wa[k]), a1 = __float_as_uint(wa[8 * GP_PITCH + k]);
+        uint32_t a2 = __float_as_uint(wa[k + 4]), a3 = __float_as_uint(wa[8 * GP_PITCH + k + 4]);
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-      for (int b = 0; b < GP_BT; ++b) acc[c][b] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float* xr = s_x + (lane + 32 * i) * 4;
-#pragma unroll
-      for (int b = 0; b < GP_BT; ++b) {
-        float4 xv = *reinterpret_cast<const float4*>(xr + b * GP_PITCH);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          acc[c][b] = fmaf(wc[c][i].x, xv.x, acc[c][b]);
-          acc[c][b] = fmaf(wc[c][i].y, xv.y, acc[c][b]);
-          acc[c][b] = fmaf(wc[c][i].z, xv.z, acc[c][b]);
-          acc[c][b] = fmaf(wc[c][i].w, xv.w, acc[c][b]);
+        for (int n = 0; n < 4; ++n) {
+          uint32_t b0 = __float_as_uint(xb[n * 8 * GP_PITCH + k]), b1 = __float_as_uint(xb[n * 8 * GP_PITCH + k + 4]);
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
         }
       }
     }
+  }
+  // C fragment: c0,c1 -> (row g8, shapes 2*t4, 2*t4+1); c2,c3 -> (row g8+8, same shapes)
+  float* pout = part + (size_t)blockIdx.y * B * O;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v = warp_transpose_sum32(acc[c], lane);            // lane l: batch row l
-      int o = o_base + pair * 2 + c;
-      if (lane < B && o < O) pout[(size_t)lane * O + o] = v;
+  for (int n = 0; n < 4; ++n) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int o = o0 + wid * 16 + g8 + (i >= 2 ? 8 : 0);
+      int b = n * 8 + 2 * t4 + (i & 1);
+      if (b < B && o < O) pout[(size_t)b * O + o] = acc[n][i];
     }
   }
 }
@@ -202,7 +226,13 @@ static int gp_linear(Ctx* c, const GPLin& l, const float* x, int xs, const float
   if (nsplit > GP_MAXSPLIT) { set_error("global prior: K=%d too large", l.K); return LION_ERR_ARG; }
   size_t mk = c->mark();
   float* part = c->alloc_n<float>((size_t)nsplit * B * l.O);
-  LION_LAUNCH(c, k_gp_partial, dim3(cdiv(l.O, GP_OB), nsplit), GP_WARPS * 32, 0, l.w, x, xs, add, as, part, B, l.K, l.O);
+  const size_t smem = (size_t)(GP_OB + GP_BT) * GP_PITCH * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LION_CHECK_CUDA(cudaFuncSetAttribute(k_gp_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  LION_LAUNCH(c, k_gp_partial, dim3(cdiv(l.O, GP_OB), nsplit), GP_WARPS * 32, smem, l.w, x, xs, add, as, part, B, l.K, l.O);
   LION_LAUNCH(c, k_gp_reduce, cdiv(B * l.O, 256), 256, 0, part, nsplit, l.b, out, os, mul, ms, res, rs, B, l.O, act);
   c->release(mk);     // stream order makes reuse by the next layer safe
   return 0;
