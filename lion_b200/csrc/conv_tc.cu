@@ -48,11 +48,14 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // bounded wait: a protocol bug traps (and surfaces as a CUDA error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
     if (clock64() - t0 > 2000000000LL) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);      // common case: already complete
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -120,6 +123,7 @@ struct Params {
   int a_stages;          // depth of the A ring
   const unsigned char* occ;   // 64-row occupancy flags of the input (sparse first conv of a PVConv) or null
   int occ_stride;
+  int debug;             // bring-up experiments (LION_TC_DEBUG): 1 no global loads, 2 no MMAs, 4 no epilogue stores/stats
 };
 
 // per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
@@ -191,25 +195,30 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   const int tile0 = grp * P.G; const int ntile = min(P.G, ntile_total - tile0); const int n0 = nt * P.NT;
 
   if (warp == 0) {
-    // ===================== producer =====================
-    if (lane == 0) {
+    // ===================== producer (whole warp; lane kg issues the copy of channel group kg) ====
+    {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0;          // ring positions and phase bits
       const uint32_t bytes = (uint32_t)P.stage_rows * 16u;
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
       for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         ITEM_DECODE(w)
         (void)n0;
-        const size_t in_b = (size_t)b * P.Gin * P.rows;
         const float* wsrc = P.w + (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);
         const unsigned char* occ_b = P.occ ? P.occ + (size_t)b * P.occ_stride : nullptr;
+        const long long row_item = (long long)P.p_begin + (long long)tile0 * 128 - P.halo;
+        const float4* in_item = P.in + (size_t)b * P.Gin * P.rows;
         for (int cc = 0; cc < P.nchunk; ++cc) {
-          int kg_real = min(KG, P.Gin - cc * KG);
+          const int kg_real = min(KG, P.Gin - cc * KG);
+          const float4* in_lane = in_item + (size_t)(cc * KG + (lane < kg_real ? lane : 0)) * P.rows;
           for (int tg = 0; tg < P.ntg; ++tg) {
             mbar_wait(bar_empty_b + 8 * sb, pb ^ 1);
-            mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
-            bulk_g2s(smem_u32(sB + (size_t)sb * P.b_stage_bytes), wsrc + (size_t)(cc * P.ntg + tg) * (P.b_stage_bytes / 4),
-                     P.b_stage_bytes, bar_full_b + 8 * sb);
+            if (lane == 0) {
+              mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
+              bulk_g2s(sB_addr + sb * (uint32_t)P.b_stage_bytes, wsrc + (size_t)(cc * P.ntg + tg) * (P.b_stage_bytes / 4),
+                       P.b_stage_bytes, bar_full_b + 8 * sb);
+            }
             if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
-            long long row0 = (long long)P.p_begin + (long long)tile0 * 128 + P.tg_off[tg] - P.halo;
+            long long row0 = row_item + P.tg_off[tg];
             for (int j = 0; j < ntile; ++j, row0 += 128) {
               mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
               bool empty = false;
@@ -220,16 +229,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
                 for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(occ_b + k);
                 empty = (any == 0);
               }
-              s_skip[sa] = empty ? 1u : 0u;
-              if (empty) {
-                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar_full_a + 8 * sa) : "memory");
-              } else {
-                mbar_expect_tx(bar_full_a + 8 * sa, bytes * kg_real);
-                const float4* src = P.in + in_b + (size_t)(cc * KG) * P.rows + row0;
-                uint32_t dst = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
-                for (int kg = 0; kg < kg_real; ++kg)
-                  bulk_g2s(dst + kg * bytes, src + (size_t)kg * P.rows, bytes, bar_full_a + 8 * sa);
+              const uint32_t full = bar_full_a + 8 * sa;
+              if (lane == 0) {
+                s_skip[sa] = empty ? 1u : 0u;
+                if (empty || (P.debug & 1)) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+                else mbar_expect_tx(full, bytes * kg_real);
               }
+              __syncwarp();
+              if (!empty && !(P.debug & 1) && lane < kg_real)
+                bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, bytes, full);
               if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
             }
           }
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
                   uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
                   uint32_t blo = b_lo_c | ((b_t + k2 * b_pitch16) & 0x3fff);
                   uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
-                  umma_tf32_w(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
+                  if (!(P.debug & 2)) umma_tf32_w(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
                 }
               }
               umma_commit_w(bar_empty_a + 8 * my_sa);     // frees the A stage when these MMAs retire
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + s_bias[c32 + i] : 0.0f;
-          if (inrange) {
+          if (inrange && !(P.debug & 4)) {
 #pragma unroll
             for (int g4 = 0; g4 < 8; ++g4) {
               int g = (n0 + c32) / 4 + g4;
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
                 P.out[((size_t)b * P.Gout_store + g) * P.rows + p] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
             }
           }
-          if (P.ssum) {
+          if (P.ssum && !(P.debug & 4)) {
             float sq[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
@@ -432,8 +440,10 @@ static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, in
   int G = w.cin_pad / 4;
   // 16-channel chunks for the 3x3x3 case: a 9-tap weight slab is then <= 72 KB, two of them fit
   // next to a deep (>= 6 stage) ring of activation slabs; the 1x1 case uses 32-channel chunks
-  if (w.ntaps == 27) KG = (NT >= 64) ? 4 : 8;
+  if (w.ntaps == 27) KG = (NT > 64) ? 4 : 8;       // per-stage pipeline overhead favours few, large stages
   else KG = 8;
+  { static int kg64 = -1; if (kg64 < 0) { const char* e = getenv("LION_TC_KG64"); kg64 = e ? atoi(e) : 0; }
+    if (kg64 && w.ntaps == 27 && NT == 64) KG = kg64; }
   if (G < KG) KG = (G <= 2) ? 2 : ((G <= 4) ? 4 : 8);
   nchunk = (G + KG - 1) / KG;
 }
@@ -501,6 +511,7 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   P.G = G;
   P.B = B;
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LION_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.debug = dbg; }
   const size_t fixed = 128 * 4 + 4 * 2 * 128 * 4 + 64 * 8 + 128;
   long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
   int a_stages = (int)(room / P.a_stage_bytes);
