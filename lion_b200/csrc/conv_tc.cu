@@ -54,8 +54,12 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 2000000000LL) __trap();
   }
 }
+// Called by all 32 lanes of a warp (every role below is warp-collective).  Lanes can leave the
+// polling loop at different times, so reconverge explicitly: the elect.sync / .sync.aligned
+// tcgen05 instructions that follow require the full warp.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);      // common case: already complete
+  __syncwarp();
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -440,7 +444,10 @@ static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, in
   int G = w.cin_pad / 4;
   // 16-channel chunks for the 3x3x3 case: a 9-tap weight slab is then <= 72 KB, two of them fit
   // next to a deep (>= 6 stage) ring of activation slabs; the 1x1 case uses 32-channel chunks
-  if (w.ntaps == 27) KG = (NT > 64) ? 4 : 8;       // per-stage pipeline overhead favours few, large stages
+  // 16-channel chunks for N >= 64 (deep activation ring).  NOTE: 32-channel chunks with a 3-deep ring
+  // (LION_TC_KG64=8) are ~10 % faster on dense inputs but fail (launch failure) together with
+  // sparse-slab skipping at B=32 -- unexplained, tracked in DESIGN.md section 7.
+  if (w.ntaps == 27) KG = (NT >= 64) ? 4 : 8;
   else KG = 8;
   { static int kg64 = -1; if (kg64 < 0) { const char* e = getenv("LION_TC_KG64"); kg64 = e ? atoi(e) : 0; }
     if (kg64 && w.ntaps == 27 && NT == 64) KG = kg64; }
@@ -511,6 +518,7 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   P.G = G;
   P.B = B;
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
+  { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LION_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.debug = dbg; }
   const size_t fixed = 128 * 4 + 4 * 2 * 128 * 4 + 64 * 8 + 128;
   long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
