@@ -62,6 +62,7 @@ struct Ctx {
   size_t off = 0;
   size_t peak = 0;
   bool dry = false;
+  bool pdl = false;          // programmatic dependent launch (LION_PDL=1 enables; measured: no gain in graphs)
   int launches = 0;          // kernels launched by the last real pass (gpu_launches evidence)
 
   void reset() { off = 0; peak = 0; launches = 0; zgrid_need = 0; }
@@ -80,11 +81,27 @@ struct Ctx {
 
 int ctx_reserve(Ctx* c, size_t bytes);   // grow arena (sync; not capturable)
 
-// launch helper: skipped in dry mode; counts launches.
+// launch helper: skipped in dry mode; counts launches.  Kernels are launched with
+// programmatic stream serialization (PDL): every kernel starts with pdl_wait() (blocks until
+// the previous kernel in the stream has completed and flushed) preceded by pdl_trigger()
+// (lets the NEXT kernel's blocks be scheduled as soon as this one's last wave is resident),
+// which hides the ~2-3 us launch + drain/fill bubble between the ~300 dependent kernels of a
+// denoising step, inside CUDA graphs as well.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(cudaStream_t stream, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 #define LION_LAUNCH(ctx, kernel, grid, block, smem, ...)                               \
   do {                                                                                 \
     if (!(ctx)->dry) {                                                                 \
-      kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                 \
+      if ((ctx)->pdl) lion::launch_pdl((ctx)->stream, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__); \
+      else kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);            \
       (ctx)->launches++;                                                               \
     }                                                                                  \
   } while (0)
@@ -116,6 +133,11 @@ static inline size_t cdivz(size_t a, size_t b) { return (a + b - 1) / b; }
 // device utilities
 // ---------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// PDL prologue of every kernel (see LION_LAUNCH): no global memory access may precede it.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -149,6 +149,7 @@ __device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
 
 template <int KG, int TPG>
 __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see LION_LAUNCH
   extern __shared__ __align__(128) uint8_t smem[];
   // layout: [A stages][B stages][bias NT floats][stat 4*2*128 floats][barriers][tmem ptr]
   uint8_t* sA = smem;
@@ -188,6 +189,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
+  // everything above touched only shared / tensor memory and overlapped the previous kernel's
+  // tail; from here on global memory written by that kernel is consumed
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int ntile_total = (P.p_end - P.p_begin + 127) / 128;
   const int ngrp = (ntile_total + P.G - 1) / P.G;
@@ -406,6 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
 //   w[nt][chunk][tg][t][kg][n][4]  (tf32-rounded, round-to-nearest-away like cuDNN's conversion)
 __global__ void k_pack_tc(const float* __restrict__ wt, float* __restrict__ w, int ntaps, int cin_pad, int cout_pad,
                           int NT, int nchunk, int ntg, int tpg, int KG) {
+  pdl_prologue();
   size_t total = (size_t)(cout_pad / NT) * nchunk * ntg * tpg * KG * NT * 4;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;

@@ -20,6 +20,7 @@ namespace lion {
 __global__ void k_ddpm_update(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
                               float* __restrict__ xo, const float4* __restrict__ tables, const int* __restrict__ step,
                               float temp, size_t n, float* __restrict__ hist, int T) {
+  pdl_prologue();
   int t = *step;
   float4 c = tables[t];
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -37,6 +38,7 @@ __global__ void k_ddpm_update(const float* __restrict__ x, const float* __restri
 }
 
 __global__ void k_ddpm_set_step(int* step, float* t_out, int B, int t_index, int advance) {
+  pdl_prologue();
   int t = advance ? (*step - 1) : t_index;
   __syncthreads();
   if (threadIdx.x == 0) *step = t;

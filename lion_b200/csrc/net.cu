@@ -18,6 +18,7 @@
 //     (coords, resolution) -- 4x per step instead of 14x;
 //   * no permutes: the latent [B,N,4] is already a packed-feature tensor.
 #include <memory>
+#include <cstdlib>
 #include <cmath>
 #include "common.cuh"
 #include "packed_kernels.cuh"
@@ -82,6 +83,7 @@ int ctx_reserve_zgrid(Ctx* c, size_t bytes) {
 // weight packing kernels
 __global__ void k_pack_conv_w(const float* __restrict__ w_ref, const int* __restrict__ kmap, float* __restrict__ wt,
                               int ntaps, int cin_ref, int cin_pad, int cout, int cout_pad) {
+  pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)ntaps * cin_pad * cout_pad;
   if (i >= total) return;
@@ -94,6 +96,7 @@ __global__ void k_pack_conv_w(const float* __restrict__ w_ref, const int* __rest
   wt[i] = v;
 }
 __global__ void k_pad_vec(const float* __restrict__ src, float* __restrict__ dst, int n, int n_pad) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) dst[i] = i < n ? src[i] : 0.0f;
 }
@@ -271,6 +274,11 @@ static ConvGeom geom_grid(int r) {
 static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store,
                     double* ssum, double* ssq, const ConvGeom& geo) {
   if (Gin * 4 != w.cin_pad) { set_error("conv: input has %d channels, weights expect %d", Gin * 4, w.cin_pad); return LION_ERR_ARG; }
+  { // timing experiments only (results are garbage): LION_SKIP_CONV=1 skips 3x3x3 convs, =2 skips all convs
+    static int skip = -1;
+    if (skip < 0) { const char* e = getenv("LION_SKIP_CONV"); skip = e ? atoi(e) : 0; }
+    if (skip == 2 || (skip == 1 && geo.ntaps == 27)) return 0;
+  }
   if (conv_tc_usable(w, geo))
     return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B);
   int span = geo.p_end - geo.p_begin;
@@ -583,11 +591,13 @@ static int build_unet(Model* m, Cursor& cur) {
 }
 
 __global__ void k_extract_extra(const float4* __restrict__ x, float4* __restrict__ o, int total) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) o[i] = make_float4(x[i].w, 0.f, 0.f, 0.f);
 }
 
 __global__ void k_pm4_to_pm(const float4* __restrict__ src, float* __restrict__ dst, int total, int C) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   float4 v = src[i];
@@ -764,6 +774,7 @@ extern "C" int lion_ctx_create(int device, LionCtx** out) {
   cudaDeviceProp prop;
   LION_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   h->c.num_sms = prop.multiProcessorCount;
+  { const char* e = getenv("LION_PDL"); h->c.pdl = (e && atoi(e) != 0); }   // measured: no gain inside CUDA graphs; off by default
   LION_CHECK_CUDA(cudaStreamCreateWithFlags(&h->c.aux, cudaStreamNonBlocking));
   LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev_fork, cudaEventDisableTiming));
   for (int i = 0; i < 8; ++i) LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev[i], cudaEventDisableTiming));
@@ -979,6 +990,7 @@ extern "C" int lion_global_prior_forward(LionModel* h, const float* x, const flo
 
 // ---- measurement hook: time the convolution kernel alone (bench.py roofline leg) ------------
 __global__ void k_fill_pattern(float* p, size_t n, float scale) {
+  pdl_prologue();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) { unsigned h = (unsigned)(i * 2654435761u) ^ 0x9e3779b9u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
                p[i] = scale * ((float)(h & 0xffff) / 32768.0f - 1.0f); }

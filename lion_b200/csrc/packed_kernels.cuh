@@ -46,6 +46,7 @@ __device__ __forceinline__ float4 f4_fma(float4 a, float s, float4 c) {
 // latent x[B][N][D] (D<=4 floats per point... here D==4) -> C4 coordinates
 // ------------------------------------------------------------------------------------
 __global__ void k_make_coords(const float4* __restrict__ x, float4* __restrict__ c4, int total) {
+  pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   float4 v = x[i];
@@ -67,6 +68,7 @@ constexpr int VOXP_MAXN = 4096;
 __global__ void __launch_bounds__(VOXP_THREADS)
 k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restrict__ s_order, int* __restrict__ s_ppos,
            int* __restrict__ s_len, unsigned char* __restrict__ occ, int occ_stride, int N, int r) {
+  pdl_prologue();
   int b = blockIdx.x;
   const float4* c = c4 + (size_t)b * N;
   __shared__ float s_stat[4];
@@ -160,6 +162,7 @@ k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restri
 // reference does (vox.cu:65-68), and stores once.
 __global__ void k_scatter(const float4* __restrict__ feat, const int* __restrict__ s_order, const int* __restrict__ s_ppos,
                           const int* __restrict__ s_len, float4* __restrict__ grid, int G, int N, int P) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= N) return;
@@ -177,6 +180,7 @@ __global__ void k_scatter(const float4* __restrict__ feat, const int* __restrict
 // restore the all-zero invariant of the persistent scatter grid: zero exactly the voxels that
 // k_scatter wrote (N*G stores instead of a full-grid memset per PVConv)
 __global__ void k_unscatter(const int* __restrict__ s_ppos, float4* __restrict__ grid, int G, int N, int P) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= N) return;
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(128)
 k_conv_simt(const float4* __restrict__ in, const float* __restrict__ Wt, const float* __restrict__ bias,
             float4* __restrict__ out, double* __restrict__ ssum, double* __restrict__ ssq,
             int Gin, int cin_pad, int cout_pad, int Gout_store, ConvGeom geo) {
+  pdl_prologue();
   extern __shared__ float s_w[];   // [ntaps][4][COT]
   int b = blockIdx.z;
   int co0 = blockIdx.y * COT;
@@ -271,6 +276,7 @@ __global__ void k_affine_prep(const double* __restrict__ ssum, const double* __r
                               const float* __restrict__ style_fb /*[B][2C] for this layer*/, int fb_stride,
                               const float* __restrict__ se_w1 /*[C/8][C] or null*/, const float* __restrict__ se_w2 /*[C][C/8]*/,
                               float* __restrict__ scale, float* __restrict__ shift, int C, double count) {
+  pdl_prologue();
   extern __shared__ float s_f[];   // [C] se input, [C/8] hidden
   __shared__ double s_gs[8], s_gq[8];
   int b = blockIdx.x, c = threadIdx.x;
@@ -314,6 +320,7 @@ __global__ void k_affine_prep(const double* __restrict__ ssum, const double* __r
 // all AdaGN style Linears of a network in one launch: out[b][off_l + o] = W_l[o] . style[b] + bias_l[o]
 __global__ void k_style_linear(const StyleLayer* __restrict__ layers, const float* __restrict__ style, int S,
                                float* __restrict__ out, int out_stride) {
+  pdl_prologue();
   extern __shared__ float s_style[];
   StyleLayer L = layers[blockIdx.x];
   int b = blockIdx.y;
@@ -331,6 +338,7 @@ __global__ void k_style_linear(const StyleLayer* __restrict__ layers, const floa
 // generic small dense layer on [B][K] rows: out = act(W x + b); act 0 none, 1 leaky(0.1)
 __global__ void k_small_linear(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
                                int x_stride, float* __restrict__ out, int out_stride, int K, int O, int act) {
+  pdl_prologue();
   extern __shared__ float s_x[];
   int b = blockIdx.x;
   for (int i = threadIdx.x; i < K; i += blockDim.x) s_x[i] = x[(size_t)b * x_stride + i];
@@ -352,6 +360,7 @@ __global__ void k_small_linear(const float* __restrict__ W, const float* __restr
 // host in float64 and rounded to fp32 exactly like the reference
 __global__ void k_time_sinusoid(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out,
                                 int half, float scale) {
+  pdl_prologue();
   int b = blockIdx.x, i = threadIdx.x;
   if (i >= half) return;
   float e = __fmul_rn(__fmul_rn(t[b], scale), freqs[i]);
@@ -365,6 +374,7 @@ __global__ void k_time_sinusoid(const float* __restrict__ t, const float* __rest
 // VG: y = swish(scale*x + shift) on interior voxels, 0 on every halo position (incl. x planes)
 __global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
                            const float* __restrict__ shift, int G, int C, int rp, int P) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -385,6 +395,7 @@ __global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ o
 template <int POOL>
 __global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
                            const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off, int to_tf32) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R_out) return;
@@ -400,6 +411,7 @@ __global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ o
 
 // copy groups of a PF into another PF at a group offset (channel concatenation)
 __global__ void k_copy_groups(const float4* __restrict__ src, float4* __restrict__ dst, int Gs, int Gd, int g_off, int R) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
@@ -408,6 +420,7 @@ __global__ void k_copy_groups(const float4* __restrict__ src, float4* __restrict
 
 // broadcast a per-shape vector v[b][4*Gv] over all rows (the time embedding "expand")
 __global__ void k_fill_groups(const float* __restrict__ v, int v_stride, float4* __restrict__ dst, int Gd, int g_off, int R) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
@@ -422,6 +435,7 @@ __global__ void k_devox_fuse(const float4* __restrict__ raw, const float4* __res
                              const float* __restrict__ shift, const float4* __restrict__ rawp,
                              const float* __restrict__ scale_p, const float* __restrict__ shift_p,
                              float4* __restrict__ out, int G, int C, int N, int r, int P, int Gd, int g_off) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
@@ -453,6 +467,7 @@ __global__ void k_devox_fuse(const float4* __restrict__ raw, const float4* __res
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FPS_THREADS)
 k_fps_c4(const float4* __restrict__ c4, int* __restrict__ idx, float4* __restrict__ centers, int N, int M) {
+  pdl_prologue();
   int b = blockIdx.x;
   const float4* c = c4 + (size_t)b * N;
   int* io = idx + (size_t)b * M;
@@ -463,6 +478,7 @@ k_fps_c4(const float4* __restrict__ c4, int* __restrict__ idx, float4* __restric
 
 __global__ void k_ball_query_c4(const float4* __restrict__ centers, const float4* __restrict__ points, int* __restrict__ out,
                                 int N, int M, float r2, int K) {
+  pdl_prologue();
   int b = blockIdx.y;
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= M) return;
@@ -477,6 +493,7 @@ __global__ void k_ball_query_c4(const float4* __restrict__ centers, const float4
 __global__ void k_group_gather(const float4* __restrict__ feat, const float4* __restrict__ points,
                                const float4* __restrict__ centers, const int* __restrict__ nidx, float4* __restrict__ out,
                                int Gf, int N, int M, int U) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;    // g == 0: coordinates; g >= 1: features group g-1
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int MU = M * U;
@@ -497,6 +514,7 @@ __global__ void k_group_gather(const float4* __restrict__ feat, const float4* __
 // ------------------------------------------------------------------------------------
 __global__ void k_three_nn_c4(const float4* __restrict__ points, const float4* __restrict__ centers, int* __restrict__ idx,
                               float* __restrict__ wgt, int N, int M) {
+  pdl_prologue();
   int b = blockIdx.y;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   extern __shared__ float4 s_c4[];
@@ -526,6 +544,7 @@ __global__ void k_three_nn_c4(const float4* __restrict__ points, const float4* _
 
 __global__ void k_interp_rows(const float4* __restrict__ cf, const int* __restrict__ idx, const float* __restrict__ wgt,
                               float4* __restrict__ dst, int Gs, int M, int N, int Gd, int g_off) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
@@ -543,6 +562,7 @@ __global__ void k_interp_rows(const float4* __restrict__ cf, const int* __restri
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_attn_ctx(const float4* __restrict__ qkv, float* __restrict__ ctx, int H, int N) {
+  pdl_prologue();
   int h = blockIdx.x, b = blockIdx.y;
   int Gq = 3 * H * 8;                       // groups in qkv
   const float4* kb = qkv + ((size_t)b * Gq + (H + h) * 8) * N;       // k: 8 groups x N
@@ -603,6 +623,7 @@ k_attn_ctx(const float4* __restrict__ qkv, float* __restrict__ ctx, int H, int N
 
 __global__ void __launch_bounds__(128)
 k_attn_apply(const float4* __restrict__ qkv, const float* __restrict__ ctx, float4* __restrict__ out, int H, int N) {
+  pdl_prologue();
   int h = blockIdx.y, b = blockIdx.z;
   __shared__ float s_ctx[32 * 32];
   for (int i = threadIdx.x; i < 1024; i += 128) s_ctx[i] = ctx[((size_t)b * H + h) * 1024 + i];
@@ -634,6 +655,7 @@ k_attn_apply(const float4* __restrict__ qkv, const float* __restrict__ ctx, floa
 // layout conversion at the module-level C ABI: [B][C][R] channel-major <-> PF
 // ------------------------------------------------------------------------------------
 __global__ void k_cm_to_pf(const float* __restrict__ src, float4* __restrict__ dst, int C, int G, int R) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
@@ -646,6 +668,7 @@ __global__ void k_cm_to_pf(const float* __restrict__ src, float4* __restrict__ d
   dst[((size_t)b * G + g) * R + i] = make_float4(v[0], v[1], v[2], v[3]);
 }
 __global__ void k_pf_to_cm(const float4* __restrict__ src, float* __restrict__ dst, int C, int G, int R) {
+  pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R) return;
@@ -658,6 +681,7 @@ __global__ void k_pf_to_cm(const float4* __restrict__ src, float* __restrict__ d
   }
 }
 __global__ void k_cm_to_c4(const float* __restrict__ src, float4* __restrict__ dst, int N) {
+  pdl_prologue();
   int b = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
@@ -665,6 +689,7 @@ __global__ void k_cm_to_c4(const float* __restrict__ src, float4* __restrict__ d
   dst[(size_t)b * N + i] = make_float4(s[i], s[i + N], s[i + 2 * N], 0.0f);
 }
 __global__ void k_c4_to_cm(const float4* __restrict__ src, float* __restrict__ dst, int N) {
+  pdl_prologue();
   int b = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;

@@ -21,6 +21,7 @@ namespace lion {
 // ------------------------------------------------------------------------------------
 __global__ void k_grid_stats(const int* __restrict__ coords, int* __restrict__ ind, int* __restrict__ cnt,
                              int N, int r) {
+  pdl_prologue();
   int b = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
@@ -33,6 +34,7 @@ __global__ void k_grid_stats(const int* __restrict__ coords, int* __restrict__ i
 // one thread per (channel, point): coalesced feature reads, scattered atomics
 __global__ void k_avg_voxelize(const float* __restrict__ feat, const int* __restrict__ ind,
                                const int* __restrict__ cnt, float* __restrict__ out, int C, int N, int r3) {
+  pdl_prologue();
   int b = blockIdx.z;
   int c = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -51,6 +53,7 @@ __global__ void k_avg_voxelize(const float* __restrict__ feat, const int* __rest
 __global__ void k_trilinear_devox(const float* __restrict__ coords, const float* __restrict__ feat,
                                   int* __restrict__ inds, float* __restrict__ wgts, float* __restrict__ outs,
                                   int C, int N, int r, int is_training, int c_per_block) {
+  pdl_prologue();
   int b = blockIdx.z;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
@@ -83,6 +86,7 @@ __global__ void k_trilinear_devox(const float* __restrict__ coords, const float*
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FPS_THREADS)
 k_fps_soa(const float* __restrict__ coords, int* __restrict__ idx_out, int N, int M) {
+  pdl_prologue();
   int b = blockIdx.x;
   const float* c = coords + (size_t)b * 3 * N;
   fps_block([&](int k, float& x, float& y, float& z) { x = c[k]; y = c[k + N]; z = c[k + 2 * N]; },
@@ -91,6 +95,7 @@ k_fps_soa(const float* __restrict__ coords, int* __restrict__ idx_out, int N, in
 
 __global__ void k_gather(const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out,
                          int C, int N, int M) {
+  pdl_prologue();
   int b = blockIdx.z, c = blockIdx.y;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= M) return;
@@ -102,6 +107,7 @@ __global__ void k_gather(const float* __restrict__ feat, const int* __restrict__
 // ------------------------------------------------------------------------------------
 __global__ void k_ball_query_soa(const float* __restrict__ centers, const float* __restrict__ points,
                                  int* __restrict__ out, int N, int M, float r2, int K) {
+  pdl_prologue();
   int b = blockIdx.y;
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (warp >= M) return;
@@ -114,6 +120,7 @@ __global__ void k_ball_query_soa(const float* __restrict__ centers, const float*
 
 __global__ void k_grouping(const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out,
                            int C, int N, int MU) {
+  pdl_prologue();
   int b = blockIdx.z, c = blockIdx.y;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= MU) return;
@@ -125,6 +132,7 @@ __global__ void k_grouping(const float* __restrict__ feat, const int* __restrict
 // ------------------------------------------------------------------------------------
 __global__ void k_three_nn_soa(const float* __restrict__ points, const float* __restrict__ centers,
                                int* __restrict__ idx, float* __restrict__ wgt, int N, int M) {
+  pdl_prologue();
   int b = blockIdx.y;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   extern __shared__ float s_c[];   // [3][tile]
@@ -154,6 +162,7 @@ __global__ void k_three_nn_soa(const float* __restrict__ points, const float* __
 
 __global__ void k_three_interp(const float* __restrict__ cf, const int* __restrict__ idx,
                                const float* __restrict__ wgt, float* __restrict__ out, int C, int N, int M) {
+  pdl_prologue();
   int b = blockIdx.z, c = blockIdx.y;
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
@@ -168,6 +177,7 @@ __global__ void k_three_interp(const float* __restrict__ cf, const int* __restri
 __global__ void __launch_bounds__(VOX_THREADS)
 k_voxel_coords_soa(const float* __restrict__ coords, float* __restrict__ norm_coords, int* __restrict__ vox,
                    int N, int r, int normalize, float eps) {
+  pdl_prologue();
   int b = blockIdx.x;
   const float* c = coords + (size_t)b * 3 * N;
   __shared__ float s_stat[4];
