@@ -29,7 +29,8 @@
 namespace lion {
 namespace tc {
 
-constexpr int THREADS = 224;       // warp 0 producer, warps 1-2 MMA issuers (even / odd row tiles), warps 3-6 epilogue
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 96 + 32 * EPI_WARPS;   // warp 0 producer, warps 1-2 MMA issuers (even / odd row tiles), warps 3-10 epilogue
 constexpr int MAX_A_STAGES = 16;   // the A ring is as deep as shared memory allows (Params::a_stages)
 constexpr int B_STAGES = 2;
 constexpr int MAX_ACC = 8;
@@ -147,27 +148,43 @@ __device__ __forceinline__ float warp_transpose_sum(float* v, int lane) {
   return v[0];
 }
 
+// per 16 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel
+// ch16(l) = 8*bit4 + 4*bit3 + 2*bit2 + bit1 of l (lanes 2k and 2k+1 hold the same channel): 16 shuffles.
+__device__ __forceinline__ float warp_transpose_sum16(float* v, int lane) {
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const int bit = half * 2;               // lane bit 16, 8, 4, 2
+    bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float keep = upper ? v[i + half] : v[i];
+      float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int ch16_of_lane(int lane) { return (lane >> 1) & 15; }
+
 template <int KG, int TPG>
 __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: see LION_LAUNCH
   extern __shared__ __align__(128) uint8_t smem[];
-  // layout: [A stages][B stages][bias NT floats][stat 4*2*128 floats][barriers][tmem ptr]
+  // layout: [A stages][B stages][bias 128 floats][stat 8*2*64 floats][barriers][tmem ptr, skip flags]
   uint8_t* sA = smem;
   const int A_STAGES = P.a_stages;
   uint8_t* sB = sA + (size_t)A_STAGES * P.a_stage_bytes;
   float* s_bias = (float*)(sB + (size_t)B_STAGES * P.b_stage_bytes);
-  float* s_stat = s_bias + 128;                 // [4 warps][2][128]
-  uint64_t* bars = (uint64_t*)(s_stat + 4 * 2 * 128);
+  float* s_stat = s_bias + 128;                 // [8 epilogue warps][2][64]
+  uint64_t* bars = (uint64_t*)(s_stat + 8 * 2 * 64);
   uint32_t* s_tmem = (uint32_t*)(bars + 64);
   volatile uint32_t* s_skip = s_tmem + 1;        // [MAX_A_STAGES] stage holds no data (all-zero input slab)
-  volatile uint32_t* s_started = s_tmem + 1 + MAX_A_STAGES;   // per item: bit j = accumulator j received MMAs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + MAX_A_STAGES);
   const uint32_t bar_full_b = smem_u32(bars + 2 * MAX_A_STAGES), bar_empty_b = smem_u32(bars + 2 * MAX_A_STAGES + B_STAGES);
-  const uint32_t bar_acc = smem_u32(bars + 2 * MAX_A_STAGES + 2 * B_STAGES);
-  const uint32_t bar_tfree = bar_acc + 8;       // MAX_ACC barriers: accumulator j drained by the epilogue
-  const uint32_t bar_meta = bar_tfree + 8 * MAX_ACC;   // s_started published for the item
+  const uint32_t bar_accf = smem_u32(bars + 2 * MAX_A_STAGES + 2 * B_STAGES);   // MAX_ACC: accumulator j complete
+  const uint32_t bar_tfree = bar_accf + 8 * MAX_ACC;                            // MAX_ACC: accumulator j drained
 
   // zero the A stages once: channel-group slots that a partial chunk does not load must hold
   // finite values (their weights are zero)
@@ -175,9 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   if (tid == 0) {
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 1); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 2); }
-    mbar_init(bar_acc, 2);
-    mbar_init(bar_meta, 2);
-    for (int i = 0; i < MAX_ACC; ++i) mbar_init(bar_tfree + 8 * i, 4);
+    for (int i = 0; i < MAX_ACC; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_tfree + 8 * i, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill -> async proxy readers
@@ -204,50 +219,51 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
 
   if (warp == 0) {
     // ===================== producer (whole warp; lane kg issues the copy of channel group kg) ====
-    {
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0;          // ring positions and phase bits
-      const uint32_t bytes = (uint32_t)P.stage_rows * 16u;
-      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        ITEM_DECODE(w)
-        (void)n0;
-        const float* wsrc = P.w + (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);
-        const unsigned char* occ_b = P.occ ? P.occ + (size_t)b * P.occ_stride : nullptr;
-        const long long row_item = (long long)P.p_begin + (long long)tile0 * 128 - P.halo;
-        const float4* in_item = P.in + (size_t)b * P.Gin * P.rows;
-        for (int cc = 0; cc < P.nchunk; ++cc) {
-          const int kg_real = min(KG, P.Gin - cc * KG);
-          const float4* in_lane = in_item + (size_t)(cc * KG + (lane < kg_real ? lane : 0)) * P.rows;
-          for (int tg = 0; tg < P.ntg; ++tg) {
-            mbar_wait(bar_empty_b + 8 * sb, pb ^ 1);
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;          // ring positions and phase bits
+    const uint32_t bytes = (uint32_t)P.stage_rows * 16u;
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      ITEM_DECODE(w)
+      (void)n0;
+      const float* wsrc = P.w + (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);
+      const unsigned char* occ_b = P.occ ? P.occ + (size_t)b * P.occ_stride : nullptr;
+      const long long row_item = (long long)P.p_begin + (long long)tile0 * 128 - P.halo;
+      const float4* in_item = P.in + (size_t)b * P.Gin * P.rows;
+      for (int cc = 0; cc < P.nchunk; ++cc) {
+        const int kg_real = min(KG, P.Gin - cc * KG);
+        const float4* in_lane = in_item + (size_t)(cc * KG + (lane < kg_real ? lane : 0)) * P.rows;
+        for (int tg = 0; tg < P.ntg; ++tg) {
+          // the last sweep of an item is never skipped: every accumulator then receives at
+          // least one (zero-initialising) MMA per item and needs no "was it touched" bookkeeping
+          const bool may_skip = occ_b && !(cc == P.nchunk - 1 && tg == P.ntg - 1);
+          mbar_wait(bar_empty_b + 8 * sb, pb ^ 1);
+          if (lane == 0) {
+            mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
+            bulk_g2s(sB_addr + sb * (uint32_t)P.b_stage_bytes, wsrc + (size_t)(cc * P.ntg + tg) * (P.b_stage_bytes / 4),
+                     P.b_stage_bytes, bar_full_b + 8 * sb);
+          }
+          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          long long row0 = row_item + P.tg_off[tg];
+          for (int j = 0; j < ntile; ++j, row0 += 128) {
+            mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
+            bool empty = false;
+            if (may_skip) {
+              long long lo = row0 < 0 ? 0 : row0, hi = row0 + P.stage_rows - 1;
+              if (hi > P.rows - 1) hi = P.rows - 1;
+              unsigned any = 0;
+              for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(occ_b + k);
+              empty = (any == 0);
+            }
+            const uint32_t full = bar_full_a + 8 * sa;
             if (lane == 0) {
-              mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
-              bulk_g2s(sB_addr + sb * (uint32_t)P.b_stage_bytes, wsrc + (size_t)(cc * P.ntg + tg) * (P.b_stage_bytes / 4),
-                       P.b_stage_bytes, bar_full_b + 8 * sb);
+              s_skip[sa] = empty ? 1u : 0u;
+              if (empty || (P.debug & 1)) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+              else mbar_expect_tx(full, bytes * kg_real);
             }
-            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
-            long long row0 = row_item + P.tg_off[tg];
-            for (int j = 0; j < ntile; ++j, row0 += 128) {
-              mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
-              bool empty = false;
-              if (occ_b) {
-                long long lo = row0 < 0 ? 0 : row0, hi = row0 + P.stage_rows - 1;
-                if (hi > P.rows - 1) hi = P.rows - 1;
-                unsigned any = 0;
-                for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(occ_b + k);
-                empty = (any == 0);
-              }
-              const uint32_t full = bar_full_a + 8 * sa;
-              if (lane == 0) {
-                s_skip[sa] = empty ? 1u : 0u;
-                if (empty || (P.debug & 1)) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
-                else mbar_expect_tx(full, bytes * kg_real);
-              }
-              __syncwarp();
-              if (!empty && !(P.debug & 1) && lane < kg_real)
-                bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, bytes, full);
-              if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
-            }
+            __syncwarp();
+            if (!empty && !(P.debug & 1) && lane < kg_real)
+              bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, bytes, full);
+            if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
           }
         }
       }
@@ -256,85 +272,82 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
     // ===================== MMA issuers: warp 1 owns even row tiles, warp 2 odd ones ==========
     // (each whole warp runs the loop; one elected lane issues).  Two issuers because a single
     // thread cannot generate descriptors + issue one UMMA every 16-32 cycles (N <= 64).
-    {
-      const int me = warp - 1;
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_pitch16 = (uint32_t)P.stage_rows;             // (bytes between channel groups) >> 4
-      const uint32_t b_pitch16 = (uint32_t)P.NT;
-      const uint32_t b_tap16 = (uint32_t)KG * b_pitch16;
-      // descriptor high words are constant: SBO = 128 B, version 1, no swizzle; LBO = group pitch
-      const uint32_t d_hi = (128u >> 4) | (1u << 14);
-      const uint32_t a_lo_c = (a_pitch16 & 0x3fff) << 16, b_lo_c = (b_pitch16 & 0x3fff) << 16;
-      const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4;
-      const uint32_t a_ring16 = (smem_u32(sA) >> 4) + (uint32_t)P.halo;
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-        ITEM_DECODE(w)
-        (void)b; (void)n0; (void)tile0;
-        uint32_t started = 0;
-        for (int cc = 0; cc < P.nchunk; ++cc) {
-          for (int tg = 0; tg < P.ntg; ++tg) {
-            mbar_wait(bar_full_b + 8 * sb, pb);
-            const uint32_t b_base16 = smem_u32(sB + (size_t)sb * P.b_stage_bytes) >> 4;
-            const bool first = (cc | tg) == 0;
-            for (int j = 0; j < ntile; ++j) {
-              const uint32_t my_sa = sa, my_pa = pa;
-              if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
-              if ((j & 1) != me) continue;                               // the other issuer's tile
-              if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);     // accumulator j drained (previous item)
-              mbar_wait(bar_full_a + 8 * my_sa, my_pa);
-              if (s_skip[my_sa]) {
-                // all-zero input slab: nothing to accumulate, hand the stage straight back
-                mbar_arrive_w(bar_empty_a + 8 * my_sa);
-                continue;
-              }
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t a_base16 = a_ring16 + my_sa * a_stage16;
-              const uint32_t d = tmem_base + (uint32_t)(j * P.NT);
-              const bool fresh = ((started >> j) & 1u) == 0;
-              started |= 1u << j;
-#pragma unroll
-              for (int t = 0; t < TPG; ++t) {
-                const uint32_t a_t = a_base16 + (uint32_t)P.tap_off[t];
-                const uint32_t b_t = b_base16 + t * b_tap16;
-#pragma unroll
-                for (int k2 = 0; k2 < KG; k2 += 2) {
-                  uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
-                  uint32_t blo = b_lo_c | ((b_t + k2 * b_pitch16) & 0x3fff);
-                  uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
-                  if (!(P.debug & 2)) umma_tf32_w(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
-                }
-              }
-              umma_commit_w(bar_empty_a + 8 * my_sa);     // frees the A stage when these MMAs retire
+    const int me = warp - 1;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_pitch16 = (uint32_t)P.stage_rows;             // (bytes between channel groups) >> 4
+    const uint32_t b_pitch16 = (uint32_t)P.NT;
+    const uint32_t b_tap16 = (uint32_t)KG * b_pitch16;
+    // descriptor high words are constant: SBO = 128 B, version 1, no swizzle; LBO = group pitch
+    const uint32_t d_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lo_c = (a_pitch16 & 0x3fff) << 16, b_lo_c = (b_pitch16 & 0x3fff) << 16;
+    const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4;
+    const uint32_t a_ring16 = (smem_u32(sA) >> 4) + (uint32_t)P.halo;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+      ITEM_DECODE(w)
+      (void)b; (void)n0; (void)tile0;
+      uint32_t started = 0;
+      // accumulators this item does not use still take part in the per-item phase bookkeeping:
+      // wait until the epilogue released them (previous item) before re-arming them below
+      for (int j = me; j < MAX_ACC; j += 2)
+        if (j >= ntile) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);
+      for (int cc = 0; cc < P.nchunk; ++cc) {
+        for (int tg = 0; tg < P.ntg; ++tg) {
+          mbar_wait(bar_full_b + 8 * sb, pb);
+          const uint32_t b_base16 = smem_u32(sB + (size_t)sb * P.b_stage_bytes) >> 4;
+          const bool first = (cc | tg) == 0;
+          const bool last = (cc == P.nchunk - 1) && (tg == P.ntg - 1);
+          for (int j = 0; j < ntile; ++j) {
+            const uint32_t my_sa = sa, my_pa = pa;
+            if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
+            if ((j & 1) != me) continue;                               // the other issuer's tile
+            if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);     // accumulator j drained (previous item)
+            mbar_wait(bar_full_a + 8 * my_sa, my_pa);
+            if (s_skip[my_sa]) {
+              // all-zero input slab: nothing to accumulate, hand the stage straight back
+              mbar_arrive_w(bar_empty_a + 8 * my_sa);
+              continue;
             }
-            umma_commit_w(bar_empty_b + 8 * sb);          // (count 2: both issuers)
-            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_base16 = a_ring16 + my_sa * a_stage16;
+            const uint32_t d = tmem_base + (uint32_t)(j * P.NT);
+            const bool fresh = ((started >> j) & 1u) == 0;
+            started |= 1u << j;
+#pragma unroll
+            for (int t = 0; t < TPG; ++t) {
+              const uint32_t a_t = a_base16 + (uint32_t)P.tap_off[t];
+              const uint32_t b_t = b_base16 + t * b_tap16;
+#pragma unroll
+              for (int k2 = 0; k2 < KG; k2 += 2) {
+                uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
+                uint32_t blo = b_lo_c | ((b_t + k2 * b_pitch16) & 0x3fff);
+                uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
+                if (!(P.debug & 2)) umma_tf32_w(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
+              }
+            }
+            umma_commit_w(bar_empty_a + 8 * my_sa);       // frees the A stage when these MMAs retire
+            if (last) umma_commit_w(bar_accf + 8 * j);    // accumulator j complete -> epilogue may drain it
           }
+          umma_commit_w(bar_empty_b + 8 * sb);            // (count 2: both issuers)
+          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
         }
-        if (lane == 0) s_started[me] = started;
-        __syncwarp();
-        mbar_arrive_w(bar_meta);
-        umma_commit_w(bar_acc);
-        // keep the two issuers in the same item: the count-2 barriers above identify arrivals by
-        // number, not by warp, so an idle issuer must not run ahead into the next item
-        asm volatile("bar.sync 2, 64;" ::: "memory");
       }
+      for (int j = me; j < MAX_ACC; j += 2)
+        if (j >= ntile) umma_commit_w(bar_accf + 8 * j);  // exactly one arrival per accumulator per item
     }
   } else {
-    // ===================== epilogue =====================
-    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =========
     const int ew = warp - 3, et = tid - 96;
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int hcol = (ew >> 2) * (P.NT / 2);       // first accumulator column of this warp's half
+    const int CH = P.NT / 2;
     uint32_t it = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
       ITEM_DECODE(w)
-      asm volatile("bar.sync 1, 128;" ::: "memory");            // previous item's s_bias / s_stat readers are done
+      asm volatile("bar.sync 1, 256;" ::: "memory");            // previous item's s_bias / s_stat readers are done
       if (et < P.NT) s_bias[et] = P.bias ? P.bias[n0 + et] : 0.0f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(bar_meta, it & 1);
-      const uint32_t started = s_started[0] | s_started[1];
-      mbar_wait(bar_acc, it & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // lane l: channels l, l+32, l+64, l+96
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // per 16-column chunk of this warp's half
       for (int j = 0; j < ntile; ++j) {
         int p = P.p_begin + (tile0 + j) * 128 + q * 32 + lane;
         bool inrange = p < P.p_end;
@@ -343,55 +356,55 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           int z = p % P.rp, y = (p / P.rp) % P.rp;
           valid = (z >= 1 && z <= P.rp - 2 && y >= 1 && y <= P.rp - 2);
         }
-        for (int c32 = 0; c32 < P.NT; c32 += 32) {
-          float v[32];
-          uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + c32);
-          if ((started >> j) & 1u) {                 // warp-uniform
-            tmem_ld16(taddr, v);
-            tmem_ld16(taddr + 16, v + 16);
-          } else {
+        mbar_wait(bar_accf + 8 * j, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int c16 = 0; c16 < CH; c16 += 16) {
+          float v[16];
+          const int col = hcol + c16;
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + col), v);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.0f;     // no occupied input near this tile: the sum is exactly zero
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = valid ? v[i] + s_bias[c32 + i] : 0.0f;
+          for (int i = 0; i < 16; ++i) v[i] = valid ? v[i] + s_bias[col + i] : 0.0f;
           if (inrange && !(P.debug & 4)) {
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-              int g = (n0 + c32) / 4 + g4;
+            for (int g4 = 0; g4 < 4; ++g4) {
+              int g = (n0 + col) / 4 + g4;
               if (g < P.Gout_store)
                 P.out[((size_t)b * P.Gout_store + g) * P.rows + p] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
             }
           }
           if (P.ssum && !(P.debug & 4)) {
-            float sq[32];
+            float sq[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sq[i] = v[i] * v[i];
-            run_s[c32 >> 5] += warp_transpose_sum(v, lane);
-            run_q[c32 >> 5] += warp_transpose_sum(sq, lane);
+            for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+            run_s[c16 >> 4] += warp_transpose_sum16(v, lane);
+            run_q[c16 >> 4] += warp_transpose_sum16(sq, lane);
           }
         }
-        // accumulator j is drained: let the MMA warp start the next item's tile j
+        // accumulator j is drained (this warp's part): let the issuers start the next item's tile j
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree + 8 * j) : "memory");
       }
       if (P.ssum) {
-        for (int k = 0; k < P.NT / 32; ++k) {
-          s_stat[(ew * 2 + 0) * 128 + k * 32 + lane] = run_s[k];
-          s_stat[(ew * 2 + 1) * 128 + k * 32 + lane] = run_q[k];
+        if ((lane & 1) == 0) {
+          for (int k = 0; k < CH / 16; ++k) {
+            s_stat[(ew * 2 + 0) * 64 + k * 16 + ch16_of_lane(lane)] = run_s[k];
+            s_stat[(ew * 2 + 1) * 64 + k * 16 + ch16_of_lane(lane)] = run_q[k];
+          }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et < P.NT) {
+          const int half = et / CH, ch = et % CH;
           float s = 0.f, qq = 0.f;
 #pragma unroll
-          for (int ww = 0; ww < 4; ++ww) { s += s_stat[(ww * 2 + 0) * 128 + et]; qq += s_stat[(ww * 2 + 1) * 128 + et]; }
+          for (int ww = 0; ww < 4; ++ww) { s += s_stat[((half * 4 + ww) * 2 + 0) * 64 + ch]; qq += s_stat[((half * 4 + ww) * 2 + 1) * 64 + ch]; }
           atomicAdd(P.ssum + (size_t)b * P.cout_pad + n0 + et, (double)s);
           atomicAdd(P.ssq + (size_t)b * P.cout_pad + n0 + et, (double)qq);
         }
       }
-      // tiles beyond ntile of this item were never touched: release them too so the phase
-      // bookkeeping of bar_tfree stays in step with the item counter
+      // accumulators this item did not use: release them too so that the phase bookkeeping of
+      // bar_tfree stays in step with the item counter
       for (int j = ntile; j < MAX_ACC; ++j) {
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree + 8 * j) : "memory");
@@ -463,7 +476,7 @@ static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, in
 int conv_tc_prepare(Model* m, ConvW& w) {
   w.tc = ConvTcW();
   if (!(w.ntaps == 27 || w.ntaps == 1)) return 0;
-  if (w.cout_pad < 16 || w.cout_pad % 16) return 0;
+  if (w.cout_pad < 32 || w.cout_pad % 32) return 0;      // epilogue splits N into two halves of 16-column chunks
   int NT, KG, nchunk, ntg, tpg;
   tc_shape(w, NT, KG, nchunk, ntg, tpg);
   if (w.cout_pad % NT) return 0;
@@ -525,13 +538,13 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LION_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.debug = dbg; }
-  const size_t fixed = 128 * 4 + 4 * 2 * 128 * 4 + 64 * 8 + 128;
+  const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128;
   long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
   int a_stages = (int)(room / P.a_stage_bytes);
   if (a_stages > tc::MAX_A_STAGES) a_stages = tc::MAX_A_STAGES;
   if (a_stages < 2) { set_error("conv_tc: shared memory cannot hold the operand pipeline (N=%d, KG=%d)", NT, KG); return LION_ERR_ARG; }
   P.a_stages = a_stages;
-  size_t smem = (size_t)a_stages * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 4 * 2 * 128 * 4 + 64 * 8 + 128;
+  size_t smem = (size_t)a_stages * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128;
   if (smem > 227 * 1024) { set_error("conv_tc: %zu bytes of shared memory needed", smem); return LION_ERR_ARG; }
   long long n_items = (long long)cdiv(ntile, G) * n_tiles_n * B;
   int grid = (int)(n_items < c->num_sms ? n_items : c->num_sms);      // persistent: one CTA per SM
