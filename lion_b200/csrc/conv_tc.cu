@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   // finite values (their weights are zero)
   for (int i = tid; i < A_STAGES * P.a_stage_bytes / 16; i += THREADS) ((float4*)sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 1); }
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 2); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 2); }
     for (int i = 0; i < MAX_ACC; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_tfree + 8 * i, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -300,9 +300,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           for (int j = 0; j < ntile; ++j) {
             const uint32_t my_sa = sa, my_pa = pa;
             if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
-            if ((j & 1) != me) continue;                               // the other issuer's tile
-            if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);     // accumulator j drained (previous item)
+            // BOTH issuers wait on every stage and both release it (empty count 2).  A parity wait is
+            // only sound for a waiter that observes every phase of a barrier: bulk copies complete out
+            // of order, so an issuer that skipped the other's stages could see a slot's barrier one
+            // phase behind and mistake "not yet loaded" for "loaded" (seen with odd ring depths).
             mbar_wait(bar_full_a + 8 * my_sa, my_pa);
+            if ((j & 1) != me) {                                       // the other issuer's tile
+              mbar_arrive_w(bar_empty_a + 8 * my_sa);
+              continue;
+            }
+            if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);     // accumulator j drained (previous item)
             if (s_skip[my_sa]) {
               // all-zero input slab: nothing to accumulate, hand the stage straight back
               mbar_arrive_w(bar_empty_a + 8 * my_sa);
@@ -465,7 +472,7 @@ static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, in
   // 16-channel chunks for N >= 64 (deep activation ring).  NOTE: 32-channel chunks with a 3-deep ring
   // (LION_TC_KG64=8) are ~10 % faster on dense inputs but fail (launch failure) together with
   // sparse-slab skipping at B=32 -- unexplained, tracked in DESIGN.md section 7.
-  if (w.ntaps == 27) KG = (NT >= 64) ? 4 : 8;
+  if (w.ntaps == 27) KG = (NT > 64) ? 4 : 8;
   else KG = 8;
   { static int kg64 = -1; if (kg64 < 0) { const char* e = getenv("LION_TC_KG64"); kg64 = e ? atoi(e) : 0; }
     if (kg64 && w.ntaps == 27 && NT == 64) KG = kg64; }
@@ -529,10 +536,21 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   int n_tiles_n = w.cout_pad / NT;
   int gmax = 512 / NT;
   if (gmax > tc::MAX_ACC) gmax = tc::MAX_ACC;
-  // enough CTAs to fill the machine about twice when the problem allows it
-  long long want = 2LL * c->num_sms;
-  int G = gmax;
-  while (G > 1 && (long long)cdiv(ntile, G) * n_tiles_n * B < want) G >>= 1;
+  // row tiles per work item: more tiles amortise the weight slab (B stage) over more MMAs but
+  // leave fewer, longer items to balance over the SMs.  Pick G by a small cost model:
+  //   rounds(G) * G * max(1, L2 bytes per stage / (MMA cycles per stage * ~38 B/clk/SM))
+  int G = 1;
+  {
+    const double mma_cycles = (double)tpg * (KG / 2) * (NT / 2.0);          // UMMA M128 x N x K8 = N/2 cycles
+    double best = 1e30;
+    for (int g = 1; g <= gmax; g <<= 1) {
+      long long items = (long long)cdiv(ntile, g) * n_tiles_n * B;
+      double rounds = (double)((items + c->num_sms - 1) / c->num_sms);
+      double bw = ((double)P.b_stage_bytes / g + P.a_stage_bytes) / (mma_cycles * 38.0);
+      double cost = rounds * g * (bw > 1.0 ? bw : 1.0);
+      if (cost < best * 0.999) { best = cost; G = g; }
+    }
+  }
   P.G = G;
   P.B = B;
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
@@ -542,6 +560,7 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
   int a_stages = (int)(room / P.a_stage_bytes);
   if (a_stages > tc::MAX_A_STAGES) a_stages = tc::MAX_A_STAGES;
+  { static int as = -1; if (as < 0) { const char* e = getenv("LION_TC_ASTAGES"); as = e ? atoi(e) : 0; } if (as > 0 && as < a_stages) a_stages = as; }
   if (a_stages < 2) { set_error("conv_tc: shared memory cannot hold the operand pipeline (N=%d, KG=%d)", NT, KG); return LION_ERR_ARG; }
   P.a_stages = a_stages;
   size_t smem = (size_t)a_stages * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128;
