@@ -314,6 +314,13 @@ def main():
     roofline = {"bound": "tensor", "kernel": "lion::tc::k_conv_tc (3x3x3 conv 64->64 @ 32^3, B=%d; 4 launches / denoising step, 49%% of FLOPs)" % B,
                 "achieved": achieved, "peak": bf16_peak / 2.0, "unit": "TFLOP/s", "frac": achieved / (bf16_peak / 2.0),
                 "ms_per_launch": ms_k.value, "flops_per_launch": fl.value, "peak_source": peak_src, "traffic": None}
+    try:   # DRAM bytes of the same kernel from the committed ncu --set full capture (B=32 only)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_fp3_traffic.json")))
+        if B == 32:
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_unit"] = "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; algorithmic %d)" % tr["algorithmic_bytes"]
+    except Exception:
+        pass
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -332,7 +339,7 @@ def main():
                        "weights": "key-seeded synthetic (tests/synth.py)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch,
             "ms_per_denoise_step_pair": ms / args.steps / T,
-            "tensor_roofline_frac_whole_job": value * GFLOP_PER_SHAPE / 1e3 / world / (bf16_peak / 2.0),
+            "tensor_roofline_frac_whole_job": (value * GFLOP_PER_SHAPE / 1e3 / world / (bf16_peak / 2.0)) if T == T_STEPS else None,
             "phases": phases, "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line))
     if world > 1:

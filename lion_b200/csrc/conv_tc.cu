@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
 
   // zero the A stages once: channel-group slots that a partial chunk does not load must hold
   // finite values (their weights are zero)
-  for (int i = tid; i < A_STAGES * P.a_stage_bytes / 16; i += THREADS) ((float4*)sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (P.Gin % KG != 0)
+    for (int i = tid; i < A_STAGES * P.a_stage_bytes / 16; i += THREADS) ((float4*)sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 2); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 2); }
