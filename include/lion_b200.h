@@ -64,7 +64,7 @@ int lion_voxel_coords(const float* coords, float* norm_coords, int* vox, int B, 
  * must stay valid (weights are re-packed into kernel layouts at creation).
  * kinds: */
 enum { LION_KIND_UNET = 1, LION_KIND_PVCONV = 2, LION_KIND_SA = 3, LION_KIND_FP = 4, LION_KIND_ATTN = 5,
-       LION_KIND_SHARED_MLP = 6, LION_KIND_GLOBAL_PRIOR = 7 };
+       LION_KIND_SHARED_MLP = 6, LION_KIND_GLOBAL_PRIOR = 7, LION_KIND_ADAGN = 8 };
 int lion_model_create(LionCtx* ctx, int kind, const int* desc, int ndesc, const float* const* params, int nparams,
                       LionModel** out);
 int lion_model_destroy(LionModel* m);
@@ -92,6 +92,12 @@ int lion_fp_module_fwd(LionModel* m, const float* points_coords, const float* ce
 int lion_linear_attention_fwd(LionModel* m, const float* x, float* out, int B, int N, void* stream);
 /* SharedMLP.forward (models/pvcnn2_ada.py:140-164): x [B,C,R] -> out [B,Cout,R] */
 int lion_shared_mlp_fwd(LionModel* m, const float* x, const float* style, float* out, int B, int R, void* stream);
+/* AdaGN.forward (models/adagn.py:45-65), stand-alone: x [B,C,R] (R = product of the trailing dims) -> out [B,C,R] */
+int lion_adagn_fwd(LionModel* m, const float* x, const float* style, float* out, int B, int R, void* stream);
+/* SE3d.forward (models/pvcnn2_ada.py:40-41): x [B,C,V] * sigmoid(W2 relu(W1 mean_V x)); w1 [C/8,C], w2 [C,C/8] */
+int lion_se3d_fwd(LionCtx* ctx, const float* w1, const float* w2, const float* x, float* out, int B, int C, int V, void* stream);
+/* Swish.forward (models/pvcnn2_ada.py:74-83): x * sigmoid(x), elementwise over n floats */
+int lion_swish_fwd(const float* x, float* out, size_t n, void* stream);
 /* Prior.forward with SE cells (models/score_sde/resnet.py:195-218): x [B,D], t [B], clip [B,clip_dim] or NULL */
 int lion_global_prior_forward(LionModel* m, const float* x, const float* t, const float* clip, float* out, int B,
                               void* stream);

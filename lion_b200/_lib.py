@@ -50,6 +50,9 @@ def _proto(lib):
         "lion_linear_attention_fwd": (P(vp, vp, vp, i, i, vp), i),
         "lion_shared_mlp_fwd": (P(vp, vp, vp, vp, i, i, vp), i),
         "lion_global_prior_forward": (P(vp, vp, vp, vp, vp, i, vp), i),
+        "lion_adagn_fwd": (P(vp, vp, vp, vp, i, i, vp), i),
+        "lion_se3d_fwd": (P(vp, vp, vp, vp, vp, i, i, i, vp), i),
+        "lion_swish_fwd": (P(vp, vp, sz, vp), i),
         "lion_ddpm_update": (P(vp, vp, vp, vp, vp, vp, f, sz, vp, i, vp), i),
         "lion_ddpm_set_step": (P(vp, vp, i, i, vp), i),
         "lion_ddpm_next_step": (P(vp, vp, i, vp), i),
@@ -123,7 +126,7 @@ def last_launches(device=None):
     return lib().lion_ctx_last_launches(ctx(device))
 
 
-KIND_UNET, KIND_PVCONV, KIND_SA, KIND_FP, KIND_ATTN, KIND_SHARED_MLP, KIND_GLOBAL_PRIOR = 1, 2, 3, 4, 5, 6, 7
+KIND_UNET, KIND_PVCONV, KIND_SA, KIND_FP, KIND_ATTN, KIND_SHARED_MLP, KIND_GLOBAL_PRIOR, KIND_ADAGN = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 def float_bits(x):

@@ -108,6 +108,7 @@ struct Model {
   std::unique_ptr<AttnBlk> attn;
   std::unique_ptr<SharedMLPBlk> mlp;
   GlobalPriorBlk* gp = nullptr;
+  AdaGNW gn_single;            // LION_KIND_ADAGN
 
   template <typename T> int dmalloc(T** p, size_t n) {
     void* q = nullptr;

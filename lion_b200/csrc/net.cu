@@ -850,6 +850,12 @@ extern "C" int lion_model_create(LionCtx* ctx, int kind, const int* desc, int nd
       break;
     }
     case LION_KIND_GLOBAL_PRIOR: LION_TRY(global_prior_build(m, cur)); break;
+    case LION_KIND_ADAGN: {        // [C, S]
+      LION_REQUIRE(need(2), "adagn descriptor: [C, style_dim]");
+      m->S = d[1];
+      LION_TRY(make_adagn(m, m->gn_single, cur, d[0]));
+      break;
+    }
     default: LION_REQUIRE(false, "lion_model_create: unknown kind %d", kind);
   }
   LION_REQUIRE(!cur.bad && cur.i == cur.n, "lion_model_create(kind %d): %d parameters given, %d consumed", kind, cur.n, cur.i);
@@ -978,6 +984,52 @@ extern "C" int lion_shared_mlp_fwd(LionModel* h, const float* x, const float* st
     from_pf(f, o, out, s.cout());
     return check_launch(f.c, "lion_shared_mlp_fwd");
   });
+}
+
+// ---- stand-alone AdaGN / SE3d / Swish (reference interfaces models/adagn.py:45-65,
+// models/pvcnn2_ada.py:27-41, :74-83); the fused path never calls these -------------------------
+extern "C" int lion_adagn_fwd(LionModel* h, const float* x, const float* style, float* out, int B, int R, void* stream) {
+  LION_REQUIRE(h && h->m.kind == LION_KIND_ADAGN, "lion_adagn_fwd: not an AdaGN model");
+  LION_REQUIRE(x && style && out && B > 0 && R > 0, "lion_adagn_fwd: bad arguments");
+  Model* m = &h->m;
+  return two_pass(m, stream, B, [&](Fwd& f) {
+    const AdaGNW& g = m->gn_single;
+    LION_TRY(style_affine_all(f, style));
+    PF xi = to_pf(f, x, g.C, R);
+    double *ssum, *ssq;
+    LION_TRY(alloc_stats(f, g.C, &ssum, &ssq));
+    LION_LAUNCH(f.c, k_row_stats, dim3(cdiv(R, 1024) > 64 ? 64 : cdiv(R, 1024), xi.G, B), 256, 0, xi.p, ssum, ssq, xi.G, R, g.C);
+    Affine a;
+    LION_TRY(run_affine(f, g, ssum, ssq, g.C, (double)R, nullptr, nullptr, a));
+    PF o = alloc_pf(f, xi.G, R);
+    LION_LAUNCH(f.c, k_act_rows<1>, dim3(cdiv(R, 256), xi.G, B), 256, 0, xi.p, o.p, a.scale, a.shift, xi.G, g.C, R, xi.G, 0, 2);
+    from_pf(f, o, out, g.C);
+    return check_launch(f.c, "lion_adagn_fwd");
+  });
+}
+extern "C" int lion_se3d_fwd(LionCtx* ctx, const float* w1, const float* w2, const float* x, float* out, int B, int C, int V,
+                             void* stream) {
+  LION_REQUIRE(ctx && w1 && w2 && x && out && B > 0 && C > 0 && C % 8 == 0 && C <= 1024 && V > 0, "lion_se3d_fwd: bad arguments");
+  Model tmp;
+  tmp.ctx = &ctx->c;
+  return two_pass(&tmp, stream, B, [&](Fwd& f) {
+    PF xi = to_pf(f, x, C, V);
+    double *ssum, *ssq;
+    LION_TRY(alloc_stats(f, xi.G * 4, &ssum, &ssq));
+    LION_LAUNCH(f.c, k_row_stats, dim3(cdiv(V, 1024) > 64 ? 64 : cdiv(V, 1024), xi.G, B), 256, 0, xi.p, ssum, ssq, xi.G, V, xi.G * 4);
+    float* gate = f.c->alloc_n<float>((size_t)B * C);
+    LION_LAUNCH(f.c, k_se_gate, B, C, (C + C / 8) * sizeof(float), ssum, xi.G * 4, w1, w2, gate, C, (double)V);
+    size_t total = (size_t)B * C * V;
+    LION_LAUNCH(f.c, k_scale_or_swish, (unsigned)cdivz(total, 256), 256, 0, x, gate, out, (size_t)V, total);
+    return check_launch(f.c, "lion_se3d_fwd");
+  });
+}
+extern "C" int lion_swish_fwd(const float* x, float* out, size_t n, void* stream) {
+  LION_REQUIRE(x && out && n > 0, "lion_swish_fwd: bad arguments");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_scale_or_swish, (unsigned)cdivz(n, 256), 256, 0, x, (const float*)nullptr, out, (size_t)1, n);
+  return check_launch(&c, "lion_swish_fwd");
 }
 
 extern "C" int lion_global_prior_forward(LionModel* h, const float* x, const float* t, const float* clip, float* out,

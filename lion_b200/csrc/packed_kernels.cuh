@@ -394,7 +394,7 @@ __global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ o
 // POOL > 1: max over POOL consecutive rows (neighbours of one centre) after the activation.
 template <int POOL>
 __global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
-                           const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off, int to_tf32) {
+                           const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off, int flags) {
   pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,11 +402,62 @@ __global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ o
   float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
   float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
   const float4* src = in + ((size_t)b * G + g) * (size_t)R_out * POOL + (size_t)i * POOL;
-  float4 r = f4_swish(f4_affine(src[0], s, t));
+  float4 r = f4_affine(src[0], s, t);
+  if (!(flags & 2)) r = f4_swish(r);
 #pragma unroll 4
   for (int k = 1; k < POOL; ++k) r = f4_max(r, f4_swish(f4_affine(src[k], s, t)));
-  if (to_tf32) r = f4_tf32(r);
+  if (flags & 1) r = f4_tf32(r);
   out[((size_t)b * Gd + g_off + g) * R_out + i] = r;
+}
+
+// per-channel sum / sum of squares over the rows of a PF (stand-alone AdaGN / SE3d entry points;
+// on the fused path these statistics come out of the convolution epilogue instead)
+__global__ void k_row_stats(const float4* __restrict__ in, double* __restrict__ ssum, double* __restrict__ ssq, int G, int R,
+                            int stat_stride) {
+  pdl_prologue();
+  int b = blockIdx.z, g = blockIdx.y;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R; i += gridDim.x * blockDim.x) {
+    float4 v = in[((size_t)b * G + g) * R + i];
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = warp_sum(s[j]), c = warp_sum(q[j]);
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd(ssum + (size_t)b * stat_stride + g * 4 + j, (double)a);
+      atomicAdd(ssq + (size_t)b * stat_stride + g * 4 + j, (double)c);
+    }
+  }
+}
+
+// SE3d gate from channel means (models/pvcnn2_ada.py:27-41): gate[b][c] = sigmoid(W2 relu(W1 mean)); grid = B, block = C
+__global__ void k_se_gate(const double* __restrict__ ssum, int stat_stride, const float* __restrict__ w1, const float* __restrict__ w2,
+                          float* __restrict__ gate, int C, double count) {
+  pdl_prologue();
+  extern __shared__ float s_f[];
+  int b = blockIdx.x, c = threadIdx.x, H = C / 8;
+  float* s_h = s_f + C;
+  s_f[c] = (float)(ssum[(size_t)b * stat_stride + c] / count);
+  __syncthreads();
+  if (c < H) {
+    float a = 0.0f;
+    for (int k = 0; k < C; ++k) a = fmaf(w1[c * C + k], s_f[k], a);
+    s_h[c] = fmaxf(a, 0.0f);
+  }
+  __syncthreads();
+  float a = 0.0f;
+  for (int k = 0; k < H; ++k) a = fmaf(w2[c * H + k], s_h[k], a);
+  gate[(size_t)b * C + c] = 1.0f / (1.0f + expf(-a));
+}
+// y = x * gate[b][c] on channel-major data [B][C][V];  also plain swish when gate == nullptr
+__global__ void k_scale_or_swish(const float* __restrict__ x, const float* __restrict__ gate, float* __restrict__ y, size_t V, size_t total) {
+  pdl_prologue();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float v = x[i];
+  y[i] = gate ? v * gate[i / V] : swishf(v);
 }
 
 // copy groups of a PF into another PF at a group offset (channel concatenation)

@@ -4,11 +4,13 @@ Parameter names match the reference (`norm.weight/bias`, `emd.weight/bias`; rows
 `emd` are the factor, [C:2C] the bias, adagn.py:62).  On the hot path the parent block
 (SharedMLP / PVConv) hands these tensors to the fused kernels, which take the GroupNorm
 statistics from the producing convolution's epilogue and fold GroupNorm + style affine into a
-single per-(sample, channel) scale/shift; a stand-alone call runs the same kernels through a
-one-layer identity path (`lion_b200._lib` raises if the CUDA library is missing).
+single per-(sample, channel) scale/shift; a stand-alone call (`forward`) runs the same affine
+through `lion_adagn_fwd` with a separate statistics kernel.
 """
+import torch
 import torch.nn as nn
 
+from .. import _lib as L
 from .dense import dense
 
 
@@ -32,6 +34,16 @@ class AdaGN(nn.Module):
     def lion_params(self):
         return [self.norm.weight, self.norm.bias, self.emd.weight, self.emd.bias]
 
+    @torch.no_grad()
     def forward(self, image, style):
-        raise NotImplementedError(
-            "lion_b200: AdaGN is evaluated inside the fused SharedMLP / PVConv kernels; call the parent block")
+        """image [B, C, ...] (ndim trailing dims), style [B, style_dim] -> same shape as image."""
+        assert style.dim() == 2, 'get {} {}'.format(style.shape, len(style.shape))
+        assert image.dim() == self.ndim + 2, 'get {} {}'.format(image.shape, len(image.shape))
+        shape = image.shape
+        x = image.detach().to(torch.float32).contiguous().view(shape[0], shape[1], -1)
+        style = style.detach().to(torch.float32).contiguous()
+        m = L.model_for(self, L.KIND_ADAGN, [self.n_channel, self.style_dim], self.lion_params())
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            L.check(L.lib().lion_adagn_fwd(m.h, L.ptr(x), L.ptr(style), L.ptr(out), shape[0], x.shape[2], L.stream()), "adagn_fwd")
+        return out.view(shape)

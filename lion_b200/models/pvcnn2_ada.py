@@ -45,8 +45,17 @@ class SE3d(nn.Module):
     def lion_params(self):
         return [self.fc[0].weight, self.fc[2].weight]
 
+    @torch.no_grad()
     def forward(self, inputs):
-        raise NotImplementedError("lion_b200: SE3d is folded into PVConv's fused kernels; call PVConv")
+        """inputs [B,C,r,r,r] -> inputs * sigmoid(fc(mean_xyz inputs)) (stand-alone; PVConv folds this gate)."""
+        shape = inputs.shape
+        x = _f32c(inputs).view(shape[0], shape[1], -1)
+        w1, w2 = self.fc[0].weight.detach().contiguous(), self.fc[2].weight.detach().contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _run(L.lib().lion_se3d_fwd, L.ctx(x.device), L.ptr(w1), L.ptr(w2), L.ptr(x), L.ptr(out), shape[0], shape[1],
+                 x.shape[2], L.stream())
+        return out.view(shape)
 
 
 class LinearAttention(nn.Module):
@@ -74,15 +83,22 @@ class LinearAttention(nn.Module):
         return out
 
 
+@torch.no_grad()
 def swish(input):
-    raise NotImplementedError("lion_b200: swish is fused into the producing kernels")
+    """x * sigmoid(x) (pvcnn2_ada.py:74-75); stand-alone kernel -- the fused blocks apply it on load."""
+    x = _f32c(input)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _run(L.lib().lion_swish_fwd, L.ptr(x), L.ptr(out), x.numel(), L.stream())
+    return out
 
 
 class Swish(nn.Module):
-    """Placeholder keeping the reference's module numbering inside SharedMLP / PVConv."""
+    """Keeps the reference's module numbering inside SharedMLP / PVConv; the fused blocks apply the
+    activation inside their kernels, a stand-alone call runs `lion_swish_fwd`."""
 
     def forward(self, input):
-        raise NotImplementedError("lion_b200: Swish is fused into the producing kernels")
+        return swish(input)
 
 
 class BallQuery(nn.Module):

@@ -82,3 +82,21 @@ def test_fp_module(cc, cp, outs, N, M):
     blk = dict(kind="fp", cin=cc + cp, mlp=outs)
     o, _ = ON.fp_module(sd, "", blk, pc, cctr, cf, pf, None, style)
     assert_close(out, o, TOL, "FP module")
+
+
+@pytest.mark.parametrize("C,shape", [(64, (5, 7, 3)), (32, (300,)), (128, (40, 32))])
+def test_adagn_standalone(C, shape):
+    from lion_b200.models.adagn import AdaGN
+    m, sd = _load(AdaGN(len(shape), _cfg(), C), 26)
+    x, style = gen(14, 2, C, *shape), gen(15, 2, 128)
+    assert_close(m(x.cuda(), style.cuda()), ON.adagn(sd, "", x, style), 1e-5, "AdaGN")
+
+
+def test_se3d_and_swish_standalone():
+    from lion_b200.models.pvcnn2_ada import SE3d, Swish
+    m, sd = _load(SE3d(64), 27)
+    x = gen(16, 2, 64, 8, 8, 8)
+    se = x.mean(-1).mean(-1).mean(-1)
+    ref = x * torch.sigmoid(torch.relu(se @ sd["fc.0.weight"].T) @ sd["fc.2.weight"].T)[:, :, None, None, None]
+    assert_close(m(x.cuda()), ref, 1e-5, "SE3d")
+    assert_close(Swish()(x.cuda()), x * torch.sigmoid(x), 1e-5, "Swish")
