@@ -81,12 +81,11 @@ struct Ctx {
 
 int ctx_reserve(Ctx* c, size_t bytes);   // grow arena (sync; not capturable)
 
-// launch helper: skipped in dry mode; counts launches.  Kernels are launched with
-// programmatic stream serialization (PDL): every kernel starts with pdl_wait() (blocks until
-// the previous kernel in the stream has completed and flushed) preceded by pdl_trigger()
-// (lets the NEXT kernel's blocks be scheduled as soon as this one's last wave is resident),
-// which hides the ~2-3 us launch + drain/fill bubble between the ~300 dependent kernels of a
-// denoising step, inside CUDA graphs as well.
+// launch helper: skipped in dry mode; counts launches.  With Ctx::pdl (LION_PDL=1) kernels are
+// launched with programmatic stream serialization: every kernel starts with pdl_prologue()
+// (launch_dependents, then wait for the previous kernel to complete and flush).  Measured on
+// B200 inside the CUDA-graph-captured step: no gain (the step is the sum of kernel times, not of
+// launch gaps), so it is off by default.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(cudaStream_t stream, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -468,11 +468,10 @@ static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, in
   ntg = w.ntaps == 27 ? 3 : 1;
   tpg = w.ntaps == 27 ? 9 : 1;
   int G = w.cin_pad / 4;
-  // 16-channel chunks for the 3x3x3 case: a 9-tap weight slab is then <= 72 KB, two of them fit
-  // next to a deep (>= 6 stage) ring of activation slabs; the 1x1 case uses 32-channel chunks
-  // 16-channel chunks for N >= 64 (deep activation ring).  NOTE: 32-channel chunks with a 3-deep ring
-  // (LION_TC_KG64=8) are ~10 % faster on dense inputs but fail (launch failure) together with
-  // sparse-slab skipping at B=32 -- unexplained, tracked in DESIGN.md section 7.
+  // 3x3x3: 32-channel chunks (36 UMMAs per activation stage) for N <= 64 -- the per-stage barrier
+  // round trip is amortised over more MMAs, ~15 % faster than 16-channel chunks -- and 16-channel
+  // chunks for N = 128, where the 9-tap weight slab (2 x 72 KB) leaves room for a 16-channel ring only.
+  // 1x1: 32-channel chunks.
   if (w.ntaps == 27) KG = (NT > 64) ? 4 : 8;
   else KG = 8;
   { static int kg64 = -1; if (kg64 < 0) { const char* e = getenv("LION_TC_KG64"); kg64 = e ? atoi(e) : 0; }
