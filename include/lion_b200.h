@@ -25,6 +25,9 @@ int lion_ctx_destroy(LionCtx* ctx);
 /* kernels launched by the last network-level call on this context (bench.py: gpu_launches) */
 int lion_ctx_last_launches(LionCtx* ctx);
 size_t lion_ctx_arena_bytes(LionCtx* ctx);
+/* device scratch the context currently owns (arena + persistent zero grid).  Entry points size it with a dry
+ * pass and grow it on demand -- outside stream capture: run one eager call per shape before capturing. */
+size_t lion_workspace_bytes(LionCtx* ctx);
 
 /* ---------------------------------------------------------------------------------------
  * The seven operators of third_party/pvcnn/functional (reference layouts: features [B,C,N]
@@ -64,7 +67,7 @@ int lion_voxel_coords(const float* coords, float* norm_coords, int* vox, int B, 
  * must stay valid (weights are re-packed into kernel layouts at creation).
  * kinds: */
 enum { LION_KIND_UNET = 1, LION_KIND_PVCONV = 2, LION_KIND_SA = 3, LION_KIND_FP = 4, LION_KIND_ATTN = 5,
-       LION_KIND_SHARED_MLP = 6, LION_KIND_GLOBAL_PRIOR = 7, LION_KIND_ADAGN = 8 };
+       LION_KIND_SHARED_MLP = 6, LION_KIND_GLOBAL_PRIOR = 7, LION_KIND_ADAGN = 8, LION_KIND_CONV3D = 9 };
 int lion_model_create(LionCtx* ctx, int kind, const int* desc, int ndesc, const float* const* params, int nparams,
                       LionModel** out);
 int lion_model_destroy(LionModel* m);
@@ -98,9 +101,19 @@ int lion_adagn_fwd(LionModel* m, const float* x, const float* style, float* out,
 int lion_se3d_fwd(LionCtx* ctx, const float* w1, const float* w2, const float* x, float* out, int B, int C, int V, void* stream);
 /* Swish.forward (models/pvcnn2_ada.py:74-83): x * sigmoid(x), elementwise over n floats */
 int lion_swish_fwd(const float* x, float* out, size_t n, void* stream);
+/* nn.Conv3d(Cin, Cout, 3, stride 1, padding 1) of a PVConv (models/pvcnn2_ada.py:211-222), stand-alone, with
+ * the fused GroupNorm statistics of the following AdaGN (models/adagn.py:36).  Model kind LION_KIND_CONV3D,
+ * descriptor [Cin, Cout, r], parameters [weight [Cout,Cin,3,3,3], bias [Cout]].  x [B,Cin,r,r,r] ->
+ * out [B,Cout,r,r,r]; gn_sum / gn_sqsum (both or neither; [B,Cout] doubles) receive per (shape, channel) the
+ * sum and the sum of squares of the outputs over the r^3 voxels.  TF32 operands, fp32 accumulation, like the
+ * reference's cuDNN path under torch's default flags. */
+int lion_conv3d_gn_fwd(LionModel* m, const float* x, float* out, double* gn_sum, double* gn_sqsum, int B, void* stream);
 /* Prior.forward with SE cells (models/score_sde/resnet.py:195-218): x [B,D], t [B], clip [B,clip_dim] or NULL */
 int lion_global_prior_forward(LionModel* m, const float* x, const float* t, const float* clip, float* out, int B,
                               void* stream);
+/* the same call under the name SURVEY.md 8(b) lists (one denoising-step evaluation of the global prior) */
+int lion_global_prior_step(LionModel* m, const float* x, const float* t, const float* clip, float* out, int B,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * One ancestral DDPM step (utils/diffusion_pvd.py:283-296 + :475-486), elementwise over n.
@@ -119,6 +132,22 @@ int lion_ddpm_update(const float* x, const float* eps, const float* noise, float
 /* set / decrement the device-side step counter and write the model's timestep (t+1, 1..T) into t_out[B] */
 int lion_ddpm_set_step(int* step_ptr, float* t_out, int B, int t_index, void* stream);
 int lion_ddpm_next_step(int* step_ptr, float* t_out, int B, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * One DDIM step (utils/diffusion_pvd.py:389-473, update at :450 and :464-465), elementwise:
+ *   x_out = x*a + (c*eps + sigma*noise[i])        row i of `tables` ([S][4] fp32) = {a, c, sigma, t_i + 1}
+ * with a = sqrt(abar_next/abar_t), c = sqrt(1-abar_next-sigma^2) - sqrt(1-abar_t)*a and sigma
+ * built on the host with the reference's own fp32 scalar expressions; i = *step_ptr (0..S-1,
+ * ascending) is read on the device so the captured step graph can be replayed.  `noise` is the
+ * whole [S][n] block of per-step draws (the reference draws them on the CPU generator, one per
+ * step including the last, where sigma = 0) or NULL (treated as zeros); hist (optional, [S][n])
+ * receives every intermediate (output_list).  x_out may alias x.
+ * ------------------------------------------------------------------------------------- */
+int lion_ddim_update(const float* x, const float* eps, const float* noise, float* x_out, const float* tables,
+                     const int* step_ptr, size_t n, float* hist, void* stream);
+/* set / increment the device-side step index and write the model's timestep tables[i][3] into t_out[B] */
+int lion_ddim_set_step(int* step_ptr, float* t_out, const float* tables, int B, int S, int index, void* stream);
+int lion_ddim_next_step(int* step_ptr, float* t_out, const float* tables, int B, int S, void* stream);
 
 /* measurement hook (bench.py roofline leg): average device time of `iters` launches of the
  * convolution kernel alone (CUDA events on `stream`), on synthetic data: ntaps = 27 -> 3x3x3

@@ -56,6 +56,12 @@ def _proto(lib):
         "lion_ddpm_update": (P(vp, vp, vp, vp, vp, vp, f, sz, vp, i, vp), i),
         "lion_ddpm_set_step": (P(vp, vp, i, i, vp), i),
         "lion_ddpm_next_step": (P(vp, vp, i, vp), i),
+        "lion_conv3d_gn_fwd": (P(vp, vp, vp, vp, vp, i, vp), i),
+        "lion_global_prior_step": (P(vp, vp, vp, vp, vp, i, vp), i),
+        "lion_workspace_bytes": (P(vp), sz),
+        "lion_ddim_update": (P(vp, vp, vp, vp, vp, vp, sz, vp, vp), i),
+        "lion_ddim_set_step": (P(vp, vp, vp, i, i, i, vp), i),
+        "lion_ddim_next_step": (P(vp, vp, vp, i, i, vp), i),
         "lion_bench_conv": (P(vp, i, i, i, i, i, i, i, C.POINTER(f), C.POINTER(C.c_double), vp), i),
     }
     for name, (args, res) in sig.items():
@@ -126,7 +132,7 @@ def last_launches(device=None):
     return lib().lion_ctx_last_launches(ctx(device))
 
 
-KIND_UNET, KIND_PVCONV, KIND_SA, KIND_FP, KIND_ATTN, KIND_SHARED_MLP, KIND_GLOBAL_PRIOR, KIND_ADAGN = 1, 2, 3, 4, 5, 6, 7, 8
+KIND_UNET, KIND_PVCONV, KIND_SA, KIND_FP, KIND_ATTN, KIND_SHARED_MLP, KIND_GLOBAL_PRIOR, KIND_ADAGN, KIND_CONV3D = 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 def float_bits(x):

@@ -45,6 +45,34 @@ __global__ void k_ddpm_set_step(int* step, float* t_out, int B, int t_index, int
   for (int b = threadIdx.x; b < B; b += blockDim.x) t_out[b] = (float)(t + 1);
 }
 
+// DDIM update (reference: utils/diffusion_pvd.py:450-465):  x = x_noisy * a;  x += c*eps + sigma*z
+// with the 0-dim fp32 scalars a = sqrt(abar_next/abar_t), c, sigma of step i (host-built table
+// row { a, c, sigma, t+1 }, see DiffusionDiscretized._ddim_tables); same operation order, no FMA.
+// noise is the whole [S][n] block of the run's draws; row i is consumed at step i.
+__global__ void k_ddim_update(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                              float* __restrict__ xo, const float4* __restrict__ tables, const int* __restrict__ step,
+                              size_t n, float* __restrict__ hist) {
+  pdl_prologue();
+  int s = *step;
+  float4 c = tables[s];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float z = noise ? noise[(size_t)s * n + i] : 0.0f;
+  float r = __fadd_rn(__fmul_rn(x[i], c.x), __fadd_rn(__fmul_rn(c.y, eps[i]), __fmul_rn(c.z, z)));
+  xo[i] = r;
+  if (hist) hist[(size_t)s * n + i] = r;
+}
+
+// step index i -> i+1 (or set), and the model's timestep vector t_out[b] = tables[i].w
+__global__ void k_ddim_set_step(int* step, float* t_out, const float4* __restrict__ tables, int B, int S, int index, int advance) {
+  pdl_prologue();
+  int s = advance ? (*step + 1) : index;
+  __syncthreads();
+  if (threadIdx.x == 0) *step = s;
+  float t = s < S ? tables[s].w : 0.0f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) t_out[b] = t;
+}
+
 }  // namespace lion
 
 using namespace lion;
@@ -70,4 +98,27 @@ extern "C" int lion_ddpm_next_step(int* step_ptr, float* t_out, int B, void* str
   c.stream = (cudaStream_t)stream;
   LION_LAUNCH(&c, k_ddpm_set_step, 1, 64, 0, step_ptr, t_out, B, 0, 1);
   return check_launch(&c, "lion_ddpm_next_step");
+}
+
+extern "C" int lion_ddim_update(const float* x, const float* eps, const float* noise, float* x_out, const float* tables,
+                                const int* step_ptr, size_t n, float* hist, void* stream) {
+  LION_REQUIRE(x && eps && x_out && tables && step_ptr && n > 0, "lion_ddim_update: bad arguments");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_ddim_update, (unsigned)cdivz(n, 256), 256, 0, x, eps, noise, x_out, (const float4*)tables, step_ptr, n, hist);
+  return check_launch(&c, "lion_ddim_update");
+}
+extern "C" int lion_ddim_set_step(int* step_ptr, float* t_out, const float* tables, int B, int S, int index, void* stream) {
+  LION_REQUIRE(step_ptr && t_out && tables && B > 0 && S > 0 && index >= 0 && index < S, "lion_ddim_set_step: bad arguments");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_ddim_set_step, 1, 64, 0, step_ptr, t_out, (const float4*)tables, B, S, index, 0);
+  return check_launch(&c, "lion_ddim_set_step");
+}
+extern "C" int lion_ddim_next_step(int* step_ptr, float* t_out, const float* tables, int B, int S, void* stream) {
+  LION_REQUIRE(step_ptr && t_out && tables && B > 0 && S > 0, "lion_ddim_next_step: bad arguments");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_ddim_set_step, 1, 64, 0, step_ptr, t_out, (const float4*)tables, B, S, 0, 1);
+  return check_launch(&c, "lion_ddim_next_step");
 }

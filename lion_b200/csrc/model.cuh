@@ -109,6 +109,7 @@ struct Model {
   std::unique_ptr<SharedMLPBlk> mlp;
   GlobalPriorBlk* gp = nullptr;
   AdaGNW gn_single;            // LION_KIND_ADAGN
+  ConvW conv_single;           // LION_KIND_CONV3D
 
   template <typename T> int dmalloc(T** p, size_t n) {
     void* q = nullptr;

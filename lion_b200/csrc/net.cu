@@ -798,6 +798,7 @@ extern "C" int lion_ctx_destroy(LionCtx* h) {
 }
 extern "C" int lion_ctx_last_launches(LionCtx* h) { return h ? h->c.launches : 0; }
 extern "C" size_t lion_ctx_arena_bytes(LionCtx* h) { return h ? h->c.cap : 0; }
+extern "C" size_t lion_workspace_bytes(LionCtx* h) { return h ? h->c.cap + h->c.zgrid_cap : 0; }
 
 extern "C" int lion_model_create(LionCtx* ctx, int kind, const int* desc, int ndesc, const float* const* params,
                                  int nparams, LionModel** out) {
@@ -854,6 +855,13 @@ extern "C" int lion_model_create(LionCtx* ctx, int kind, const int* desc, int nd
       LION_REQUIRE(need(2), "adagn descriptor: [C, style_dim]");
       m->S = d[1];
       LION_TRY(make_adagn(m, m->gn_single, cur, d[0]));
+      break;
+    }
+    case LION_KIND_CONV3D: {       // [cin, cout, r]
+      LION_REQUIRE(need(3) && d[0] > 0 && d[1] > 0 && d[2] > 0 && d[2] <= 64, "conv3d descriptor: [cin, cout, r]");
+      const float* w = cur.next(); const float* bi = cur.next();
+      LION_REQUIRE(!cur.bad, "conv3d: parameters are [weight, bias]");
+      LION_TRY(make_conv(m, m->conv_single, w, bi, 27, d[0], d[1], ident_map(d[0])));
       break;
     }
     default: LION_REQUIRE(false, "lion_model_create: unknown kind %d", kind);
@@ -1030,6 +1038,40 @@ extern "C" int lion_swish_fwd(const float* x, float* out, size_t n, void* stream
   c.stream = (cudaStream_t)stream;
   LION_LAUNCH(&c, k_scale_or_swish, (unsigned)cdivz(n, 256), 256, 0, x, (const float*)nullptr, out, (size_t)1, n);
   return check_launch(&c, "lion_swish_fwd");
+}
+
+// ---- stand-alone Conv3d 3x3x3 + fused GroupNorm statistics (reference: nn.Conv3d in
+// models/pvcnn2_ada.py:211-222 followed by AdaGN's GroupNorm, models/adagn.py:36) -----------------
+extern "C" int lion_conv3d_gn_fwd(LionModel* h, const float* x, float* out, double* gn_sum, double* gn_sqsum, int B, void* stream) {
+  LION_REQUIRE(h && h->m.kind == LION_KIND_CONV3D, "lion_conv3d_gn_fwd: not a conv3d model");
+  LION_REQUIRE(x && out && B > 0 && ((gn_sum == nullptr) == (gn_sqsum == nullptr)), "lion_conv3d_gn_fwd: bad arguments");
+  Model* m = &h->m;
+  return two_pass(m, stream, B, [&](Fwd& f) -> int {
+    const ConvW& w = m->conv_single;
+    const int cin = m->desc[0], cout = m->desc[1], r = m->desc[2];
+    const int Gin = w.cin_pad / 4, Gout = (cout + 3) / 4, rp = r + 2, V = r * r * r;
+    const size_t P = (size_t)rp * rp * rp;
+    float4* gi = alloc_vg(f, Gin, r);
+    LION_TRY(memset_async(f.c, gi, 0, sizeof(float4) * (size_t)B * Gin * P));
+    LION_LAUNCH(f.c, k_cm_to_vg, dim3(cdiv(V, 256), Gin, B), 256, 0, x, gi, cin, Gin, r, 1);
+    float4* go = alloc_vg(f, Gout, r);
+    double *ssum = nullptr, *ssq = nullptr;
+    if (gn_sum) LION_TRY(alloc_stats(f, w.cout_pad, &ssum, &ssq));
+    LION_TRY(run_conv(f, w, gi, Gin, go, Gout, ssum, ssq, geom_grid(r)));
+    LION_LAUNCH(f.c, k_vg_to_cm, dim3(cdiv(V, 256), Gout, B), 256, 0, go, out, cout, Gout, r);
+    if (gn_sum && !f.c->dry) {
+      LION_CHECK_CUDA(cudaMemcpy2DAsync(gn_sum, sizeof(double) * cout, ssum, sizeof(double) * w.cout_pad, sizeof(double) * cout, B,
+                                        cudaMemcpyDeviceToDevice, f.c->stream));
+      LION_CHECK_CUDA(cudaMemcpy2DAsync(gn_sqsum, sizeof(double) * cout, ssq, sizeof(double) * w.cout_pad, sizeof(double) * cout, B,
+                                        cudaMemcpyDeviceToDevice, f.c->stream));
+    }
+    return check_launch(f.c, "lion_conv3d_gn_fwd");
+  });
+}
+
+extern "C" int lion_global_prior_step(LionModel* h, const float* x, const float* t, const float* clip, float* out, int B,
+                                      void* stream) {
+  return lion_global_prior_forward(h, x, t, clip, out, B, stream);
 }
 
 extern "C" int lion_global_prior_forward(LionModel* h, const float* x, const float* t, const float* clip, float* out,

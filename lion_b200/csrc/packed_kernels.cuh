@@ -731,6 +731,42 @@ __global__ void k_pf_to_cm(const float4* __restrict__ src, float* __restrict__ d
     if (c < C) dst[((size_t)b * C + c) * R + i] = vv[j];
   }
 }
+// dense voxel tensor [B][C][r^3] (flat index x*r^2 + y*r + z) <-> zero-haloed VG [B][G][(r+2)^3][4];
+// the halo rows of the VG must already be zero.  tf32 != 0: round to TF32 (rna) for the tensor cores.
+__global__ void k_cm_to_vg(const float* __restrict__ src, float4* __restrict__ dst, int C, int G, int r, int tf32) {
+  pdl_prologue();
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int V = r * r * r, rp = r + 2;
+  if (i >= V) return;
+  int x = i / (r * r), y = (i / r) % r, z = i % r;
+  size_t prow = ((size_t)(x + 1) * rp + (y + 1)) * rp + (z + 1);
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = g * 4 + j;
+    v[j] = c < C ? src[((size_t)b * C + c) * V + i] : 0.0f;
+  }
+  float4 o = make_float4(v[0], v[1], v[2], v[3]);
+  if (tf32) o = f4_tf32(o);
+  dst[((size_t)b * G + g) * ((size_t)rp * rp * rp) + prow] = o;
+}
+__global__ void k_vg_to_cm(const float4* __restrict__ src, float* __restrict__ dst, int C, int G, int r) {
+  pdl_prologue();
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int V = r * r * r, rp = r + 2;
+  if (i >= V) return;
+  int x = i / (r * r), y = (i / r) % r, z = i % r;
+  size_t prow = ((size_t)(x + 1) * rp + (y + 1)) * rp + (z + 1);
+  float4 v = src[((size_t)b * G + g) * ((size_t)rp * rp * rp) + prow];
+  float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = g * 4 + j;
+    if (c < C) dst[((size_t)b * C + c) * V + i] = vv[j];
+  }
+}
 __global__ void k_cm_to_c4(const float* __restrict__ src, float4* __restrict__ dst, int N) {
   pdl_prologue();
   int b = blockIdx.y;

@@ -31,6 +31,40 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
+class Conv3d(nn.Conv3d):
+    """nn.Conv3d(cin, cout, 3, stride=1, padding=1) as PVConv builds it (reference:
+    models/pvcnn2_ada.py:211-222), evaluated stand-alone by the tcgen05 convolution kernel
+    (lion_conv3d_gn_fwd).  Same parameters / state_dict keys as nn.Conv3d.  PVConv itself does
+    not go through this class (its convolutions run inside the fused lion_pvconv_fwd /
+    lion_unet_forward calls); it exists so the convolution can be used and checked on its own."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=True):
+        assert kernel_size == 3 and stride == 1 and padding == 1 and bias, \
+            "lion_b200: only the 3x3x3 / stride 1 / padding 1 / bias convolution of PVConv is provided"
+        super().__init__(in_channels, out_channels, 3, stride=1, padding=1, bias=True)
+
+    def lion_params(self):
+        return [self.weight, self.bias]
+
+    @torch.no_grad()
+    def forward(self, inputs, return_gn_stats=False):
+        """inputs [B,Cin,r,r,r] -> [B,Cout,r,r,r]; with return_gn_stats also the per (shape, channel)
+        sum and sum of squares over the voxels (float64 [B,Cout]) that the kernel's epilogue
+        accumulates for the AdaGN that follows."""
+        B, C, r = inputs.shape[0], inputs.shape[1], inputs.shape[2]
+        assert C == self.in_channels and inputs.dim() == 5 and inputs.shape[3] == r and inputs.shape[4] == r
+        x = _f32c(inputs)
+        m = L.model_for(self, L.KIND_CONV3D, [self.in_channels, self.out_channels, r], self.lion_params())
+        out = torch.empty(B, self.out_channels, r, r, r, device=x.device, dtype=torch.float32)
+        ssum = ssq = None
+        if return_gn_stats:
+            ssum = torch.empty(B, self.out_channels, device=x.device, dtype=torch.float64)
+            ssq = torch.empty_like(ssum)
+        with torch.cuda.device(x.device):
+            _run(L.lib().lion_conv3d_gn_fwd, m.h, L.ptr(x), L.ptr(out), L.ptr(ssum), L.ptr(ssq), B, L.stream())
+        return (out, ssum, ssq) if return_gn_stats else out
+
+
 class SE3d(nn.Module):
     def __init__(self, channel, reduction=8):
         super().__init__()

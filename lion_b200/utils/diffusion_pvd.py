@@ -160,11 +160,40 @@ class DiffusionDiscretized(object):
         model.train()
         return x_image, {'pred_x': pred_x}
 
+    def _ddim_tables(self, steps, kappa, device):
+        """[S][4] fp32 rows {a, c, sigma, t+1} consumed by lion_ddim_update, built with the
+        reference's own fp32 scalar expressions (diffusion_pvd.py:437-451)."""
+        Alpha_bar = self._alpha_bars.cpu()
+        rows = []
+        for i, t in enumerate(steps):
+            if i == len(steps) - 1:
+                assert t == 0
+                alpha_next = torch.tensor(1.0)
+                sigma = torch.tensor(0.0)
+            else:
+                alpha_next = Alpha_bar[steps[i + 1]]
+                sigma = kappa * torch.sqrt((1 - alpha_next) / (1 - Alpha_bar[t]) * (1 - Alpha_bar[t] / alpha_next))
+            a = torch.sqrt(alpha_next / Alpha_bar[t])
+            c = torch.sqrt(1 - alpha_next - sigma ** 2) - torch.sqrt(1 - Alpha_bar[t]) * torch.sqrt(alpha_next / Alpha_bar[t])
+            rows.append(torch.stack([a, c, sigma.to(torch.float32), torch.tensor(float(t + 1))]))
+        return torch.stack(rows).to(torch.float32).contiguous().to(device)
+
     @torch.no_grad()
     def run_ddim(self, model, num_samples, shape, temp=1.0, enable_autocast=False, is_image=True, prior_var=1.0,
                  condition_input=None, ddim_step=100, skip_type='uniform', kappa=1.0, clip_feat=None, grid_emb=None,
-                 x_noisy=None, dae_index=-1):
-        """DDIM sampler on the same networks (reference: diffusion_pvd.py:389-473)."""
+                 x_noisy=None, dae_index=-1, given_noise=None):
+        """DDIM sampler on the same networks (reference: diffusion_pvd.py:389-473): S = ddim_step model
+        calls instead of T.  Like the DDPM loop, the step (model forward + update + step counter)
+        is captured in a CUDA graph and replayed; the per-step scalars come from a device table.
+
+        Noise: the reference draws `torch.randn(size)` on the CPU generator once per step and
+        copies it to the device (:464-465); the S draws are made up front, in the same order,
+        from the same generator (nothing else consumes it inside the loop), so a seeded run sees
+        the same values.  given_noise (extension, [S, *size]) replaces them."""
+        if grid_emb is not None or enable_autocast:
+            raise NotImplementedError("lion_b200: grid_emb / autocast are not used by LION's sampling path")
+        if getattr(model, 'mixed_prediction', False):
+            raise NotImplementedError("lion_b200: mixed prediction is disabled in every shipped prior config")
         model.eval()
         size = [num_samples] + list(shape)
         x_noisy = torch.randn(size=size, device='cuda') if x_noisy is None else x_noisy.cuda()
@@ -179,22 +208,44 @@ class DiffusionDiscretized(object):
         else:
             raise NotImplementedError(skip_type)
         steps = sorted(list(list_tau), reverse=True)
-        Alpha_bar = self._alpha_bars.to(dev)
-        output_list = []
-        for i, t in enumerate(steps):
-            timestep = torch.ones(num_samples, dtype=torch.float32, device=dev) * (t + 1)
-            if i == len(steps) - 1:
-                assert t == 0
-                alpha_next = torch.tensor(1.0, device=dev)
-                sigma = torch.tensor(0.0, device=dev)
-            else:
-                alpha_next = Alpha_bar[steps[i + 1]]
-                sigma = kappa * torch.sqrt((1 - alpha_next) / (1 - Alpha_bar[t]) * (1 - Alpha_bar[t] / alpha_next))
-            x = x_noisy * torch.sqrt(alpha_next / Alpha_bar[t])
-            c = torch.sqrt(1 - alpha_next - sigma ** 2) - torch.sqrt(1 - Alpha_bar[t]) * torch.sqrt(alpha_next / Alpha_bar[t])
-            eps = model(x=x_noisy, t=timestep, condition_input=condition_input, clip_feat=clip_feat)
-            x += c * eps + sigma * torch.randn(size, device=dev)
-            x_noisy = x
-            output_list.append(x_noisy)
+        tables = self._ddim_tables(steps, kappa, dev)
+        if given_noise is None:
+            noise = torch.stack([torch.randn(size) for _ in range(S)]).to(dev)
+        else:
+            noise = torch.as_tensor(given_noise, dtype=torch.float32).reshape([S] + size).to(dev)
+        noise = noise.contiguous()
+        x = x_noisy.to(torch.float32).clone().contiguous()
+        n = x.numel()
+        hist = torch.empty([S] + size, device=dev, dtype=torch.float32)
+        step = torch.zeros(1, device=dev, dtype=torch.int32)
+        tfl = torch.zeros(num_samples, device=dev, dtype=torch.float32)
+        lib = L.lib()
+
+        def body():
+            pred = model(x=x, t=tfl, condition_input=condition_input, clip_feat=clip_feat)
+            L.check(lib.lion_ddim_update(L.ptr(x), L.ptr(pred.contiguous()), L.ptr(noise), L.ptr(x), L.ptr(tables),
+                                         L.ptr(step), n, L.ptr(hist), L.stream()), "ddim_update")
+            L.check(lib.lion_ddim_next_step(L.ptr(step), L.ptr(tfl), L.ptr(tables), num_samples, S, L.stream()), "ddim_next_step")
+
+        launches = 0
+        with torch.cuda.device(dev):
+            L.check(lib.lion_ddim_set_step(L.ptr(step), L.ptr(tfl), L.ptr(tables), num_samples, S, 0, L.stream()), "ddim_set_step")
+            body()                      # eager first step: builds/packs the model, sizes the arena
+            per_step = L.last_launches(dev) + 2
+            launches += per_step
+            graph = None
+            if self.use_cuda_graph and getattr(model, 'lion_graph_safe', True) and S > 2:
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize(dev)
+                with torch.cuda.graph(graph):
+                    body()
+            for _ in range(1, S):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    body()
+                launches += per_step
+        self.last_gpu_launches = launches
+        self.total_gpu_launches += launches
         model.train()
-        return x_noisy, output_list
+        return hist[S - 1], [hist[k] for k in range(S)]

@@ -5,11 +5,15 @@ TEST INFRASTRUCTURE ONLY -- see oracle/point_ops.py for the import rules.
   make_schedule        utils/diffusion.py:52-53 (linear) + utils/diffusion_pvd.py:118-142
   ddpm_step            utils/diffusion_pvd.py:475-486 (get_q_posterior_mean) + :283-296
   run_denoising        utils/diffusion_pvd.py:223-303 (run_denoising_diffusion)
+  ddim_taus / ddim_coeffs / ddim_step / run_ddim
+                       utils/diffusion_pvd.py:389-473 (run_ddim; the DDIM route of
+                       generate_samples_vada_2prior, trainers/train_2prior.py:87-93)
   sample_2prior        trainers/train_2prior.py:49-127 (generate_samples_vada_2prior,
                        ode_sample=0, ddim_step=0) + models/vae_adain.py:301-333 (sample)
 
-Parity status: pinned by tests/golden/schedule.npz and ddpm10.npz (made by running the
-reference's own DiffusionDiscretized on CPU, tests/golden/make_golden.py).
+Parity status: pinned by tests/golden/schedule.npz, ddpm10.npz and ddim5.npz (made by running
+the reference's own DiffusionDiscretized on CPU, tests/golden/make_golden.py and
+make_golden_ddim.py).
 """
 import numpy as np
 import torch
@@ -66,3 +70,58 @@ def sample_2prior(global_fn, local_fn, decoder_fn, sched, noise_g, noise_l):
     z_l, _ = run_denoising(lambda x, t: local_fn(x, t, style), sched, noise_l[0], noise_l[1])
     pts = decoder_fn(z_l.reshape(z_l.shape[0], -1), style)
     return pts, z_g, z_l
+
+
+# ------------------------------------------------------------------------------------------
+# DDIM (utils/diffusion_pvd.py:389-473)
+# ------------------------------------------------------------------------------------------
+def ddim_taus(T, S, skip_type="uniform"):
+    """Sub-sequence of loop variables, descending (:411-423).  'uniform': floor(i*(T-1)/(S-1));
+    'quad': int(linspace(0, sqrt(0.8 T), S)**2)."""
+    if skip_type == "uniform":
+        c = (T - 1.0) / (S - 1.0)
+        taus = [int(np.floor(i * c)) for i in range(S)]
+    elif skip_type == "quad":
+        taus = [int(s) for s in list(np.linspace(0, np.sqrt(T * 0.8), S) ** 2)]
+    else:
+        raise NotImplementedError(skip_type)
+    return sorted(taus, reverse=True)
+
+
+def ddim_coeffs(sched, taus, i, kappa=1.0):
+    """fp32 0-dim tensors (a, c, sigma) of step i (:437-451):
+       alpha_next = abar[tau_{i+1}] (1 at the last step), sigma = kappa*sqrt((1-an)/(1-ab)*(1-ab/an)),
+       a = sqrt(an/ab), c = sqrt(1-an-sigma^2) - sqrt(1-ab)*sqrt(an/ab);   x' = x*a + (c*eps + sigma*z)."""
+    ab = sched["alpha_bars"][taus[i]]
+    if i == len(taus) - 1:
+        assert taus[i] == 0
+        an, sigma = torch.tensor(1.0), torch.tensor(0.0)
+    else:
+        an = sched["alpha_bars"][taus[i + 1]]
+        sigma = kappa * torch.sqrt((1 - an) / (1 - ab) * (1 - ab / an))
+    a = torch.sqrt(an / ab)
+    c = torch.sqrt(1 - an - sigma ** 2) - torch.sqrt(1 - ab) * torch.sqrt(an / ab)
+    return a, c, sigma
+
+
+def ddim_step(x, eps, noise, a, c, sigma):
+    """x = x_noisy*a;  x += c*eps + sigma*z   (:450,:464-465)."""
+    x = x * a
+    x = x + (c * eps + sigma * noise)
+    return x
+
+
+def run_ddim(model_fn, sched, x_T, noises, S, skip_type="uniform", kappa=1.0):
+    """noises[i] is the i-th draw (the reference draws torch.randn(size) on the CPU generator
+    once per step, including the last one where sigma = 0, :464-465)."""
+    T = sched["betas"].shape[0]
+    taus = ddim_taus(T, S, skip_type)
+    x = x_T
+    traj = []
+    for i, t in enumerate(taus):
+        tt = torch.ones(x.shape[0]) * (t + 1)
+        eps = model_fn(x, tt)
+        a, c, sigma = ddim_coeffs(sched, taus, i, kappa)
+        x = ddim_step(x, eps, noises[i], a, c, sigma)
+        traj.append(x)
+    return x, traj

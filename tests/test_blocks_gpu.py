@@ -100,3 +100,41 @@ def test_se3d_and_swish_standalone():
     ref = x * torch.sigmoid(torch.relu(se @ sd["fc.0.weight"].T) @ sd["fc.2.weight"].T)[:, :, None, None, None]
     assert_close(m(x.cuda()), ref, 1e-5, "SE3d")
     assert_close(Swish()(x.cuda()), x * torch.sigmoid(x), 1e-5, "Swish")
+
+
+def _tf32_rna(x):
+    """cvt.rna.tf32.f32 on the CPU: round the magnitude to 10 mantissa bits, ties away from zero."""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1fff).view(torch.float32)
+
+
+@pytest.mark.parametrize("cin,cout,r,B", [
+    (4, 32, 32, 1),      # sa0 first conv (K padded to one chunk)
+    (32, 32, 32, 2),     # N = 32 tiles
+    (64, 64, 32, 1),     # the dominant shape of the step (fp3)
+    (128, 64, 16, 2),    # N = 64, four 32-channel chunks
+    (192, 128, 8, 3),    # N = 128, 16-channel chunks, ragged row-tile groups
+    (128, 128, 16, 1),
+    (64, 256, 8, 2),     # two N tiles
+    (20, 40, 5, 2),      # cout not a multiple of 32: SIMT kernel
+    (3, 8, 4, 1),
+])
+def test_conv3d_standalone(cin, cout, r, B):
+    """a7: the 3x3x3 convolution alone (tcgen05 kernel, lion_conv3d_gn_fwd) against torch's fp32
+    conv3d on the CPU -- TF32 tolerance -- and against the same convolution evaluated on
+    TF32-rounded operands, which isolates the kernel's indexing / accumulation (fp32 order only)."""
+    from lion_b200.models.pvcnn2_ada import Conv3d
+    m = Conv3d(cin, cout, 3, stride=1, padding=1)
+    w, b = gen(61, cout, cin, 3, 3, 3, scale=(27 * cin) ** -0.5), gen(62, cout, scale=0.1)
+    m.load_state_dict({"weight": w, "bias": b})
+    m = m.cuda().eval()
+    x = gen(63, B, cin, r, r, r)
+    out, ssum, ssq = m(x.cuda(), return_gn_stats=True)
+    ref = torch.nn.functional.conv3d(x, w, b, padding=1)
+    assert_close(out, ref, TOL, "conv3d vs fp32")
+    ref_t = torch.nn.functional.conv3d(_tf32_rna(x), _tf32_rna(w), b, padding=1)
+    assert_close(out, ref_t, 2e-5, "conv3d vs TF32-operand emulation")
+    o64 = out.double().cpu().view(B, cout, -1)
+    assert_close(ssum, o64.sum(-1), 1e-5, "fused GroupNorm sum")
+    assert_close(ssq, (o64 * o64).sum(-1), 1e-5, "fused GroupNorm sum of squares")
+    assert torch.equal(m(x.cuda()), out), "conv3d is not bit-reproducible"

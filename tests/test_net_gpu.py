@@ -188,3 +188,84 @@ def test_generate_samples_entry_point_shapes_and_graph_determinism():
         outs.append(img)
     # same seed, same draw order: the graph-replayed loop reproduces the eager loop
     assert_close(outs[0], outs[1], 1e-3, "graph vs eager sampling")
+
+
+# ---- the DDIM route (utils/diffusion_pvd.py:389-473) -----------------------------
+def test_ddim_update_kernel_matches_reference_arithmetic():
+    from lion_b200.utils.diffusion_pvd import DiffusionDiscretized
+    from lion_b200 import _lib as L
+    d = DiffusionDiscretized(None, None, _cfg())
+    sched = OD.make_schedule(1000, 1e-4, 0.02)
+    for skip, kappa, S in (("uniform", 1.0, 25), ("quad", 0.3, 10), ("uniform", 0.0, 4)):
+        taus = OD.ddim_taus(1000, S, skip)
+        tab = d._ddim_tables(taus, kappa, torch.device("cuda"))
+        x, e = gen(51, 2, 8192), gen(52, 2, 8192)
+        zn = gen(53, S, 2, 8192)
+        xc, ec, zc = x.cuda(), e.cuda(), zn.cuda().contiguous()
+        for i in (0, 1, S // 2, S - 1):
+            step = torch.tensor([i], dtype=torch.int32, device="cuda")
+            out = torch.empty(2, 8192, device="cuda")
+            L.check(L.lib().lion_ddim_update(L.ptr(xc), L.ptr(ec), L.ptr(zc), L.ptr(out), L.ptr(tab), L.ptr(step),
+                                             x.numel(), None, L.stream()))
+            a, c, sigma = OD.ddim_coeffs(sched, taus, i, kappa)
+            ref = OD.ddim_step(x, e, zn[i], a, c, sigma)
+            assert float(tab[i, 3]) == taus[i] + 1
+            assert torch.equal(out.cpu(), ref), "DDIM update is not bit-identical to the reference arithmetic (%s, i=%d)" % (skip, i)
+
+
+def test_ddim5_golden():
+    """run_ddim, 5 of 10 steps, against the reference's own CPU run (tests/golden/ddim5.npz): the
+    global prior end to end (uniform kappa=1 and quad kappa=0.5), the local prior free-running
+    (loose, see the DDPM test) and teacher-forced per step (strict), graph-replayed and eager."""
+    from lion_b200.utils.diffusion_pvd import DiffusionDiscretized
+    from lion_b200 import _lib as L
+    z = np.load(os.path.join(G, "ddim5.npz"))
+    cfg = _cfg(num_steps=10)
+    diff = DiffusionDiscretized(cfg.sde, None, cfg)
+    gp, lp = _global(), _prior()
+    for use_graph in (False, True):
+        diff.use_cuda_graph = use_graph
+        out, lst = diff.run_ddim(gp, 2, [128, 1, 1], ddim_step=5, x_noisy=torch.from_numpy(z["g_xT"]), given_noise=z["g_z"])
+        assert_close(out, torch.from_numpy(z["g_out"]), 5e-3, "ddim global (graph=%s)" % use_graph)
+        assert_close(torch.stack(lst), torch.from_numpy(z["g_traj"]), 5e-3, "ddim global trajectory")
+        out, _ = diff.run_ddim(gp, 2, [128, 1, 1], ddim_step=5, skip_type='quad', kappa=0.5,
+                               x_noisy=torch.from_numpy(z["q_xT"]), given_noise=z["q_z"])
+        assert_close(out, torch.from_numpy(z["q_out"]), 5e-3, "ddim global quad (graph=%s)" % use_graph)
+        cond = torch.from_numpy(z["l_cond"]).cuda()
+        out, lst = diff.run_ddim(lp, 1, [8192, 1, 1], condition_input=cond, ddim_step=5,
+                                 x_noisy=torch.from_numpy(z["l_xT"]), given_noise=z["l_z"])
+        assert len(lst) == 5 and out.shape == (1, 8192, 1, 1)
+        assert rms_err(out, z["l_out"]) < 5e-2
+    # the reference's seeded CPU draws are reproduced when no noise is passed in
+    torch.manual_seed(201)
+    out, _ = diff.run_ddim(gp, 2, [128, 1, 1], ddim_step=5, x_noisy=torch.from_numpy(z["g_xT"]))
+    torch.manual_seed(201)
+    torch.randn(2, 128, 1, 1)           # the reference's x_T draw precedes the per-step draws
+    out2, _ = diff.run_ddim(gp, 2, [128, 1, 1], ddim_step=5, x_noisy=torch.from_numpy(z["g_xT"]))
+    assert_close(out2, torch.from_numpy(z["g_out"]), 5e-3, "ddim global with CPU-generator noise")
+    assert not torch.equal(out, out2)
+    # teacher-forced local-prior steps
+    taus = OD.ddim_taus(10, 5)
+    tab = diff._ddim_tables(taus, 1.0, torch.device("cuda"))
+    traj = torch.from_numpy(z["l_traj"])                          # [5, 8192]
+    noise = torch.from_numpy(z["l_z"]).reshape(5, 8192).cuda().contiguous()
+    for i, t in enumerate(taus):
+        x_in = (torch.from_numpy(z["l_xT"]).view(1, 8192) if i == 0 else traj[i - 1:i]).cuda().contiguous()
+        eps = lp(x=x_in.view(1, 8192, 1, 1), t=torch.tensor([t + 1.0]).cuda(), condition_input=cond).view(1, 8192).contiguous()
+        step = torch.tensor([i], dtype=torch.int32, device="cuda")
+        o = torch.empty_like(x_in)
+        L.check(L.lib().lion_ddim_update(L.ptr(x_in), L.ptr(eps), L.ptr(noise), L.ptr(o), L.ptr(tab), L.ptr(step),
+                                         x_in.numel(), None, L.stream()))
+        assert_close(o, traj[i:i + 1], TOL, "teacher-forced DDIM step %d (t=%d)" % (i, t))
+
+
+def test_generate_samples_ddim_route():
+    from lion_b200.utils.diffusion_pvd import DiffusionDiscretized
+    from lion_b200.trainers.train_2prior import generate_samples_vada_2prior
+    cfg = _cfg(num_steps=50)
+    diff = DiffusionDiscretized(cfg.sde, None, cfg)
+    dae = torch.nn.ModuleList([_global(), _prior()])
+    vae = _vae()
+    torch.manual_seed(9)
+    img, nfe, _, _, out = generate_samples_vada_2prior(vae.latent_shape(), dae, diff, vae, 2, False, ddim_step=5)
+    assert img.shape == (2, 2048, 3) and torch.isfinite(img).all()

@@ -88,3 +88,29 @@ def test_ddpm10_config0_matches_reference():
     _close(z_g, z["out_g"], 5e-5, "global latent")
     _close(z_l, z["out_l"], 2e-4, "local latent")
     _close(pts, z["image"], 2e-4, "decoded points")
+
+
+def test_ddim5_matches_reference():
+    """run_ddim (5 of 10 steps; uniform kappa=1 on both priors, quad kappa=0.5 on the
+    global prior; noise = the reference's CPU-generator draws, stored in the golden)."""
+    z = np.load(os.path.join(G, "ddim5.npz"))
+    sched = OD.make_schedule(10, 1e-4, 0.02)
+    assert np.array_equal(sched["alpha_bars"].numpy(), z["alpha_bars"])
+    assert OD.ddim_taus(10, 5, "uniform") == [9, 6, 4, 2, 0]
+    assert OD.ddim_taus(10, 5, "quad") == [8, 4, 2, 0, 0]
+    sd_g = synth_state_dict(KEYS["global"], 14)
+    sd_l = synth_state_dict(KEYS["prior"], 11)
+    spec = ON.prior_spec()
+    with torch.no_grad():
+        g_out, g_traj = OD.run_ddim(lambda x, t: ON.global_prior_forward(sd_g, x, t), sched,
+                                    torch.from_numpy(z["g_xT"]), list(torch.from_numpy(z["g_z"])), 5)
+        q_out, _ = OD.run_ddim(lambda x, t: ON.global_prior_forward(sd_g, x, t), sched,
+                               torch.from_numpy(z["q_xT"]), list(torch.from_numpy(z["q_z"])), 5, "quad", 0.5)
+        style = torch.from_numpy(z["l_cond"]).reshape(1, -1)
+        l_out, l_traj = OD.run_ddim(lambda x, t: ON.prior_forward(sd_l, spec, x, t, style), sched,
+                                    torch.from_numpy(z["l_xT"]), list(torch.from_numpy(z["l_z"])), 5)
+    _close(g_out, z["g_out"], 5e-5, "ddim global")
+    _close(torch.stack(g_traj), z["g_traj"], 5e-5, "ddim global trajectory")
+    _close(q_out, z["q_out"], 5e-5, "ddim global quad")
+    _close(l_out, z["l_out"], 2e-4, "ddim local")
+    _close(torch.stack(l_traj)[:, 0, :, 0, 0], z["l_traj"], 2e-4, "ddim local trajectory")

@@ -18,6 +18,9 @@ SHAPES = [  # (ntaps, cin, cout, r_or_rows, launches per step, label)
     (1, 64, 128, 8192, 1, "SA1 mlp1"), (1, 196, 128, 2048, 1, "fp3 mlp0"), (1, 128, 128, 2048, 1, "fp3 mlp1"),
     (1, 64, 384, 1024, 1, "attn qkv"),
 ]
+ONLY = os.environ.get("ONLY")  # e.g. ONLY="fp3 r=32" to time one shape (ncu captures)
+if ONLY:
+    SHAPES = [s for s in SHAPES if s[5] == ONLY]
 torch.cuda.init()
 tot = 0.0
 for nt, ci, co, r, n, label in SHAPES:
