@@ -149,6 +149,17 @@ int lion_ddim_update(const float* x, const float* eps, const float* noise, float
 int lion_ddim_set_step(int* step_ptr, float* t_out, const float* tables, int B, int S, int index, void* stream);
 int lion_ddim_next_step(int* step_ptr, float* t_out, const float* tables, int B, int S, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * One step of the diffusers-style DDPM scheduler used by LION.sample (models/lion.py:24-26,:55,:70;
+ * the scheduler itself is the un-vendored dependency diffusers==0.11.1 -- its published
+ * DDPMScheduler.step is restated, PARITY UNPINNED):
+ *   x0 = (x - r0*eps)/r1;  prev = r2*x0 + r3*x;  x_out = prev + r4*noise (t > 0), prev (t = 0)
+ * row t of `tables` ([T][8] fp32) = {sqrt(1-abar_t), sqrt(abar_t), c0, c1, sqrt(var_t), 0,0,0};
+ * t = *step_ptr on the device (use lion_ddpm_set_step / lion_ddpm_next_step).  x_out may alias x.
+ * ------------------------------------------------------------------------------------- */
+int lion_scheduler_step(const float* x, const float* eps, const float* noise, float* x_out, const float* tables,
+                        const int* step_ptr, size_t n, void* stream);
+
 /* measurement hook (bench.py roofline leg): average device time of `iters` launches of the
  * convolution kernel alone (CUDA events on `stream`), on synthetic data: ntaps = 27 -> 3x3x3
  * over [B, cin, r^3] (r_or_rows = r), ntaps = 1 -> 1x1 over r_or_rows rows.  flops_out = the

@@ -5,7 +5,8 @@ host-side mirror of the reference's Python interface for that path:
     lion_b200.third_party.pvcnn.functional      the 7 point/voxel operators
     lion_b200.models.pvcnn2_ada / .latent_points_ada / .latent_points_ada_localprior
     lion_b200.models.score_sde.resnet / .vae_adain
-    lion_b200.utils.diffusion_pvd               DiffusionDiscretized
+    lion_b200.utils.diffusion_pvd               DiffusionDiscretized (DDPM + DDIM loops)
+    lion_b200.models.lion                       LION (demo wrapper; diffusers-style scheduler restated)
     lion_b200.trainers.train_2prior             generate_samples_vada_2prior
 
 `lion_b200.install()` registers these under the reference's own import paths (`models.*`,
@@ -26,6 +27,7 @@ _ALIASES = {
     "models.latent_points_ada_localprior": "lion_b200.models.latent_points_ada_localprior",
     "models.score_sde.resnet": "lion_b200.models.score_sde.resnet",
     "models.vae_adain": "lion_b200.models.vae_adain",
+    "models.lion": "lion_b200.models.lion",
     "utils.diffusion_pvd": "lion_b200.utils.diffusion_pvd",
     "trainers.train_2prior": "lion_b200.trainers.train_2prior",
 }

@@ -73,6 +73,26 @@ __global__ void k_ddim_set_step(int* step, float* t_out, const float4* __restric
   for (int b = threadIdx.x; b < B; b += blockDim.x) t_out[b] = t;
 }
 
+// diffusers-style DDPMScheduler.step (the models/lion.py:37-80 route; algorithm of diffusers 0.11.1,
+// scheduling_ddpm.py, epsilon prediction, clip_sample=False):
+//   x0   = (x - sqrt(1-abar_t) * eps) / sqrt(abar_t)
+//   prev = c0 * x0 + c1 * x,   c0 = sqrt(abar_{t-1}) * beta_t / (1-abar_t),  c1 = sqrt(alpha_t) * (1-abar_{t-1}) / (1-abar_t)
+//   x'   = prev + sqrt(var_t) * z   for t > 0,   x' = prev   at t = 0
+// table row t (8 floats): { sqrt(1-abar_t), sqrt(abar_t), c0, c1, sqrt(var_t), 0, 0, 0 }.
+__global__ void k_sched_step(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                             float* __restrict__ xo, const float4* __restrict__ tables, const int* __restrict__ step, size_t n) {
+  pdl_prologue();
+  int t = *step;
+  float4 c = tables[2 * t];
+  float sigma = tables[2 * t + 1].x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xv = x[i];
+  float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(c.x, eps[i])), c.y);
+  float prev = __fadd_rn(__fmul_rn(c.z, x0), __fmul_rn(c.w, xv));
+  xo[i] = t > 0 ? __fadd_rn(prev, __fmul_rn(sigma, noise[i])) : prev;
+}
+
 }  // namespace lion
 
 using namespace lion;
@@ -121,4 +141,13 @@ extern "C" int lion_ddim_next_step(int* step_ptr, float* t_out, const float* tab
   c.stream = (cudaStream_t)stream;
   LION_LAUNCH(&c, k_ddim_set_step, 1, 64, 0, step_ptr, t_out, (const float4*)tables, B, S, 0, 1);
   return check_launch(&c, "lion_ddim_next_step");
+}
+
+extern "C" int lion_scheduler_step(const float* x, const float* eps, const float* noise, float* x_out, const float* tables,
+                                   const int* step_ptr, size_t n, void* stream) {
+  LION_REQUIRE(x && eps && x_out && tables && step_ptr && n > 0, "lion_scheduler_step: bad arguments");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_sched_step, (unsigned)cdivz(n, 256), 256, 0, x, eps, noise ? noise : x, x_out, (const float4*)tables, step_ptr, n);
+  return check_launch(&c, "lion_scheduler_step");
 }
