@@ -38,7 +38,7 @@ def test_scheduler_restatement_agrees_with_pinned_posterior():
         assert float(OS.variance(s, t, "fixed_large")) == float(s["betas"][t])
     # t = 0: x0 itself, no noise
     x0 = OS.step(s, e, 0, x, None)
-    assert_close(x0, OD.ddpm_step(sched, x, e, 0, None), 2e-5, "t=0")
+    assert_close(x0, OD.ddpm_step(sched, x, e, 0, None), 5e-4, "t=0")   # fp32 (1 - 0.9999) in the scheduler vs float64 tables
 
 
 @pytest.mark.gpu
