@@ -19,9 +19,12 @@
 //   * B operand: weights pre-packed [n-tile][chunk][x-plane][tap][C/4][co][4] so one bulk copy
 //     brings the 9 taps of a (channel chunk, x-plane); a CTA reuses it for up to 8 row tiles
 //     (8 x 64 fp32 accumulator columns = all 512 TMEM columns).
-//   * warp 0: bulk-copy producer, warp 1: single-thread MMA issuer, warps 2-5: epilogue
-//     (tcgen05.ld -> +bias -> halo mask -> coalesced float4 stores, GroupNorm sum / sum-of-squares
-//     reduced in registers/shared memory, one fp64 atomic per channel per CTA).
+//   * persistent CTAs (one per SM, 352 threads): warp 0 = bulk-copy producer, warps 1-2 = UMMA
+//     issuers (even / odd row tiles), warps 3-10 = epilogue (tcgen05.ld -> +bias -> halo mask ->
+//     coalesced float4 stores, GroupNorm sum / sum-of-squares reduced in registers / shared memory,
+//     one fp64 atomic per channel per work item).
+//   * 1x1 convolutions may stage several consecutive row tiles per pipeline stage (Params::MT):
+//     their stages carry only KG/2 MMAs per tile, so the barrier round trip per stage dominates.
 #include "common.cuh"
 #include "model.cuh"
 #include <cstdlib>
@@ -123,6 +126,7 @@ struct Params {
   int KG, nchunk;        // channel groups per chunk, chunks
   int NT;                // output channels per CTA (UMMA N)
   int G;                 // row tiles (accumulators) per work item
+  int MT;                // row tiles per A stage (1 for 3x3x3; 1x1: consecutive tiles share one bulk copy)
   int B;                 // shapes
   int a_stage_bytes, b_stage_bytes, stage_rows;
   int a_stages;          // depth of the A ring
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           }
           if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
           long long row0 = row_item + P.tg_off[tg];
-          for (int j = 0; j < ntile; ++j, row0 += 128) {
+          for (int j = 0; j < ntile; j += P.MT, row0 += 128 * P.MT) {
             mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
             bool empty = false;
             if (may_skip) {
@@ -255,15 +259,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
               for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(occ_b + k);
               empty = (any == 0);
             }
+            // multi-tile stages (1x1 only): copy just the rows this item still has, and never past
+            // the end of the (b, group) slab
+            uint32_t nbytes = bytes;
+            if (P.MT > 1) {
+              long long nr = (long long)min(P.MT, ntile - j) * 128;
+              if (nr > P.rows - row0) nr = P.rows - row0;
+              nbytes = (uint32_t)nr * 16u;
+            }
             const uint32_t full = bar_full_a + 8 * sa;
             if (lane == 0) {
               s_skip[sa] = empty ? 1u : 0u;
               if (empty || (P.debug & 1)) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
-              else mbar_expect_tx(full, bytes * kg_real);
+              else mbar_expect_tx(full, nbytes * kg_real);
             }
             __syncwarp();
             if (!empty && !(P.debug & 1) && lane < kg_real)
-              bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, bytes, full);
+              bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, nbytes, full);
             if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
           }
         }
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           const uint32_t b_base16 = smem_u32(sB + (size_t)sb * P.b_stage_bytes) >> 4;
           const bool first = (cc | tg) == 0;
           const bool last = (cc == P.nchunk - 1) && (tg == P.ntg - 1);
-          for (int j = 0; j < ntile; ++j) {
+          for (int j = 0; j < ntile; j += P.MT) {
             const uint32_t my_sa = sa, my_pa = pa;
             if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
             // BOTH issuers wait on every stage and both release it (empty count 2).  A parity wait is
@@ -306,35 +318,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             // of order, so an issuer that skipped the other's stages could see a slot's barrier one
             // phase behind and mistake "not yet loaded" for "loaded" (seen with odd ring depths).
             mbar_wait(bar_full_a + 8 * my_sa, my_pa);
-            if ((j & 1) != me) {                                       // the other issuer's tile
-              mbar_arrive_w(bar_empty_a + 8 * my_sa);
-              continue;
-            }
-            if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);     // accumulator j drained (previous item)
-            if (s_skip[my_sa]) {
-              // all-zero input slab: nothing to accumulate, hand the stage straight back
-              mbar_arrive_w(bar_empty_a + 8 * my_sa);
-              continue;
-            }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_base16 = a_ring16 + my_sa * a_stage16;
-            const uint32_t d = tmem_base + (uint32_t)(j * P.NT);
-            const bool fresh = ((started >> j) & 1u) == 0;
-            started |= 1u << j;
+            bool issued = false;
+            for (int jj = 0; jj < P.MT; ++jj) {
+              const int jt = j + jj;
+              if (jt >= ntile) break;
+              if ((jt & 1) != me) continue;                              // the other issuer's tile
+              if (first) mbar_wait(bar_tfree + 8 * jt, (it & 1) ^ 1);    // accumulator jt drained (previous item)
+              if (s_skip[my_sa]) continue;                               // all-zero input slab: nothing to accumulate
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t a_base16 = a_ring16 + my_sa * a_stage16 + (uint32_t)jj * 128u;
+              const uint32_t d = tmem_base + (uint32_t)(jt * P.NT);
+              const bool fresh = ((started >> jt) & 1u) == 0;
+              started |= 1u << jt;
 #pragma unroll
-            for (int t = 0; t < TPG; ++t) {
-              const uint32_t a_t = a_base16 + (uint32_t)P.tap_off[t];
-              const uint32_t b_t = b_base16 + t * b_tap16;
+              for (int t = 0; t < TPG; ++t) {
+                const uint32_t a_t = a_base16 + (uint32_t)P.tap_off[t];
+                const uint32_t b_t = b_base16 + t * b_tap16;
 #pragma unroll
-              for (int k2 = 0; k2 < KG; k2 += 2) {
-                uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
-                uint32_t blo = b_lo_c | ((b_t + k2 * b_pitch16) & 0x3fff);
-                uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
-                if (!(P.debug & 2)) umma_tf32_w(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
+                for (int k2 = 0; k2 < KG; k2 += 2) {
+                  uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
+                  uint32_t blo = b_lo_c | ((b_t + k2 * b_pitch16) & 0x3fff);
+                  uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
+                  if (!(P.debug & 2)) umma_tf32_w(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
+                }
               }
+              if (last) umma_commit_w(bar_accf + 8 * jt);   // accumulator jt complete -> epilogue may drain it
+              issued = true;
             }
-            umma_commit_w(bar_empty_a + 8 * my_sa);       // frees the A stage when these MMAs retire
-            if (last) umma_commit_w(bar_accf + 8 * j);    // accumulator j complete -> epilogue may drain it
+            // hand the stage back: when this warp's MMAs retire, or at once if it issued none
+            if (issued) umma_commit_w(bar_empty_a + 8 * my_sa);
+            else mbar_arrive_w(bar_empty_a + 8 * my_sa);
           }
           umma_commit_w(bar_empty_b + 8 * sb);            // (count 2: both issuers)
           if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
@@ -529,8 +542,9 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   } else {
     P.tg_off[0] = 0; P.tap_off[0] = 0; P.halo = 0;
   }
+  P.MT = 1;
   P.stage_rows = 128 + 2 * P.halo;
-  P.a_stage_bytes = KG * P.stage_rows * 16;
+  P.a_stage_bytes = KG * P.stage_rows * 16;     // per row tile; multi-tile stages are sized below, once G is known
   P.b_stage_bytes = tpg * KG * NT * 16;
   int ntile = cdiv(geo.p_end - geo.p_begin, 128);
   int n_tiles_n = w.cout_pad / NT;
@@ -553,6 +567,18 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   }
   P.G = G;
   P.B = B;
+  if (w.ntaps == 1) {
+    // 1x1: a stage carries only KG/2 MMAs per row tile, so the per-stage barrier round trips of
+    // producer and issuers dominate; stage MT consecutive row tiles with one bulk copy per group
+    static int mt_env = -1;
+    if (mt_env < 0) { const char* e = getenv("LION_TC_MT"); mt_env = e ? atoi(e) : 1; }
+    int mt = mt_env < 1 ? 1 : mt_env;
+    while (mt > 1 && (mt > G || (mt & (mt - 1)))) --mt;
+    while (mt > 1 && 3LL * KG * 128 * mt * 16 + (long long)tc::B_STAGES * P.b_stage_bytes + 8192 > 227LL * 1024) mt >>= 1;   // ring >= 3
+    P.MT = mt;
+    P.stage_rows = 128 * mt;
+    P.a_stage_bytes = KG * P.stage_rows * 16;
+  }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LION_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.debug = dbg; }

@@ -21,6 +21,8 @@ SHAPES = [  # (ntaps, cin, cout, r_or_rows, launches per step, label)
 ONLY = os.environ.get("ONLY")  # e.g. ONLY="fp3 r=32" to time one shape (ncu captures)
 if ONLY:
     SHAPES = [s for s in SHAPES if s[5] == ONLY]
+if os.environ.get("TAPS"):           # TAPS=1 -> only the 1x1 shapes, TAPS=27 -> only the 3x3x3 ones
+    SHAPES = [s for s in SHAPES if s[0] == int(os.environ["TAPS"])]
 torch.cuda.init()
 tot = 0.0
 for nt, ci, co, r, n, label in SHAPES:
