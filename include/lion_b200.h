@@ -160,6 +160,26 @@ int lion_ddim_next_step(int* step_ptr, float* t_out, const float* tables, int B,
 int lion_scheduler_step(const float* x, const float* eps, const float* noise, float* x_out, const float* tables,
                         const int* step_ptr, size_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Generation metrics that follow sampling: Chamfer nearest neighbours.
+ *
+ * lion_chamfer_forward replaces chamfer_3D.forward (third_party/ChamferDistancePytorch/chamfer3D/
+ * chamfer_cuda.cpp:17-19 -> chamfer3D.cu:12-143): xyz1 [B,N,3], xyz2 [B,M,3] point-major ->
+ * dist1 [B,N] (squared distance to the nearest point of xyz2), idx1 [B,N] (its index; lowest index on
+ * exact ties), dist2 [B,M], idx2 [B,M] the other way round.  idx1 / idx2 may be NULL.  Distances are
+ * bit-identical to the reference kernel (same FMA contraction), indices exact.
+ *
+ * lion_chamfer_pairwise computes the whole CD matrix of utils/evaluation_metrics_fast.py:272-340
+ * (_pairwise_EMD_CD_, metric 'CD'): samples [Ns,N,3], refs [Nr,M,3] -> out [Ns,Nr],
+ * out[i][j] = mean_n dist(samples_i -> refs_j) + mean_m dist(refs_j -> samples_i), one CTA per pair,
+ * deterministic.  N, M <= 2048.  (The means are summed in a fixed order that differs from torch's
+ * reduction order: equal to the reference within fp32 rounding of a 2048-term sum.)
+ * ------------------------------------------------------------------------------------- */
+int lion_chamfer_forward(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2,
+                         int B, int N, int M, void* stream);
+int lion_chamfer_pairwise(const float* samples, const float* refs, float* out, int n_sample, int n_ref, int N, int M,
+                          void* stream);
+
 /* measurement hook (bench.py roofline leg): average device time of `iters` launches of the
  * convolution kernel alone (CUDA events on `stream`), on synthetic data: ntaps = 27 -> 3x3x3
  * over [B, cin, r^3] (r_or_rows = r), ntaps = 1 -> 1x1 over r_or_rows rows.  flops_out = the

@@ -7,6 +7,8 @@ host-side mirror of the reference's Python interface for that path:
     lion_b200.models.score_sde.resnet / .vae_adain
     lion_b200.utils.diffusion_pvd               DiffusionDiscretized (DDPM + DDIM loops)
     lion_b200.models.lion                       LION (demo wrapper; diffusers-style scheduler restated)
+    lion_b200.third_party.ChamferDistancePytorch.chamfer3D.dist_chamfer_3D   Chamfer NN (metrics)
+    lion_b200.utils.evaluation_metrics_fast     pairwise CD matrix (not aliased: the reference module holds more)
     lion_b200.trainers.train_2prior             generate_samples_vada_2prior
 
 `lion_b200.install()` registers these under the reference's own import paths (`models.*`,
@@ -20,6 +22,8 @@ __version__ = "0.1.0"
 
 _ALIASES = {
     "third_party.pvcnn.functional": "lion_b200.third_party.pvcnn.functional",
+    "third_party.ChamferDistancePytorch.chamfer3D.dist_chamfer_3D":
+        "lion_b200.third_party.ChamferDistancePytorch.chamfer3D.dist_chamfer_3D",
     "models.adagn": "lion_b200.models.adagn",
     "models.dense": "lion_b200.models.dense",
     "models.pvcnn2_ada": "lion_b200.models.pvcnn2_ada",

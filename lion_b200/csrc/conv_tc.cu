@@ -113,6 +113,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: issue the load, then make the registers depend on the wait (the "+r" operands keep
+// the compiler from scheduling consumers above tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
 struct Params {
   const float4* in; const float* w; const float* bias; float4* out; double* ssum; double* ssq;
   int Gin, Gout_store, cout_pad;
@@ -369,6 +384,65 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       if (et < P.NT) s_bias[et] = P.bias ? P.bias[n0 + et] : 0.0f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // per 16-column chunk of this warp's half
+      if (CH <= 32) {
+        // N <= 64: per-lane (= per-row) running sums over the item's tiles, ONE cross-lane reduction
+        // per item instead of one per tile; both 16-column loads of a tile are in flight together.
+        // (1x1 convolutions have almost no MMA work per tile, so this loop is their critical path.)
+        float acc_s[2][16], acc_q[2][16];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { acc_s[cc][i] = 0.0f; acc_q[cc][i] = 0.0f; }
+        for (int j = 0; j < ntile; ++j) {
+          int p = P.p_begin + (tile0 + j) * 128 + q * 32 + lane;
+          bool inrange = p < P.p_end;
+          bool valid = inrange;
+          if (P.rp > 0 && inrange) {
+            int z = p % P.rp, y = (p / P.rp) % P.rp;
+            valid = (z >= 1 && z <= P.rp - 2 && y >= 1 && y <= P.rp - 2);
+          }
+          mbar_wait(bar_accf + 8 * j, it & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          uint32_t rr[2][16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + hcol);
+          tmem_ld16_issue(taddr, rr[0]);
+          if (CH > 16) tmem_ld16_issue(taddr + 16, rr[1]);
+          tmem_ld16_wait(rr[0]);
+          if (CH > 16) tmem_ld16_wait(rr[1]);
+          // accumulator j is in registers: let the issuers start the next item's tile j
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree + 8 * j) : "memory");
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            if (cc * 16 < CH) {
+              const int col = hcol + cc * 16;
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = valid ? __uint_as_float(rr[cc][i]) + s_bias[col + i] : 0.0f;
+              if (inrange && !(P.debug & 4)) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                  int g = (n0 + col) / 4 + g4;
+                  if (g < P.Gout_store)
+                    P.out[((size_t)b * P.Gout_store + g) * P.rows + p] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) { acc_s[cc][i] += v[i]; acc_q[cc][i] = fmaf(v[i], v[i], acc_q[cc][i]); }
+            }
+          }
+        }
+        if (P.ssum && !(P.debug & 4)) {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            if (cc * 16 < CH) {
+              run_s[cc] = warp_transpose_sum16(acc_s[cc], lane);
+              run_q[cc] = warp_transpose_sum16(acc_q[cc], lane);
+            }
+          }
+        }
+      } else
       for (int j = 0; j < ntile; ++j) {
         int p = P.p_begin + (tile0 + j) * 128 + q * 32 + lane;
         bool inrange = p < P.p_end;

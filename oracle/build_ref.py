@@ -1,4 +1,4 @@
-"""Build the reference's own pvcnn CUDA extension into oracle/_ref/ (TEST INFRASTRUCTURE ONLY).
+"""Build the reference's own pvcnn and Chamfer CUDA extensions into oracle/_ref/ (TEST INFRASTRUCTURE ONLY).
 
 The reference's point-op kernels (third_party/pvcnn/functional/src/**/*.cu, bound in
 src/bindings.cpp:10-37) compile from their own 13 source files with nothing but torch's
@@ -11,7 +11,12 @@ It is used by `tests/` (-m gpu) as the ground truth for the index-producing ops 
 query, 3-NN, voxel indices) -- their results depend on nvcc's FMA contraction, which a CPU
 restatement can only approximate -- and never by the product path.
 
-Run:  python oracle/build_ref.py          (no GPU needed; ~2 min)
+The Chamfer extension (third_party/ChamferDistancePytorch/chamfer3D/{chamfer_cuda.cpp,
+chamfer3D.cu}, JIT-loaded by dist_chamfer_3D.py:12-16 with default flags) is built the same way
+into oracle/_ref/chamfer_3D.so: ground truth for lion_chamfer_forward (distances bit-exact,
+indices exact).
+
+Run:  python oracle/build_ref.py          (no GPU needed; ~3 min)
 """
 import os
 import sys
@@ -45,6 +50,36 @@ def build(verbose=False):
     return so if os.path.exists(so) else None
 
 
+CHAMFER_SRC = "/root/reference/third_party/ChamferDistancePytorch/chamfer3D"
+
+
+def build_chamfer(verbose=False):
+    so = os.path.join(OUT_DIR, "chamfer_3D.so")
+    if os.path.exists(so):
+        return so
+    if not os.path.isdir(CHAMFER_SRC):
+        return None
+    os.makedirs(OUT_DIR, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    from torch.utils.cpp_extension import load
+    load(name="chamfer_3D",
+         sources=[os.path.join(CHAMFER_SRC, "chamfer_cuda.cpp"), os.path.join(CHAMFER_SRC, "chamfer3D.cu")],
+         build_directory=OUT_DIR, verbose=verbose, is_python_module=False)       # dist_chamfer_3D.py:12-16: default flags
+    return so if os.path.exists(so) else None
+
+
+def load_chamfer():
+    import importlib.util
+    import torch  # noqa: F401
+    so = os.path.join(OUT_DIR, "chamfer_3D.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("chamfer_3D", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load_ref():
     """Import oracle/_ref/_pvcnn_backend.so (needs a GPU to *run* its functions)."""
     import importlib.util
@@ -60,3 +95,4 @@ def load_ref():
 
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
+    print(build_chamfer(verbose="-v" in sys.argv))

@@ -1,0 +1,65 @@
+"""SURVEY 8f rank 2 (Chamfer part): lion_chamfer_forward / lion_chamfer_pairwise through the
+reference-facing wrappers, against the CPU oracle and -- where it was built -- the reference's own
+chamfer_3D extension (oracle/_ref/chamfer_3D.so): distances bit-exact, indices exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import build_ref
+from oracle import metrics as OM
+from tests.util import assert_close, gen
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_forward(mod, a, b):
+    B, n, m = a.shape[0], a.shape[1], b.shape[1]
+    d1 = torch.zeros(B, n, device="cuda"); d2 = torch.zeros(B, m, device="cuda")
+    i1 = torch.zeros(B, n, dtype=torch.int32, device="cuda"); i2 = torch.zeros(B, m, dtype=torch.int32, device="cuda")
+    mod.forward(a, b, d1, d2, i1, i2)
+    return d1, d2, i1, i2
+
+
+@pytest.mark.parametrize("B,N,M", [(3, 2048, 2048), (2, 1000, 777), (1, 5, 3000), (4, 1, 1), (2, 4100, 513)])
+def test_chamfer_forward_matches_oracle_and_reference_kernel(B, N, M):
+    from lion_b200.third_party.ChamferDistancePytorch.chamfer3D.dist_chamfer_3D import chamfer_3DDist_nograd
+    a, b = gen(81, B, N, 3), gen(82, B, M, 3)
+    if N > 4 and M > 4:
+        b[:, 3] = b[:, 1]                      # duplicated candidates: exact ties, lowest index must win
+        a[:, 2] = a[:, 0]
+    d1, d2, i1, i2 = chamfer_3DDist_nograd()(a.cuda(), b.cuda())
+    assert i1.dtype == torch.int32 and d1.shape == (B, N) and i2.shape == (B, M)
+    o1, o2, j1, j2 = OM.chamfer_forward(a.numpy(), b.numpy())
+    assert np.array_equal(i1.cpu().numpy(), j1) and np.array_equal(i2.cpu().numpy(), j2)
+    assert np.array_equal(d1.cpu().numpy(), o1) and np.array_equal(d2.cpu().numpy(), o2)
+    mod = build_ref.load_chamfer()
+    if mod is not None:
+        r1, r2, k1, k2 = _ref_forward(mod, a.cuda(), b.cuda())
+        assert torch.equal(i1, k1) and torch.equal(i2, k2), "indices differ from the reference kernel"
+        assert torch.equal(d1, r1) and torch.equal(d2, r2), "distances differ from the reference kernel"
+
+
+def test_reference_chamfer_extension_was_built():
+    """oracle/_ref/chamfer_3D.so is built in the container (build()) and shipped; without it the
+    comparison above silently loses its strongest leg."""
+    assert build_ref.load_chamfer() is not None, "oracle/_ref/chamfer_3D.so missing: run python oracle/build_ref.py"
+
+
+def test_pairwise_cd_matrix():
+    from lion_b200.utils.evaluation_metrics_fast import _pairwise_EMD_CD_, distChamferCUDAnograd
+    s, r = gen(83, 5, 2048, 3), gen(84, 7, 2048, 3) * 1.1
+    cd, cd2 = _pairwise_EMD_CD_('CD', s.cuda(), r.cuda(), batch_size=3, require_grad=False)
+    assert cd.shape == (5, 7) and cd2 is cd
+    assert_close(cd, torch.from_numpy(OM.pairwise_cd(s.numpy(), r.numpy())), 1e-5, "pairwise CD vs oracle")
+    # the reference's composition: one sample expanded against the reference batch, dl.mean(1) + dr.mean(1)
+    for i in (0, 4):
+        dl, dr = distChamferCUDAnograd(s[i:i + 1].expand(7, -1, -1).contiguous().cuda(), r.cuda())
+        assert_close(cd[i], dl.mean(1) + dr.mean(1), 1e-5, "pairwise CD vs drop-in composition")
+    again, _ = _pairwise_EMD_CD_('CD', s.cuda(), r.cuda(), batch_size=3)
+    assert torch.equal(again, cd), "pairwise CD is not bit-reproducible"
+    # ragged sizes
+    s2, r2 = gen(85, 2, 300, 3), gen(86, 3, 1111, 3)
+    cd3, _ = _pairwise_EMD_CD_('CD', s2.cuda(), r2.cuda(), batch_size=8)
+    assert_close(cd3, torch.from_numpy(OM.pairwise_cd(s2.numpy(), r2.numpy())), 1e-5, "ragged pairwise CD")
+    with pytest.raises(NotImplementedError):
+        _pairwise_EMD_CD_('EMD', s.cuda(), r.cuda(), batch_size=3)
