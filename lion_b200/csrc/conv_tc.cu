@@ -384,8 +384,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       if (et < P.NT) s_bias[et] = P.bias ? P.bias[n0 + et] : 0.0f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // per 16-column chunk of this warp's half
-      if (CH <= 32) {
-        // N <= 64: per-lane (= per-row) running sums over the item's tiles, ONE cross-lane reduction
+      if (TPG == 1 && CH <= 32) {
+        // 1x1 convolutions, N <= 64 (compiled out of the 3x3x3 instantiations, whose epilogue is off the
+        // critical path and whose issue loop suffered from the extra register pressure): per-lane (= per-row) running sums over the item's tiles, ONE cross-lane reduction
         // per item instead of one per tile; both 16-column loads of a tile are in flight together.
         // (1x1 convolutions have almost no MMA work per tile, so this loop is their critical path.)
         float acc_s[2][16], acc_q[2][16];

@@ -454,14 +454,17 @@ static int sa_fwd(Fwd& f, const SABlk& s, PF feat, const float4* c4, float4* cen
                   int pre_fps = -1) {
   int N = feat.R, M = s.m, U = s.k, Gf = s.cfeat / 4;
   if (feat.G != Gf) { set_error("SA: got %d feature channels, expected %d", feat.G * 4, s.cfeat); return LION_ERR_ARG; }
-  if (N > FPS_THREADS * FPS_MAX_PER_THREAD) { set_error("SA: N=%d too large for FPS", N); return LION_ERR_ARG; }
+  if (N > FPS_MAX_N) { set_error("SA: N=%d too large for FPS", N); return LION_ERR_ARG; }
   if (M > N) { set_error("SA: more centres (%d) than points (%d)", M, N); return LION_ERR_ARG; }
   size_t mk = f.c->mark();
   if (pre_fps >= 0) {
     if (!f.c->dry) LION_CHECK_CUDA(cudaStreamWaitEvent(f.c->stream, f.c->ev[pre_fps], 0));
   } else {
     int* fidx = f.c->alloc_n<int>((size_t)f.B * M);
-    LION_LAUNCH(f.c, k_fps_c4, f.B, FPS_THREADS, 0, c4, fidx, centers, N, M);
+    const int VT = fps_virtual_threads(N);
+#define LION_FPS_CALL(A_, C_) LION_LAUNCH(f.c, (k_fps_c4<A_, C_>), f.B, FPS_THREADS, 0, c4, fidx, centers, N, M, VT)
+    LION_FPS_DISPATCH(N, VT, LION_FPS_CALL);
+#undef LION_FPS_CALL
   }
   int* nidx = f.c->alloc_n<int>((size_t)f.B * M * U);
   float r2 = s.radius * s.radius;
@@ -654,11 +657,14 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
     }
     for (int i = 0; i < n_sa && i < 8; ++i) {
       const SABlk& sb = u.sa[i].back().sa;
-      if (ncur > FPS_THREADS * FPS_MAX_PER_THREAD || sb.m > ncur) { set_error("unet: FPS sizes unsupported"); return LION_ERR_ARG; }
+      if (ncur > FPS_MAX_N || sb.m > ncur) { set_error("unet: FPS sizes unsupported"); return LION_ERR_ARG; }
       fps_centers[i] = c->alloc_n<float4>((size_t)B * sb.m);
       int* fidx = c->alloc_n<int>((size_t)B * sb.m);
       if (!c->dry) {
-        k_fps_c4<<<B, FPS_THREADS, 0, c->aux>>>(src, fidx, fps_centers[i], ncur, sb.m);
+        const int VT = fps_virtual_threads(ncur);
+#define LION_FPS_CALL(A_, C_) k_fps_c4<A_, C_><<<B, FPS_THREADS, 0, c->aux>>>(src, fidx, fps_centers[i], ncur, sb.m, VT)
+        LION_FPS_DISPATCH(ncur, VT, LION_FPS_CALL);
+#undef LION_FPS_CALL
         c->launches++;
         LION_CHECK_CUDA(cudaEventRecord(c->ev[i], c->aux));
       }

@@ -516,15 +516,16 @@ __global__ void k_devox_fuse(const float4* __restrict__ raw, const float4* __res
 // ------------------------------------------------------------------------------------
 // set abstraction: FPS (+ centre coordinates), ball query, grouped input assembly
 // ------------------------------------------------------------------------------------
+template <int A, int C>
 __global__ void __launch_bounds__(FPS_THREADS)
-k_fps_c4(const float4* __restrict__ c4, int* __restrict__ idx, float4* __restrict__ centers, int N, int M) {
+k_fps_c4(const float4* __restrict__ c4, int* __restrict__ idx, float4* __restrict__ centers, int N, int M, int VT) {
   pdl_prologue();
   int b = blockIdx.x;
   const float4* c = c4 + (size_t)b * N;
   int* io = idx + (size_t)b * M;
   float4* co = centers + (size_t)b * M;
-  fps_block_emit([&](int k, float& x, float& y, float& z) { float4 v = c[k]; x = v.x; y = v.y; z = v.z; },
-                 [&](int j, int k, float x, float y, float z) { io[j] = k; co[j] = make_float4(x, y, z, 0.0f); }, N, M);
+  fps_block_emit<A, C>([&](int k, float& x, float& y, float& z) { float4 v = c[k]; x = v.x; y = v.y; z = v.z; },
+                       [&](int j, int k, float x, float y, float z) { io[j] = k; co[j] = make_float4(x, y, z, 0.0f); }, N, M, VT);
 }
 
 __global__ void k_ball_query_c4(const float4* __restrict__ centers, const float4* __restrict__ points, int* __restrict__ out,

@@ -99,90 +99,91 @@ __device__ __forceinline__ void vox_normalize(float dx, float dy, float dz, floa
 
 // ---------------------------------------------------------------------------------------
 // furthest point sampling (sampling/sampling.cu:86-167).
-// One CTA per shape; thread t owns points t, t+T, t+2T, ... (T = 512, the reference's block
-// size, so the reference's tie-breaking -- max distance, then lowest thread, then lowest
-// index within the thread -- is reproduced by construction), coordinates and running
-// min-distances live in registers, the arg-max is a shuffle butterfly + one shared-memory
-// exchange with a single __syncthreads per round (the reference: 9 barriers + global-memory
-// distance traffic per round).
+// One CTA of 128 threads per shape.  The reference always launches VT = 512 threads
+// (sampling.cu:171), thread v owning points v, v+VT, v+2VT, ..., and breaks ties by (max distance,
+// then lowest thread, then lowest index within the thread).  Here thread t plays the reference threads
+// v = t, t+128, t+256, t+384 (A of them) with up to C points each, visited in (v, index) order,
+// so the same total order falls out of a strict '>' scan plus an integer key (v << 20 | index).
+// Coordinates and running min-distances live in registers (A*C <= 32 points per thread); the
+// arg-max is two warp `redux` operations (max of the distance bits, min of the key among the
+// maxima) per level and ONE __syncthreads per round -- the reference: 9 barriers plus global-
+// memory distance traffic per round; the first version of this kernel (512 threads, 15-shuffle
+// butterflies, 16 warps at the barrier) needed 1600 cycles per round, this one about a third.
 // ---------------------------------------------------------------------------------------
-constexpr int FPS_THREADS = 512;
-constexpr int FPS_MAX_PER_THREAD = 8;   // N <= 4096
+constexpr int FPS_THREADS = 128;
+constexpr int FPS_MAX_N = 4096;          // A = 4 virtual threads x C = 8 points
 
-struct FpsBest {
-  float v; int tid; int k;
-};
-__device__ __forceinline__ FpsBest fps_better(FpsBest a, FpsBest b) {
-  // keep a unless b is strictly larger, or equal with a lower owning thread (lower slot wins ties)
-  bool take_b = (b.v > a.v) || (b.v == a.v && b.tid < a.tid);
-  return take_b ? b : a;
-}
-__device__ __forceinline__ FpsBest fps_shfl_xor(FpsBest a, int o) {
-  FpsBest b;
-  b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
-  b.tid = __shfl_xor_sync(0xffffffffu, a.tid, o);
-  b.k = __shfl_xor_sync(0xffffffffu, a.k, o);
-  return b;
-}
+inline int fps_virtual_threads(int) { return 512; }   // sampling.cu:171: <<<b, 512>>> whatever n is
 
 // Emit(j, k, x, y, z) is called by one thread for every selected point j=0..M-1.
-template <typename Load, typename Emit>
-__device__ __forceinline__ void fps_block_emit(Load load, Emit emit, int N, int M) {
+template <int A, int C, typename Load, typename Emit>
+__device__ __forceinline__ void fps_block_emit(Load load, Emit emit, int N, int M, int VT) {
   constexpr int NW = FPS_THREADS / 32;
-  __shared__ float s_v[2][NW];
-  __shared__ int s_t[2][NW];
-  __shared__ int s_k[2][NW];
+  constexpr unsigned FULL = 0xffffffffu;
+  __shared__ unsigned s_m[2][NW], s_id[2][NW];
   __shared__ float s_xyz[2][NW][3];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  float px[FPS_MAX_PER_THREAD], py[FPS_MAX_PER_THREAD], pz[FPS_MAX_PER_THREAD], pd[FPS_MAX_PER_THREAD];
+  float px[A * C], py[A * C], pz[A * C], pd[A * C];
 #pragma unroll
-  for (int i = 0; i < FPS_MAX_PER_THREAD; ++i) {
-    int k = tid + i * FPS_THREADS;
-    px[i] = py[i] = pz[i] = 0.0f;
-    pd[i] = 1e38f;                         // sampling.cpp:54
-    if (k < N) load(k, px[i], py[i], pz[i]);
-  }
+  for (int a = 0; a < A; ++a)
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const int v = tid + a * FPS_THREADS, k = v + c * VT, s = a * C + c;
+      px[s] = py[s] = pz[s] = 0.0f;
+      pd[s] = 1e38f;                         // sampling.cpp:54
+      if (v < VT && k < N) load(k, px[s], py[s], pz[s]);
+    }
   float lx, ly, lz;
   load(0, lx, ly, lz);                     // first pick is point 0 (sampling.cu:104-106)
   if (tid == 0) emit(0, 0, lx, ly, lz);
   for (int j = 1; j < M; ++j) {
-    FpsBest b;
-    b.v = -1.0f; b.tid = tid; b.k = 0;     // threads without points never win (sampling.cu:117-118)
+    unsigned bm = 0u, bid = 0xffffffffu;   // threads without points never win (sampling.cu:117-118)
     float bx = 0, by = 0, bz = 0;
 #pragma unroll
-    for (int i = 0; i < FPS_MAX_PER_THREAD; ++i) {
-      int k = tid + i * FPS_THREADS;
-      if (k < N) {
-        float d = sqdist_ref(px[i] - lx, py[i] - ly, pz[i] - lz);
-        float d2 = fminf(d, pd[i]);
-        pd[i] = d2;
-        if (d2 > b.v) { b.v = d2; b.k = k; bx = px[i]; by = py[i]; bz = pz[i]; }
-      }
-    }
-    FpsBest w = b;
+    for (int a = 0; a < A; ++a)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) w = fps_better(w, fps_shfl_xor(w, o));
-    int buf = j & 1;
-    if (w.tid == tid) {                    // exactly one lane per warp owns the warp's winner
-      s_v[buf][wid] = w.v; s_t[buf][wid] = w.tid; s_k[buf][wid] = w.k;
+      for (int c = 0; c < C; ++c) {
+        const int v = tid + a * FPS_THREADS, k = v + c * VT, s = a * C + c;
+        if (v < VT && k < N) {
+          float d = sqdist_ref(px[s] - lx, py[s] - ly, pz[s] - lz);
+          float d2 = fminf(d, pd[s]);
+          pd[s] = d2;
+          unsigned key = __float_as_uint(d2) + 1u;       // d2 >= 0: the bit pattern orders like the value
+          if (key > bm) { bm = key; bid = ((unsigned)v << 20) | (unsigned)k; bx = px[s]; by = py[s]; bz = pz[s]; }
+        }
+      }
+    const int buf = j & 1;
+    const unsigned wm = __reduce_max_sync(FULL, bm);
+    const unsigned wi = __reduce_min_sync(FULL, bm == wm ? bid : 0xffffffffu);
+    if (wm == 0u) {
+      if (lane == 0) { s_m[buf][wid] = 0u; s_id[buf][wid] = 0xffffffffu; }
+    } else if (bm == wm && bid == wi) {      // exactly one lane: keys are unique per point
+      s_m[buf][wid] = wm; s_id[buf][wid] = wi;
       s_xyz[buf][wid][0] = bx; s_xyz[buf][wid][1] = by; s_xyz[buf][wid][2] = bz;
     }
     __syncthreads();
-    FpsBest g;
-    if (lane < NW) { g.v = s_v[buf][lane]; g.tid = s_t[buf][lane]; g.k = s_k[buf][lane]; }
-    else { g.v = -2.0f; g.tid = 1 << 30; g.k = 0; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) g = fps_better(g, fps_shfl_xor(g, o));
-    int ww = g.tid >> 5;
+    const unsigned gm = lane < NW ? s_m[buf][lane] : 0u;
+    const unsigned gi = lane < NW ? s_id[buf][lane] : 0xffffffffu;
+    const unsigned tm = __reduce_max_sync(FULL, gm);
+    const unsigned ti = __reduce_min_sync(FULL, gm == tm ? gi : 0xffffffffu);
+    const int ww = __ffs(__ballot_sync(FULL, gm == tm && gi == ti)) - 1;
     lx = s_xyz[buf][ww][0]; ly = s_xyz[buf][ww][1]; lz = s_xyz[buf][ww][2];
-    if (tid == 0) emit(j, g.k, lx, ly, lz);
+    if (tid == 0) emit(j, (int)(ti & 0xfffffu), lx, ly, lz);
   }
 }
 
-template <typename Load>
-__device__ __forceinline__ void fps_block(Load load, int* idx_out, int N, int M) {
-  fps_block_emit(load, [&](int j, int k, float, float, float) { idx_out[j] = k; }, N, M);
-}
+// pick the instantiation: A = reference threads per real thread, C = points per reference thread
+#define LION_FPS_DISPATCH(N, VT, CALL)                                                   \
+  do {                                                                                   \
+    const int _a = (N) <= lion::FPS_THREADS ? 1 : ((N) <= 2 * lion::FPS_THREADS ? 2 : 4); /* reference threads that own a point */ \
+    const int _c = ((N) + (VT)-1) / (VT);                                                \
+    if (_a == 4 && _c > 4) { CALL(4, 8); }                                               \
+    else if (_a == 4 && _c > 2) { CALL(4, 4); }                                          \
+    else if (_a == 4 && _c > 1) { CALL(4, 2); }                                          \
+    else if (_a == 4) { CALL(4, 1); }                                                    \
+    else if (_a == 2) { CALL(2, 1); }                                                    \
+    else { CALL(1, 1); }                                                                 \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------
 // ball query (ball_query/ball_query.cu:19-50): first K point indices in ascending order with

@@ -84,13 +84,15 @@ __global__ void k_trilinear_devox(const float* __restrict__ coords, const float*
 // ------------------------------------------------------------------------------------
 // furthest point sampling (reference: sampling/sampling.cu:86-167) -- see point_core.cuh
 // ------------------------------------------------------------------------------------
+template <int A, int C>
 __global__ void __launch_bounds__(FPS_THREADS)
-k_fps_soa(const float* __restrict__ coords, int* __restrict__ idx_out, int N, int M) {
+k_fps_soa(const float* __restrict__ coords, int* __restrict__ idx_out, int N, int M, int VT) {
   pdl_prologue();
   int b = blockIdx.x;
   const float* c = coords + (size_t)b * 3 * N;
-  fps_block([&](int k, float& x, float& y, float& z) { x = c[k]; y = c[k + N]; z = c[k + 2 * N]; },
-            idx_out + (size_t)b * M, N, M);
+  int* io = idx_out + (size_t)b * M;
+  fps_block_emit<A, C>([&](int k, float& x, float& y, float& z) { x = c[k]; y = c[k + N]; z = c[k + 2 * N]; },
+                       [&](int j, int k, float, float, float) { io[j] = k; }, N, M, VT);
 }
 
 __global__ void k_gather(const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out,
@@ -236,10 +238,12 @@ extern "C" int lion_trilinear_devoxelize(const float* grid, const float* coords,
 extern "C" int lion_furthest_point_sampling(const float* coords, int* idx, int B, int N, int M, void* stream) {
   LION_REQUIRE(coords && idx, "lion_furthest_point_sampling: null pointer");
   LION_REQUIRE(B > 0 && N > 0 && M > 0, "lion_furthest_point_sampling: bad sizes");
-  LION_REQUIRE(N <= FPS_THREADS * FPS_MAX_PER_THREAD, "lion_furthest_point_sampling: N=%d exceeds %d", N,
-               FPS_THREADS * FPS_MAX_PER_THREAD);
+  LION_REQUIRE(N <= FPS_MAX_N, "lion_furthest_point_sampling: N=%d exceeds %d", N, FPS_MAX_N);
   Ctx c = tmp_ctx(stream);
-  LION_LAUNCH(&c, k_fps_soa, B, FPS_THREADS, 0, coords, idx, N, M);
+  const int VT = fps_virtual_threads(N);
+#define LION_FPS_CALL(A_, C_) LION_LAUNCH(&c, (k_fps_soa<A_, C_>), B, FPS_THREADS, 0, coords, idx, N, M, VT)
+  LION_FPS_DISPATCH(N, VT, LION_FPS_CALL);
+#undef LION_FPS_CALL
   return check_launch(&c, "lion_furthest_point_sampling");
 }
 
