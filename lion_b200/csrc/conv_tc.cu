@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           }
           if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
           long long row0 = row_item + P.tg_off[tg];
-          for (int j = 0; j < ntile; j += P.MT, row0 += 128 * P.MT) {
+          const int MT = (TPG == 1) ? P.MT : 1;      // compile-time 1 in the 3x3x3 instantiations
+          for (int j = 0; j < ntile; j += MT, row0 += 128 * MT) {
             mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
             bool empty = false;
             if (may_skip) {
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             // multi-tile stages (1x1 only): copy just the rows this item still has, and never past
             // the end of the (b, group) slab
             uint32_t nbytes = bytes;
-            if (P.MT > 1) {
-              long long nr = (long long)min(P.MT, ntile - j) * 128;
+            if (MT > 1) {
+              long long nr = (long long)min(MT, ntile - j) * 128;
               if (nr > P.rows - row0) nr = P.rows - row0;
               nbytes = (uint32_t)nr * 16u;
             }
@@ -325,7 +326,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           const uint32_t b_base16 = smem_u32(sB + (size_t)sb * P.b_stage_bytes) >> 4;
           const bool first = (cc | tg) == 0;
           const bool last = (cc == P.nchunk - 1) && (tg == P.ntg - 1);
-          for (int j = 0; j < ntile; j += P.MT) {
+          const int MT = (TPG == 1) ? P.MT : 1;      // compile-time 1 in the 3x3x3 instantiations (their issue loop is the critical path)
+          for (int j = 0; j < ntile; j += MT) {
             const uint32_t my_sa = sa, my_pa = pa;
             if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
             // BOTH issuers wait on every stage and both release it (empty count 2).  A parity wait is
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             // phase behind and mistake "not yet loaded" for "loaded" (seen with odd ring depths).
             mbar_wait(bar_full_a + 8 * my_sa, my_pa);
             bool issued = false;
-            for (int jj = 0; jj < P.MT; ++jj) {
+            for (int jj = 0; jj < MT; ++jj) {
               const int jt = j + jj;
               if (jt >= ntile) break;
               if ((jt & 1) != me) continue;                              // the other issuer's tile

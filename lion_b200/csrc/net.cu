@@ -339,7 +339,7 @@ static int shared_mlp_fwd(Fwd& f, const SharedMLPBlk& m, PF in, int pool, float4
     if (last && pool > 1) {
       if (pool != 32 || cur.R % 32) { set_error("shared_mlp: unsupported pooling %d", pool); return LION_ERR_ARG; }
       int Ro = cur.R / 32;
-      LION_LAUNCH(f.c, k_act_rows<32>, dim3(cdiv(Ro, 64), Gout, f.B), 64, 0, raw.p, dst, a.scale, a.shift, Gout, w.cout, Ro, Gd, g_off, 0);
+      LION_LAUNCH(f.c, k_act_rows_pool32, dim3(cdiv(Ro, 8 * 4), Gout, f.B), 256, 0, raw.p, dst, a.scale, a.shift, Gout, w.cout, Ro, Gd, g_off);
     } else {
       PF nxt;
       float4* o; int gd, go;
@@ -410,7 +410,7 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   double V = (double)r * r * r;
   LION_TRY(run_affine(f, p.g1, s1, q1, p.c1.cout_pad, V, nullptr, nullptr, a1));
   float4* act1 = alloc_vg(f, Gout, r);
-  LION_LAUNCH(f.c, k_act_grid, dim3(cdiv(P, 256), Gout, f.B), 256, 0, raw1, act1, a1.scale, a1.shift, Gout, p.cout, rp, P);
+  LION_LAUNCH(f.c, k_act_grid, dim3(cdiv(P, 256 * ACT_U), Gout, f.B), 256, 0, raw1, act1, a1.scale, a1.shift, Gout, p.cout, rp, P);
   // conv2 -> (stats) -> AdaGN + SE folded into one affine
   float4* raw2 = alloc_vg(f, Gout, r);
   double *s2, *q2;
@@ -462,7 +462,12 @@ static int sa_fwd(Fwd& f, const SABlk& s, PF feat, const float4* c4, float4* cen
   } else {
     int* fidx = f.c->alloc_n<int>((size_t)f.B * M);
     const int VT = fps_virtual_threads(N);
-#define LION_FPS_CALL(A_, C_) LION_LAUNCH(f.c, (k_fps_c4<A_, C_>), f.B, FPS_THREADS, 0, c4, fidx, centers, N, M, VT)
+#define LION_FPS_CALL(A_, C_, F_)                                                                                         \
+  do {                                                                                                                    \
+    if (fps_smem_bytes(N) > 48 * 1024)                                                                                    \
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_fps_c4<A_, C_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+    LION_LAUNCH(f.c, (k_fps_c4<A_, C_, F_>), f.B, FPS_THREADS, fps_smem_bytes(N), c4, fidx, centers, N, M, VT);           \
+  } while (0)
     LION_FPS_DISPATCH(N, VT, LION_FPS_CALL);
 #undef LION_FPS_CALL
   }
@@ -662,7 +667,12 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
       int* fidx = c->alloc_n<int>((size_t)B * sb.m);
       if (!c->dry) {
         const int VT = fps_virtual_threads(ncur);
-#define LION_FPS_CALL(A_, C_) k_fps_c4<A_, C_><<<B, FPS_THREADS, 0, c->aux>>>(src, fidx, fps_centers[i], ncur, sb.m, VT)
+#define LION_FPS_CALL(A_, C_, F_)                                                                                         \
+  do {                                                                                                                    \
+    if (fps_smem_bytes(ncur) > 48 * 1024)                                                                                 \
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_fps_c4<A_, C_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+    k_fps_c4<A_, C_, F_><<<B, FPS_THREADS, fps_smem_bytes(ncur), c->aux>>>(src, fidx, fps_centers[i], ncur, sb.m, VT);    \
+  } while (0)
         LION_FPS_DISPATCH(ncur, VT, LION_FPS_CALL);
 #undef LION_FPS_CALL
         c->launches++;

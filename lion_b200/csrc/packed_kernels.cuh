@@ -371,23 +371,38 @@ __global__ void k_time_sinusoid(const float* __restrict__ t, const float* __rest
 // ------------------------------------------------------------------------------------
 // elementwise passes
 // ------------------------------------------------------------------------------------
-// VG: y = swish(scale*x + shift) on interior voxels, 0 on every halo position (incl. x planes)
+// VG: y = swish(scale*x + shift) on interior voxels, 0 on every halo position (incl. x planes).
+// ACT_U positions per thread, loads issued before any use: a 16-byte access per thread leaves too
+// few bytes in flight per SM to cover HBM latency (4.3 TB/s measured with one access per thread).
+constexpr int ACT_U = 4;
 __global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
                            const float* __restrict__ shift, int G, int C, int rp, int P) {
   pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  int z = p % rp, y = (p / rp) % rp, x = p / (rp * rp);
-  bool interior = z >= 1 && z <= rp - 2 && y >= 1 && y <= rp - 2 && x >= 1 && x <= rp - 2;
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (interior) {
-    float4 v = in[((size_t)b * G + g) * P + p];
-    float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
-    float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
-    r = f4_tf32(f4_swish(f4_affine(v, s, t)));   // sole consumer: the second 3x3x3 convolution
+  const float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
+  const float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
+  const float4* src = in + ((size_t)b * G + g) * P;
+  float4* dst = out + ((size_t)b * G + g) * P;
+  const int p0 = blockIdx.x * (blockDim.x * ACT_U) + threadIdx.x;
+  float4 v[ACT_U];
+  bool interior[ACT_U];
+#pragma unroll
+  for (int u = 0; u < ACT_U; ++u) {
+    int p = p0 + u * blockDim.x;
+    int z = p % rp, y = (p / rp) % rp, x = p / (rp * rp);
+    interior[u] = p < P && z >= 1 && z <= rp - 2 && y >= 1 && y <= rp - 2 && x >= 1 && x <= rp - 2;
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (interior[u]) v[u] = __ldcs(src + p);          // read once: streaming
   }
-  out[((size_t)b * G + g) * P + p] = r;
+#pragma unroll
+  for (int u = 0; u < ACT_U; ++u) {
+    int p = p0 + u * blockDim.x;
+    if (p < P) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (interior[u]) r = f4_tf32(f4_swish(f4_affine(v[u], s, t)));   // sole consumer: the second 3x3x3 convolution
+      dst[p] = r;
+    }
+  }
 }
 
 // PF: y = swish(scale*x + shift); written at group offset g_off of a destination with Gd groups.
@@ -408,6 +423,42 @@ __global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ o
   for (int k = 1; k < POOL; ++k) r = f4_max(r, f4_swish(f4_affine(src[k], s, t)));
   if (flags & 1) r = f4_tf32(r);
   out[((size_t)b * Gd + g_off + g) * R_out + i] = r;
+}
+
+// PF -> PF with max over 32 consecutive rows (the neighbours of one centre) after the activation:
+// one warp per output row, lane k reads neighbour k (one coalesced 512-byte access per warp instead
+// of 32 strided ones per thread), butterfly max.  The result is the same set maximum as
+// k_act_rows<32>, bit for bit.
+__global__ void k_act_rows_pool32(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off) {
+  pdl_prologue();
+  int b = blockIdx.z, g = blockIdx.y;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
+  const float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
+  const float4* src = in + ((size_t)b * G + g) * (size_t)R_out * 32;
+  constexpr int ROWS = 4;                                  // rows per warp, loads issued together
+  const int i0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * ROWS;
+  float4 v[ROWS];
+#pragma unroll
+  for (int u = 0; u < ROWS; ++u) {
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + u < R_out) v[u] = __ldcs(src + (size_t)(i0 + u) * 32 + lane);
+  }
+#pragma unroll
+  for (int u = 0; u < ROWS; ++u) {
+    if (i0 + u < R_out) {                                  // warp-uniform
+      float4 r = f4_swish(f4_affine(v[u], s, t));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        r.x = fmaxf(r.x, __shfl_xor_sync(0xffffffffu, r.x, o));
+        r.y = fmaxf(r.y, __shfl_xor_sync(0xffffffffu, r.y, o));
+        r.z = fmaxf(r.z, __shfl_xor_sync(0xffffffffu, r.z, o));
+        r.w = fmaxf(r.w, __shfl_xor_sync(0xffffffffu, r.w, o));
+      }
+      if (lane == 0) out[((size_t)b * Gd + g_off + g) * R_out + i0 + u] = r;
+    }
+  }
 }
 
 // per-channel sum / sum of squares over the rows of a PF (stand-alone AdaGN / SE3d entry points;
@@ -516,16 +567,18 @@ __global__ void k_devox_fuse(const float4* __restrict__ raw, const float4* __res
 // ------------------------------------------------------------------------------------
 // set abstraction: FPS (+ centre coordinates), ball query, grouped input assembly
 // ------------------------------------------------------------------------------------
-template <int A, int C>
+template <int A, int C, bool FULL>
 __global__ void __launch_bounds__(FPS_THREADS)
 k_fps_c4(const float4* __restrict__ c4, int* __restrict__ idx, float4* __restrict__ centers, int N, int M, int VT) {
   pdl_prologue();
+  extern __shared__ float s_fps[];
   int b = blockIdx.x;
   const float4* c = c4 + (size_t)b * N;
   int* io = idx + (size_t)b * M;
   float4* co = centers + (size_t)b * M;
-  fps_block_emit<A, C>([&](int k, float& x, float& y, float& z) { float4 v = c[k]; x = v.x; y = v.y; z = v.z; },
-                       [&](int j, int k, float x, float y, float z) { io[j] = k; co[j] = make_float4(x, y, z, 0.0f); }, N, M, VT);
+  fps_block_emit<A, C, FULL>([&](int k, float& x, float& y, float& z) { float4 v = c[k]; x = v.x; y = v.y; z = v.z; },
+                             [&](int j, int k, float x, float y, float z) { io[j] = k; co[j] = make_float4(x, y, z, 0.0f); },
+                             N, M, VT, s_fps);
 }
 
 __global__ void k_ball_query_c4(const float4* __restrict__ centers, const float4* __restrict__ points, int* __restrict__ out,

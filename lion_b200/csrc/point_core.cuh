@@ -116,74 +116,77 @@ constexpr int FPS_MAX_N = 4096;          // A = 4 virtual threads x C = 8 points
 inline int fps_virtual_threads(int) { return 512; }   // sampling.cu:171: <<<b, 512>>> whatever n is
 
 // Emit(j, k, x, y, z) is called by one thread for every selected point j=0..M-1.
-template <int A, int C, typename Load, typename Emit>
-__device__ __forceinline__ void fps_block_emit(Load load, Emit emit, int N, int M, int VT) {
-  constexpr int NW = FPS_THREADS / 32;
-  constexpr unsigned FULL = 0xffffffffu;
-  __shared__ unsigned s_m[2][NW], s_id[2][NW];
-  __shared__ float s_xyz[2][NW][3];
+// s_pts: dynamic shared memory, 3*N floats (SoA copy of the coordinates: the winner's position is
+// one LDS away, so the scan carries only (key, slot) -- two selects per point, branch-free, which
+// lets the 16 independent distance chains of a thread overlap).
+// FULL: every (a, c) slot of every thread holds a point (N = 128*A*C); otherwise slots are masked.
+template <int A, int C, bool FULL, typename Load, typename Emit>
+__device__ __forceinline__ void fps_block_emit(Load load, Emit emit, int N, int M, int VT, float* s_pts) {
+  constexpr unsigned ALL = 0xffffffffu;
+  __shared__ uint4 s_m[2], s_id[2];        // per warp: max key, id of the warp's winner (double-buffered by round parity)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float* sx = s_pts; float* sy = s_pts + N; float* sz = s_pts + 2 * N;
+  for (int k = tid; k < N; k += FPS_THREADS) { float x, y, z; load(k, x, y, z); sx[k] = x; sy[k] = y; sz[k] = z; }
+  __syncthreads();
   float px[A * C], py[A * C], pz[A * C], pd[A * C];
+  unsigned vmask = 0u;
 #pragma unroll
   for (int a = 0; a < A; ++a)
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const int v = tid + a * FPS_THREADS, k = v + c * VT, s = a * C + c;
-      px[s] = py[s] = pz[s] = 0.0f;
+      const bool ok = FULL || (v < VT && k < N);
+      px[s] = ok ? sx[k] : 0.0f; py[s] = ok ? sy[k] : 0.0f; pz[s] = ok ? sz[k] : 0.0f;
       pd[s] = 1e38f;                         // sampling.cpp:54
-      if (v < VT && k < N) load(k, px[s], py[s], pz[s]);
+      if (ok) vmask |= 1u << s;
     }
-  float lx, ly, lz;
-  load(0, lx, ly, lz);                     // first pick is point 0 (sampling.cu:104-106)
+  float lx = sx[0], ly = sy[0], lz = sz[0];  // first pick is point 0 (sampling.cu:104-106)
   if (tid == 0) emit(0, 0, lx, ly, lz);
   for (int j = 1; j < M; ++j) {
-    unsigned bm = 0u, bid = 0xffffffffu;   // threads without points never win (sampling.cu:117-118)
-    float bx = 0, by = 0, bz = 0;
+    unsigned bm = 0u; int bs = 0;            // threads without points keep key 0 and never win (sampling.cu:117-118)
 #pragma unroll
-    for (int a = 0; a < A; ++a)
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const int v = tid + a * FPS_THREADS, k = v + c * VT, s = a * C + c;
-        if (v < VT && k < N) {
-          float d = sqdist_ref(px[s] - lx, py[s] - ly, pz[s] - lz);
-          float d2 = fminf(d, pd[s]);
-          pd[s] = d2;
-          unsigned key = __float_as_uint(d2) + 1u;       // d2 >= 0: the bit pattern orders like the value
-          if (key > bm) { bm = key; bid = ((unsigned)v << 20) | (unsigned)k; bx = px[s]; by = py[s]; bz = pz[s]; }
-        }
-      }
-    const int buf = j & 1;
-    const unsigned wm = __reduce_max_sync(FULL, bm);
-    const unsigned wi = __reduce_min_sync(FULL, bm == wm ? bid : 0xffffffffu);
-    if (wm == 0u) {
-      if (lane == 0) { s_m[buf][wid] = 0u; s_id[buf][wid] = 0xffffffffu; }
-    } else if (bm == wm && bid == wi) {      // exactly one lane: keys are unique per point
-      s_m[buf][wid] = wm; s_id[buf][wid] = wi;
-      s_xyz[buf][wid][0] = bx; s_xyz[buf][wid][1] = by; s_xyz[buf][wid][2] = bz;
+    for (int s = 0; s < A * C; ++s) {
+      float d2 = fminf(sqdist_ref(px[s] - lx, py[s] - ly, pz[s] - lz), pd[s]);
+      pd[s] = d2;
+      unsigned key = __float_as_uint(d2) + 1u;           // d2 >= 0: the bit pattern orders like the value
+      if (!FULL) key = ((vmask >> s) & 1u) ? key : 0u;
+      const bool better = key > bm;                      // strict: slots are visited in (thread, index) order
+      bm = better ? key : bm;
+      bs = better ? s : bs;
     }
+    const int bv = tid + (bs / C) * FPS_THREADS;
+    const unsigned bid = bm ? (((unsigned)bv << 20) | (unsigned)(bv + (bs % C) * VT)) : ALL;
+    const unsigned wm = __reduce_max_sync(ALL, bm);
+    const unsigned wi = __reduce_min_sync(ALL, bm == wm ? bid : ALL);
+    const int buf = j & 1;
+    if (lane == 0) { ((unsigned*)&s_m[buf])[wid] = wm; ((unsigned*)&s_id[buf])[wid] = wi; }
     __syncthreads();
-    const unsigned gm = lane < NW ? s_m[buf][lane] : 0u;
-    const unsigned gi = lane < NW ? s_id[buf][lane] : 0xffffffffu;
-    const unsigned tm = __reduce_max_sync(FULL, gm);
-    const unsigned ti = __reduce_min_sync(FULL, gm == tm ? gi : 0xffffffffu);
-    const int ww = __ffs(__ballot_sync(FULL, gm == tm && gi == ti)) - 1;
-    lx = s_xyz[buf][ww][0]; ly = s_xyz[buf][ww][1]; lz = s_xyz[buf][ww][2];
-    if (tid == 0) emit(j, (int)(ti & 0xfffffu), lx, ly, lz);
+    const uint4 gm = s_m[buf], gi = s_id[buf];
+    unsigned tm = gm.x, ti = gi.x;
+    if (gm.y > tm || (gm.y == tm && gi.y < ti)) { tm = gm.y; ti = gi.y; }
+    if (gm.z > tm || (gm.z == tm && gi.z < ti)) { tm = gm.z; ti = gi.z; }
+    if (gm.w > tm || (gm.w == tm && gi.w < ti)) { tm = gm.w; ti = gi.w; }
+    const int kb = (int)(ti & 0xfffffu);
+    lx = sx[kb]; ly = sy[kb]; lz = sz[kb];
+    if (tid == 0) emit(j, kb, lx, ly, lz);
   }
 }
+static_assert(FPS_THREADS == 128, "fps_block_emit packs one uint4 of per-warp results");
 
 // pick the instantiation: A = reference threads per real thread, C = points per reference thread
 #define LION_FPS_DISPATCH(N, VT, CALL)                                                   \
   do {                                                                                   \
     const int _a = (N) <= lion::FPS_THREADS ? 1 : ((N) <= 2 * lion::FPS_THREADS ? 2 : 4); /* reference threads that own a point */ \
     const int _c = ((N) + (VT)-1) / (VT);                                                \
-    if (_a == 4 && _c > 4) { CALL(4, 8); }                                               \
-    else if (_a == 4 && _c > 2) { CALL(4, 4); }                                          \
-    else if (_a == 4 && _c > 1) { CALL(4, 2); }                                          \
-    else if (_a == 4) { CALL(4, 1); }                                                    \
-    else if (_a == 2) { CALL(2, 1); }                                                    \
-    else { CALL(1, 1); }                                                                 \
+    if (_a == 4 && _c > 4) { if ((N) == 4096) { CALL(4, 8, true); } else { CALL(4, 8, false); } }       \
+    else if (_a == 4 && _c > 2) { if ((N) == 2048) { CALL(4, 4, true); } else { CALL(4, 4, false); } }  \
+    else if (_a == 4 && _c > 1) { if ((N) == 1024) { CALL(4, 2, true); } else { CALL(4, 2, false); } }  \
+    else if (_a == 4) { if ((N) == 512) { CALL(4, 1, true); } else { CALL(4, 1, false); } }             \
+    else if (_a == 2) { if ((N) == 256) { CALL(2, 1, true); } else { CALL(2, 1, false); } }             \
+    else { if ((N) == 128) { CALL(1, 1, true); } else { CALL(1, 1, false); } }                          \
   } while (0)
+// dynamic shared memory of the FPS kernels: the SoA coordinate copy (49 KB at N = 4096: opt-in above 48 KB)
+inline size_t fps_smem_bytes(int N) { return (size_t)3 * N * sizeof(float); }
 
 // ---------------------------------------------------------------------------------------
 // ball query (ball_query/ball_query.cu:19-50): first K point indices in ascending order with

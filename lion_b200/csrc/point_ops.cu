@@ -84,15 +84,16 @@ __global__ void k_trilinear_devox(const float* __restrict__ coords, const float*
 // ------------------------------------------------------------------------------------
 // furthest point sampling (reference: sampling/sampling.cu:86-167) -- see point_core.cuh
 // ------------------------------------------------------------------------------------
-template <int A, int C>
+template <int A, int C, bool FULL>
 __global__ void __launch_bounds__(FPS_THREADS)
 k_fps_soa(const float* __restrict__ coords, int* __restrict__ idx_out, int N, int M, int VT) {
   pdl_prologue();
+  extern __shared__ float s_fps[];
   int b = blockIdx.x;
   const float* c = coords + (size_t)b * 3 * N;
   int* io = idx_out + (size_t)b * M;
-  fps_block_emit<A, C>([&](int k, float& x, float& y, float& z) { x = c[k]; y = c[k + N]; z = c[k + 2 * N]; },
-                       [&](int j, int k, float, float, float) { io[j] = k; }, N, M, VT);
+  fps_block_emit<A, C, FULL>([&](int k, float& x, float& y, float& z) { x = c[k]; y = c[k + N]; z = c[k + 2 * N]; },
+                             [&](int j, int k, float, float, float) { io[j] = k; }, N, M, VT, s_fps);
 }
 
 __global__ void k_gather(const float* __restrict__ feat, const int* __restrict__ idx, float* __restrict__ out,
@@ -241,7 +242,12 @@ extern "C" int lion_furthest_point_sampling(const float* coords, int* idx, int B
   LION_REQUIRE(N <= FPS_MAX_N, "lion_furthest_point_sampling: N=%d exceeds %d", N, FPS_MAX_N);
   Ctx c = tmp_ctx(stream);
   const int VT = fps_virtual_threads(N);
-#define LION_FPS_CALL(A_, C_) LION_LAUNCH(&c, (k_fps_soa<A_, C_>), B, FPS_THREADS, 0, coords, idx, N, M, VT)
+#define LION_FPS_CALL(A_, C_, F_)                                                                                          \
+  do {                                                                                                                     \
+    if (fps_smem_bytes(N) > 48 * 1024)                                                                                     \
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_fps_soa<A_, C_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+    LION_LAUNCH(&c, (k_fps_soa<A_, C_, F_>), B, FPS_THREADS, fps_smem_bytes(N), coords, idx, N, M, VT);                    \
+  } while (0)
   LION_FPS_DISPATCH(N, VT, LION_FPS_CALL);
 #undef LION_FPS_CALL
   return check_launch(&c, "lion_furthest_point_sampling");
