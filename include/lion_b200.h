@@ -180,6 +180,16 @@ int lion_chamfer_forward(const float* xyz1, const float* xyz2, float* dist1, flo
 int lion_chamfer_pairwise(const float* samples, const float* refs, float* out, int n_sample, int n_ref, int N, int M,
                           void* stream);
 
+/* Approximate earth mover's distance (third_party/PyTorchEMD/cuda/emd_kernel.cu:23-170 approxmatch +
+ * :196-246 matchcost, as driven by emd_nograd.py:9-45): xyz1 [B,N,3], xyz2 [B,M,3] -> cost [B]
+ * = sum_{k,l} |xyz1_k - xyz2_l|^2 * match[l][k] (NOT yet divided by N; the Python wrapper does that).
+ * One fused kernel, a CTA per pair, the match matrix is never materialised.  N, M <= 2048.
+ * lion_emd_pairwise: samples [Ns,N,3] x refs [Nr,M,3] -> out [Ns,Nr] (the 'EMD' matrix of
+ * utils/evaluation_metrics_fast.py:272-340) without expanding the sample clouds. */
+int lion_emd_approx(const float* xyz1, const float* xyz2, float* cost, int B, int N, int M, void* stream);
+int lion_emd_pairwise(const float* samples, const float* refs, float* out, int n_sample, int n_ref, int N, int M,
+                      void* stream);
+
 /* measurement hook (bench.py roofline leg): average device time of `iters` launches of the
  * convolution kernel alone (CUDA events on `stream`), on synthetic data: ntaps = 27 -> 3x3x3
  * over [B, cin, r^3] (r_or_rows = r), ntaps = 1 -> 1x1 over r_or_rows rows.  flops_out = the

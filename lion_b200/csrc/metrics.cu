@@ -164,3 +164,180 @@ extern "C" int lion_chamfer_pairwise(const float* samples, const float* refs, fl
   LION_LAUNCH(&c, k_chamfer_pairwise, dim3(n_ref, n_sample), CD_PW_THREADS, smem, samples, refs, out, N, M, n_ref);
   return check_launch(&c, "lion_chamfer_pairwise");
 }
+
+// =====================================================================================
+// approximate earth mover's distance (second half)
+//
+// Reference: third_party/PyTorchEMD/cuda/emd_kernel.cu:23-170 (approxmatch<<<32,512>>>: ten
+// annealing levels -4^7 .. -4^-1, 0 of a soft assignment with row / column capacities, writing a
+// dense match[b][m][n]) followed by :196-246 (matchcost<<<32,512>>>: sum of d^2 * match), as called by
+// third_party/PyTorchEMD/emd_nograd.py:9-45 and utils/evaluation_metrics_fast.py:122-147 (emd_approx).
+//
+// Here: ONE kernel, one CTA per cloud pair; both clouds and the four capacity / ratio vectors live
+// in shared memory, every thread owns EMD_Q rows (points of xyz1) whose coordinates stay in registers,
+// and the cost sum(d^2 * w) is accumulated where the reference adds w into `match`, so the
+// [b][m][n] matrix (16 MB per pair at 2048 points) is never written.  Arithmetic follows the
+// reference expression by expression (same __expf, same per-thread summation order over the
+// other cloud) so the annealing iterates agree to rounding; only the final cost is summed in a
+// different order (per level instead of per matrix element).
+// =====================================================================================
+namespace lion {
+
+constexpr int EMD_THREADS = 512;
+constexpr int EMD_Q = 4;                      // rows per thread -> n, m <= 2048
+constexpr int EMD_MAX = EMD_THREADS * EMD_Q;
+
+__device__ __forceinline__ float emd_d2(float x1, float y1, float z1, float x2, float y2, float z2) {
+  return (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1) + (z2 - z1) * (z2 - z1);
+}
+
+// pair p: xyz1 = a[(p / nb) or p], xyz2 = b[(p % nb) or p]
+__global__ void __launch_bounds__(EMD_THREADS)
+k_emd_approx(const float* __restrict__ a, const float* __restrict__ bb, float* __restrict__ out, int n, int m, int nb, int pairwise) {
+  pdl_prologue();
+  extern __shared__ float sm[];
+  float4* p1 = reinterpret_cast<float4*>(sm);            // [n] x,y,z of xyz1 + ratioL
+  float4* p2 = p1 + EMD_MAX;                             // [m] x,y,z of xyz2 + (remainR | ratioR)
+  float* remainL = reinterpret_cast<float*>(p2 + EMD_MAX);
+  float* remainR = remainL + EMD_MAX;
+  float* ratioR = remainR + EMD_MAX;
+  float* red = ratioR + EMD_MAX;                          // [EMD_THREADS]
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const float* xyz1 = a + (size_t)(pairwise ? p / nb : p) * n * 3;
+  const float* xyz2 = bb + (size_t)(pairwise ? p % nb : p) * m * 3;
+  float multiL, multiR;
+  if (n >= m) { multiL = 1; multiR = n / m; } else { multiL = m / n; multiR = 1; }       // integer division as in the reference
+  for (int k = tid; k < n; k += EMD_THREADS) { p1[k] = make_float4(xyz1[k * 3], xyz1[k * 3 + 1], xyz1[k * 3 + 2], 0.f); remainL[k] = multiL; }
+  for (int l = tid; l < m; l += EMD_THREADS) { p2[l] = make_float4(xyz2[l * 3], xyz2[l * 3 + 1], xyz2[l * 3 + 2], 0.f); remainR[l] = multiR; }
+  float cost = 0.0f;
+  __syncthreads();
+  for (int j = 7; j >= -2; j--) {
+    float level = -powf(4.0f, j);
+    if (j == -2) level = 0;
+    // ---- pass 1: ratioL[k] = remainL[k] / (1e-9 + sum_l exp(level d) remainR[l]) ---------------
+    for (int l = tid; l < m; l += EMD_THREADS) p2[l].w = remainR[l];
+    __syncthreads();
+    {
+      float x1[EMD_Q], y1[EMD_Q], z1[EMD_Q], suml[EMD_Q];
+#pragma unroll
+      for (int u = 0; u < EMD_Q; ++u) {
+        int k = u * EMD_THREADS + tid;
+        float4 q = k < n ? p1[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        x1[u] = q.x; y1[u] = q.y; z1[u] = q.z; suml[u] = 1e-9f;
+      }
+      for (int l = 0; l < m; ++l) {
+        const float4 c = p2[l];
+#pragma unroll
+        for (int u = 0; u < EMD_Q; ++u) {
+          float d = level * emd_d2(x1[u], y1[u], z1[u], c.x, c.y, c.z);
+          float w = __expf(d) * c.w;
+          suml[u] += w;
+        }
+      }
+      __syncthreads();                                   // everyone is done reading p2[].w / p1[].w
+#pragma unroll
+      for (int u = 0; u < EMD_Q; ++u) {
+        int k = u * EMD_THREADS + tid;
+        if (k < n) p1[k].w = remainL[k] / suml[u];       // ratioL
+      }
+    }
+    __syncthreads();
+    // ---- pass 2: per column l: sumr, consumption -> ratioR[l], remainR[l] ----------------------
+    {
+      float x2[EMD_Q], y2[EMD_Q], z2[EMD_Q], sumr[EMD_Q];
+#pragma unroll
+      for (int u = 0; u < EMD_Q; ++u) {
+        int l = u * EMD_THREADS + tid;
+        float4 q = l < m ? p2[l] : make_float4(0.f, 0.f, 0.f, 0.f);
+        x2[u] = q.x; y2[u] = q.y; z2[u] = q.z; sumr[u] = 0.0f;
+      }
+      for (int k = 0; k < n; ++k) {
+        const float4 c = p1[k];
+#pragma unroll
+        for (int u = 0; u < EMD_Q; ++u) {
+          float w = __expf(level * emd_d2(c.x, c.y, c.z, x2[u], y2[u], z2[u])) * c.w;
+          sumr[u] += w;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EMD_Q; ++u) {
+        int l = u * EMD_THREADS + tid;
+        if (l < m) {
+          float r = remainR[l];
+          float s = sumr[u] * r;
+          float consumption = fminf(r / (s + 1e-9f), 1.0f);
+          ratioR[l] = consumption * r;
+          remainR[l] = fmaxf(0.0f, r - s);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- pass 3: w = exp(level d) ratioL[k] ratioR[l]  (the reference adds it to match[l][k]);
+    //      cost += d2 * w;  remainL[k] = max(0, remainL[k] - sum_l w) -------------------------------
+    for (int l = tid; l < m; l += EMD_THREADS) p2[l].w = ratioR[l];
+    __syncthreads();
+    {
+      float x1[EMD_Q], y1[EMD_Q], z1[EMD_Q], rl[EMD_Q], suml[EMD_Q];
+#pragma unroll
+      for (int u = 0; u < EMD_Q; ++u) {
+        int k = u * EMD_THREADS + tid;
+        float4 q = k < n ? p1[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        x1[u] = q.x; y1[u] = q.y; z1[u] = q.z; rl[u] = q.w; suml[u] = 0.0f;
+      }
+      for (int l = 0; l < m; ++l) {
+        const float4 c = p2[l];
+#pragma unroll
+        for (int u = 0; u < EMD_Q; ++u) {
+          float d2 = emd_d2(x1[u], y1[u], z1[u], c.x, c.y, c.z);
+          float w = __expf(level * d2) * rl[u] * c.w;
+          suml[u] += w;
+          cost = fmaf(d2, w, cost);                      // rows k >= n carry rl = 0 -> w = 0
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < EMD_Q; ++u) {
+        int k = u * EMD_THREADS + tid;
+        if (k < n) remainL[k] = fmaxf(0.0f, remainL[k] - suml[u]);
+      }
+    }
+    __syncthreads();
+  }
+  // block sum in a fixed order
+  cost = warp_sum(cost);
+  if ((tid & 31) == 0) red[tid >> 5] = cost;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < EMD_THREADS / 32; ++w) t += red[w];
+    out[p] = t;
+  }
+}
+
+}  // namespace lion
+
+static int emd_launch(const float* a, const float* b, float* out, int pairs, int n, int m, int nb, int pairwise, void* stream) {
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  const size_t smem = (size_t)EMD_MAX * (2 * sizeof(float4) + 3 * sizeof(float)) + EMD_THREADS * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LION_CHECK_CUDA(cudaFuncSetAttribute(k_emd_approx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  LION_LAUNCH(&c, k_emd_approx, pairs, EMD_THREADS, smem, a, b, out, n, m, nb, pairwise);
+  return check_launch(&c, "lion_emd_approx");
+}
+
+extern "C" int lion_emd_approx(const float* xyz1, const float* xyz2, float* cost, int B, int N, int M, void* stream) {
+  LION_REQUIRE(xyz1 && xyz2 && cost && B > 0 && N > 0 && M > 0, "lion_emd_approx: bad arguments");
+  LION_REQUIRE(N <= EMD_MAX && M <= EMD_MAX, "lion_emd_approx: clouds of at most %d points (got %d, %d)", EMD_MAX, N, M);
+  return emd_launch(xyz1, xyz2, cost, B, N, M, 1, 0, stream);
+}
+
+extern "C" int lion_emd_pairwise(const float* samples, const float* refs, float* out, int n_sample, int n_ref, int N, int M,
+                                 void* stream) {
+  LION_REQUIRE(samples && refs && out && n_sample > 0 && n_ref > 0 && N > 0 && M > 0, "lion_emd_pairwise: bad arguments");
+  LION_REQUIRE(N <= EMD_MAX && M <= EMD_MAX, "lion_emd_pairwise: clouds of at most %d points (got %d, %d)", EMD_MAX, N, M);
+  LION_REQUIRE((long long)n_sample * n_ref < (1LL << 31), "lion_emd_pairwise: too many pairs");
+  return emd_launch(samples, refs, out, n_sample * n_ref, N, M, n_ref, 1, stream);
+}

@@ -5,12 +5,13 @@ utils/evaluation_metrics_fast.py: `distChamferCUDAnograd` (:83-88 region) and th
 `_pairwise_EMD_CD_(metric='CD', ...)` is ONE kernel launch per <= 65535 sample clouds
 (lion_chamfer_pairwise: a CTA per (sample, reference) pair, both directions, means reduced on
 chip) instead of the reference's Python double loop with an expanded copy of the sample cloud
-per reference batch.  EMD (third_party/PyTorchEMD, whose CUDA source no longer builds against
-current PyTorch: it includes the removed THC headers) is not provided."""
+per reference batch; metric='EMD' likewise (lion_emd_pairwise: the fused approxmatch + matchcost
+kernel per pair, no [Nr, M, N] match matrices)."""
 import torch
 
 from .. import _lib as L
 from ..third_party.ChamferDistancePytorch.chamfer3D.dist_chamfer_3D import chamfer_3DDist_nograd
+from ..third_party.PyTorchEMD.emd_nograd import earth_mover_distance_nograd
 
 
 def distChamferCUDAnograd(x, y, points_dim=3):
@@ -39,10 +40,35 @@ def pairwise_CD(sample_pcs, ref_pcs):
     return out
 
 
+def emd_approx(sample, ref, require_grad=True):
+    """[B,N,3] x [B,M,3] -> [B] approximate EMD / N (reference :122-147; forward only)."""
+    if require_grad and torch.is_grad_enabled() and (sample.requires_grad or ref.requires_grad):
+        raise NotImplementedError("lion_b200: the EMD backward kernel (training loss) is out of scope")
+    return earth_mover_distance_nograd(sample.cuda(), ref.cuda(), transpose=False)
+
+
+@torch.no_grad()
+def pairwise_EMD(sample_pcs, ref_pcs):
+    """[Ns,N,3], [Nr,M,3] -> [Ns,Nr] approximate-EMD matrix (each entry = emd_approx of the pair)."""
+    if not sample_pcs.is_cuda or not ref_pcs.is_cuda:
+        raise L.LionError("lion_b200 needs CUDA tensors; there is no CPU path")
+    s = sample_pcs.detach().to(torch.float32).contiguous()
+    r = ref_pcs.detach().to(torch.float32).contiguous()
+    assert s.dim() == 3 and r.dim() == 3 and s.shape[2] == 3 and r.shape[2] == 3
+    out = torch.empty(s.shape[0], r.shape[0], device=s.device)
+    with torch.cuda.device(s.device):
+        L.check(L.lib().lion_emd_pairwise(L.ptr(s), L.ptr(r), L.ptr(out), s.shape[0], r.shape[0], s.shape[1], r.shape[1],
+                                          L.stream()), "emd_pairwise")
+    return out / float(s.shape[1])
+
+
 def _pairwise_EMD_CD_(metric, sample_pcs, ref_pcs, batch_size, require_grad=True, accelerated_cd=True, verbose=True):
     """Same signature and return convention as the reference: (all_cd, all_emd), both the CD matrix
     when metric == 'CD' (reference :311-314 returns the same list twice)."""
-    if metric != 'CD':
-        raise NotImplementedError("lion_b200: only metric='CD' is provided (EMD: see the module docstring)")
-    cd = pairwise_CD(sample_pcs, ref_pcs)
-    return cd, cd
+    if metric == 'CD':
+        cd = pairwise_CD(sample_pcs, ref_pcs)
+        return cd, cd
+    if metric == 'EMD':
+        emd = pairwise_EMD(sample_pcs, ref_pcs)
+        return emd, emd
+    raise NotImplementedError(metric)

@@ -16,7 +16,11 @@ chamfer3D.cu}, JIT-loaded by dist_chamfer_3D.py:12-16 with default flags) is bui
 into oracle/_ref/chamfer_3D.so: ground truth for lion_chamfer_forward (distances bit-exact,
 indices exact).
 
-Run:  python oracle/build_ref.py          (no GPU needed; ~3 min)
+The approximate-EMD extension (third_party/PyTorchEMD/cuda/{emd.cpp,emd_kernel.cu}) is built into
+oracle/_ref/emd_ext.so with oracle/shim/ on the include path (it supplies the removed THC header the
+kernel source still includes): ground truth for lion_emd_approx.
+
+Run:  python oracle/build_ref.py          (no GPU needed; ~4 min)
 """
 import os
 import sys
@@ -80,6 +84,39 @@ def load_chamfer():
     return mod
 
 
+EMD_SRC = "/root/reference/third_party/PyTorchEMD/cuda"
+
+
+def build_emd(verbose=False):
+    """third_party/PyTorchEMD/backend.py:10-19 JIT-loads cuda/emd.cpp + cuda/emd_kernel.cu with -O3 -std=c++17;
+    the kernel source includes the long-removed <THC/THC.h>, which oracle/shim/ supplies (two macros)."""
+    so = os.path.join(OUT_DIR, "emd_ext.so")
+    if os.path.exists(so):
+        return so
+    if not os.path.isdir(EMD_SRC):
+        return None
+    os.makedirs(OUT_DIR, exist_ok=True)
+    os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0a")
+    from torch.utils.cpp_extension import load
+    shim = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
+    load(name="emd_ext", sources=[os.path.join(EMD_SRC, "emd.cpp"), os.path.join(EMD_SRC, "emd_kernel.cu")],
+         extra_cflags=["-O3", "-std=c++17"], extra_include_paths=[shim],
+         build_directory=OUT_DIR, verbose=verbose, is_python_module=False)
+    return so if os.path.exists(so) else None
+
+
+def load_emd():
+    import importlib.util
+    import torch  # noqa: F401
+    so = os.path.join(OUT_DIR, "emd_ext.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("emd_ext", so)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def load_ref():
     """Import oracle/_ref/_pvcnn_backend.so (needs a GPU to *run* its functions)."""
     import importlib.util
@@ -96,3 +133,4 @@ def load_ref():
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
     print(build_chamfer(verbose="-v" in sys.argv))
+    print(build_emd(verbose="-v" in sys.argv))

@@ -16,6 +16,11 @@ smaller, also across the kernel's 512-point chunks).
 Parity status: pinned on the GPU box against oracle/_ref/chamfer_3D.so (the reference's own
 extension built by oracle/build_ref.py) in tests/test_metrics_gpu.py; no golden vector exists
 in the reference for this path.
+
+  emd_approx        third_party/PyTorchEMD/cuda/emd_kernel.cu:23-170 (approxmatch) + :196-246 (matchcost),
+                    emd_nograd.py:9-45: float64 restatement (exact exp instead of __expf, so it agrees
+                    with the kernels to ~1e-4, not bit for bit); pinned on the GPU box against
+                    oracle/_ref/emd_ext.so = the reference's own kernels (built with oracle/shim/).
 """
 import numpy as np
 
@@ -52,4 +57,31 @@ def pairwise_cd(samples, refs):
             dl, _ = _nn(samples[i], refs[j])
             dr, _ = _nn(refs[j], samples[i])
             out[i, j] = dl.astype(np.float64).mean() + dr.astype(np.float64).mean()
+    return out
+
+
+def emd_approx(xyz1, xyz2):
+    """xyz1 [B,N,3], xyz2 [B,M,3] -> cost [B] (sum d^2 * match; divide by N for earth_mover_distance_nograd)."""
+    xyz1 = np.asarray(xyz1, np.float64)
+    xyz2 = np.asarray(xyz2, np.float64)
+    B, n, m = xyz1.shape[0], xyz1.shape[1], xyz2.shape[1]
+    out = np.zeros(B)
+    for b in range(B):
+        d2 = ((xyz2[b][None, :, :] - xyz1[b][:, None, :]) ** 2).sum(-1)          # [n, m]
+        multiL, multiR = (1.0, float(n // m)) if n >= m else (float(m // n), 1.0)
+        remainL = np.full(n, multiL)
+        remainR = np.full(m, multiR)
+        match = np.zeros((n, m))
+        for j in range(7, -3, -1):
+            level = -(4.0 ** j) if j != -2 else 0.0
+            e = np.exp(level * d2)
+            ratioL = remainL / (1e-9 + e @ remainR)
+            sumr = (e.T @ ratioL) * remainR
+            consumption = np.minimum(remainR / (sumr + 1e-9), 1.0)
+            ratioR = consumption * remainR
+            remainR = np.maximum(0.0, remainR - sumr)
+            w = e * ratioL[:, None] * ratioR[None, :]
+            match += w
+            remainL = np.maximum(0.0, remainL - w.sum(1))
+        out[b] = (d2 * match).sum()
     return out

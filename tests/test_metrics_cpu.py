@@ -28,3 +28,17 @@ def test_chamfer_oracle_tie_rule_lowest_index():
     c[0, 5, 0] = 1
     _, _, i1, _ = OM.chamfer_forward(q, c)
     assert (i1 == 1).all()
+
+
+def test_emd_oracle_properties():
+    """Identical clouds cost ~0; for a rigid shift t the optimal transport costs |t|^2 per point, the
+    approximate scheme (soft assignment annealed over ten levels) can only do worse, and the cost
+    grows with |t|."""
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((1, 128, 3)).astype(np.float32) * 0.3
+    assert OM.emd_approx(a, a)[0] / 128 < 1e-6
+    prev = 0.0
+    for t in (0.1, 0.5, 1.0):
+        c = OM.emd_approx(a, a + np.array([t, 0, 0], np.float32))[0] / 128
+        assert c >= t * t * 0.999 and c < 6 * t * t and c > prev
+        prev = c

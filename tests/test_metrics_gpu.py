@@ -62,4 +62,42 @@ def test_pairwise_cd_matrix():
     cd3, _ = _pairwise_EMD_CD_('CD', s2.cuda(), r2.cuda(), batch_size=8)
     assert_close(cd3, torch.from_numpy(OM.pairwise_cd(s2.numpy(), r2.numpy())), 1e-5, "ragged pairwise CD")
     with pytest.raises(NotImplementedError):
-        _pairwise_EMD_CD_('EMD', s.cuda(), r.cuda(), batch_size=3)
+        _pairwise_EMD_CD_('JSD', s.cuda(), r.cuda(), batch_size=3)
+
+
+def _ref_emd(mod, a, b):
+    match = mod.approxmatch_forward(a, b)
+    return mod.matchcost_forward(a, b, match)
+
+
+@pytest.mark.parametrize("B,N,M", [(3, 2048, 2048), (2, 512, 512), (2, 1024, 256), (2, 300, 1200), (1, 7, 5)])
+def test_emd_approx_matches_reference_kernels_and_oracle(B, N, M):
+    """lion_emd_approx (fused approxmatch + matchcost, no match matrix) against the reference's own
+    kernels (oracle/_ref/emd_ext.so) -- the annealing iterates follow the same arithmetic, only the final
+    sum is ordered differently: 2e-5 -- and against the float64 restatement (exact exp vs __expf: 2e-3)."""
+    from lion_b200.third_party.PyTorchEMD.emd_nograd import earth_mover_distance_nograd
+    a, b = gen(91, B, N, 3) * 0.4, gen(92, B, M, 3) * 0.4 + 0.1
+    cost = earth_mover_distance_nograd(a.cuda(), b.cuda(), transpose=False)
+    assert cost.shape == (B,) and torch.isfinite(cost).all()
+    assert torch.equal(cost, earth_mover_distance_nograd(a.cuda(), b.cuda(), transpose=False)), "EMD is not bit-reproducible"
+    assert_close(earth_mover_distance_nograd(a.transpose(1, 2).cuda(), b.transpose(1, 2).cuda()), cost, 0, "transpose=True path")
+    mod = build_ref.load_emd()
+    if mod is not None:
+        ref = _ref_emd(mod, a.cuda(), b.cuda()) / float(N)
+        assert_close(cost, ref, 2e-5, "EMD vs the reference kernels")
+    if N * M <= 1024 * 1024:
+        assert_close(cost, torch.from_numpy(OM.emd_approx(a.numpy(), b.numpy()) / N), 2e-3, "EMD vs float64 restatement")
+
+
+def test_reference_emd_extension_was_built():
+    assert build_ref.load_emd() is not None, "oracle/_ref/emd_ext.so missing: run python oracle/build_ref.py"
+
+
+def test_pairwise_emd_matrix():
+    from lion_b200.utils.evaluation_metrics_fast import _pairwise_EMD_CD_, emd_approx
+    s, r = gen(93, 3, 1024, 3) * 0.4, gen(94, 4, 1024, 3) * 0.5
+    emd, emd2 = _pairwise_EMD_CD_('EMD', s.cuda(), r.cuda(), batch_size=2, require_grad=False)
+    assert emd.shape == (3, 4) and emd2 is emd
+    for i in range(3):
+        row = emd_approx(s[i:i + 1].expand(4, -1, -1).contiguous().cuda(), r.cuda(), require_grad=False)
+        assert torch.equal(emd[i], row), "pairwise EMD differs from the per-pair op"

@@ -24,4 +24,4 @@ python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ben
 import json
 d=json.load(open('gpurun_out/bench_s2.json')); print('bench', d['value'], d['phases'], d['roofline']['achieved'])
 PY
-python tools/bench_metrics.py 32 405 2>&1 | tee gpurun_out/metrics_bench.jsonl
+
