@@ -8,7 +8,8 @@ host-side mirror of the reference's Python interface for that path:
     lion_b200.utils.diffusion_pvd               DiffusionDiscretized (DDPM + DDIM loops)
     lion_b200.models.lion                       LION (demo wrapper; diffusers-style scheduler restated)
     lion_b200.third_party.ChamferDistancePytorch.chamfer3D.dist_chamfer_3D   Chamfer NN (metrics)
-    lion_b200.utils.evaluation_metrics_fast     pairwise CD matrix (not aliased: the reference module holds more)
+    lion_b200.third_party.PyTorchEMD.emd_nograd / .emd                       approximate EMD (metrics)
+    lion_b200.utils.evaluation_metrics_fast     pairwise CD / EMD matrices (not aliased: the reference module holds more)
     lion_b200.trainers.train_2prior             generate_samples_vada_2prior
 
 `lion_b200.install()` registers these under the reference's own import paths (`models.*`,
@@ -24,6 +25,8 @@ _ALIASES = {
     "third_party.pvcnn.functional": "lion_b200.third_party.pvcnn.functional",
     "third_party.ChamferDistancePytorch.chamfer3D.dist_chamfer_3D":
         "lion_b200.third_party.ChamferDistancePytorch.chamfer3D.dist_chamfer_3D",
+    "third_party.PyTorchEMD.emd_nograd": "lion_b200.third_party.PyTorchEMD.emd_nograd",
+    "third_party.PyTorchEMD.emd": "lion_b200.third_party.PyTorchEMD.emd",
     "models.adagn": "lion_b200.models.adagn",
     "models.dense": "lion_b200.models.dense",
     "models.pvcnn2_ada": "lion_b200.models.pvcnn2_ada",
