@@ -9,6 +9,8 @@
 #include "common.cuh"
 #include "model.cuh"
 #include "../../include/lion_b200.h"
+#include <cooperative_groups.h>
+#include <cstdlib>
 
 namespace lion {
 
@@ -52,9 +54,17 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return u;
 }
+// FUSED: the K-slices of one output tile form a thread-block cluster (1, nsplit, 1); the partial sums
+// stay in shared memory and CTA r of the cluster reduces the r-th share of the tile's outputs over
+// distributed shared memory, in the same fixed order as k_gp_reduce, then applies the epilogue --
+// no `part` round trip through L2 and half the launches of a step.
+struct GpEpi {
+  const float* bias; float* out; int out_stride; const float* mul; int mul_stride; const float* res; int res_stride; int act;
+};
+template <bool FUSED>
 __global__ void __launch_bounds__(GP_WARPS * 32, 1)
 k_gp_partial(const float* __restrict__ W, const float* __restrict__ x, int x_stride, const float* __restrict__ add,
-             int add_stride, float* __restrict__ part, int B, int K, int O) {
+             int add_stride, float* __restrict__ part, int B, int K, int O, GpEpi epi) {
   pdl_prologue();
   extern __shared__ __align__(16) float s_mem[];
   float* s_w = s_mem;                          // [GP_OB][GP_PITCH]
@@ -136,15 +146,49 @@ k_gp_partial(const float* __restrict__ W, const float* __restrict__ x, int x_str
     }
   }
   // C fragment: c0,c1 -> (row g8, shapes 2*t4, 2*t4+1); c2,c3 -> (row g8+8, same shapes)
-  float* pout = part + (size_t)blockIdx.y * B * O;
+  if (!FUSED) {
+    float* pout = part + (size_t)blockIdx.y * B * O;
 #pragma unroll
-  for (int n = 0; n < 4; ++n) {
+    for (int n = 0; n < 4; ++n) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int o = o0 + wid * 16 + g8 + (i >= 2 ? 8 : 0);
-      int b = n * 8 + 2 * t4 + (i & 1);
-      if (b < B && o < O) pout[(size_t)b * O + o] = acc[n][i];
+      for (int i = 0; i < 4; ++i) {
+        int o = o0 + wid * 16 + g8 + (i >= 2 ? 8 : 0);
+        int b = n * 8 + 2 * t4 + (i & 1);
+        if (b < B && o < O) pout[(size_t)b * O + o] = acc[n][i];
+      }
     }
+  } else {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __syncthreads();                                   // every warp is done with s_w / s_x
+    float* s_part = s_mem;                             // [GP_BT][GP_OB]
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int ol = wid * 16 + g8 + (i >= 2 ? 8 : 0);
+        int b = n * 8 + 2 * t4 + (i & 1);
+        s_part[b * GP_OB + ol] = acc[n][i];
+      }
+    }
+    cluster.sync();                                    // all K-slices of this output tile are in shared memory
+    const int ns = (int)cluster.num_blocks(), r = (int)cluster.block_rank();
+    const int share = GP_OB / ns;                      // outputs reduced by this CTA
+    for (int e = tid; e < share * GP_BT; e += GP_WARPS * 32) {
+      const int b = e / share, ol = r * share + e % share;
+      const int o = o0 + ol;
+      float v = 0.0f;
+      for (int q = 0; q < ns; ++q) v += cluster.map_shared_rank(s_part, q)[b * GP_OB + ol];
+      if (b < B && o < O) {
+        v += epi.bias ? epi.bias[o] : 0.0f;
+        if (epi.act == 1) v = fmaxf(v, 0.0f);
+        else if (epi.act == 2) v = 1.0f / (1.0f + expf(-v));
+        if (epi.mul) v *= epi.mul[(size_t)b * epi.mul_stride + o];
+        if (epi.res) v += epi.res[(size_t)b * epi.res_stride + o];
+        epi.out[(size_t)b * epi.out_stride + o] = v;
+      }
+    }
+    cluster.sync();                                    // nobody exits while its shared memory is still being read
   }
 }
 
@@ -227,15 +271,34 @@ static int gp_linear(Ctx* c, const GPLin& l, const float* x, int xs, const float
   if (l.K % 4) { set_error("global prior: K=%d must be a multiple of 4", l.K); return LION_ERR_ARG; }
   int nsplit = cdiv(l.K, GP_KS);
   if (nsplit > GP_MAXSPLIT) { set_error("global prior: K=%d too large", l.K); return LION_ERR_ARG; }
-  size_t mk = c->mark();
-  float* part = c->alloc_n<float>((size_t)nsplit * B * l.O);
   const size_t smem = (size_t)(GP_OB + GP_BT) * GP_PITCH * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    LION_CHECK_CUDA(cudaFuncSetAttribute(k_gp_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LION_CHECK_CUDA(cudaFuncSetAttribute(k_gp_partial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LION_CHECK_CUDA(cudaFuncSetAttribute(k_gp_partial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  LION_LAUNCH(c, k_gp_partial, dim3(cdiv(l.O, GP_OB), nsplit), GP_WARPS * 32, smem, l.w, x, xs, add, as, part, B, l.K, l.O);
+  static int use_cluster = -1;
+  if (use_cluster < 0) { const char* e = getenv("LION_GP_CLUSTER"); use_cluster = e ? atoi(e) : 1; }
+  GpEpi epi{l.b, out, os, mul, ms, res, rs, act};
+  const bool pow2 = (nsplit & (nsplit - 1)) == 0;
+  if (use_cluster && pow2 && nsplit <= 8) {
+    // split-K slices as one cluster, reduction + epilogue over distributed shared memory: ONE launch per layer
+    if (!c->dry) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cdiv(l.O, GP_OB), nsplit); cfg.blockDim = dim3(GP_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = nsplit; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      LION_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gp_partial<true>, l.w, x, xs, add, as, (float*)nullptr, B, l.K, l.O, epi));
+      c->launches++;
+    }
+    return 0;
+  }
+  size_t mk = c->mark();
+  float* part = c->alloc_n<float>((size_t)nsplit * B * l.O);
+  LION_LAUNCH(c, k_gp_partial<false>, dim3(cdiv(l.O, GP_OB), nsplit), GP_WARPS * 32, smem, l.w, x, xs, add, as, part, B, l.K, l.O, epi);
   LION_LAUNCH(c, k_gp_reduce, cdiv(B * l.O, 256), 256, 0, part, nsplit, l.b, out, os, mul, ms, res, rs, B, l.O, act);
   c->release(mk);     // stream order makes reuse by the next layer safe
   return 0;
