@@ -292,14 +292,21 @@ static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* o
   return check_launch(f.c, "conv");
 }
 
-struct Affine { float* scale; float* shift; };
+// AdaGN (+SE) folded into y = scale*x + shift.  Without an SE gate no kernel runs here: the consumer
+// derives its (scale, shift) from the statistics itself (AffSrc / aff_block_load); with the gate
+// (which needs all channels of the shape) k_affine_prep materialises the two arrays.
 static int run_affine(Fwd& f, const AdaGNW& g, const double* ssum, const double* ssq, int stat_stride, double count,
-                      const float* se1, const float* se2, Affine& a) {
-  a.scale = f.c->alloc_n<float>((size_t)f.B * g.C);
-  a.shift = f.c->alloc_n<float>((size_t)f.B * g.C);
+                      const float* se1, const float* se2, AffSrc& a) {
+  a = AffSrc{nullptr, nullptr, ssum, ssq, stat_stride, g.gamma, g.beta, f.aff + g.style_off, f.m->style_total, count};
+  static int lazy = -1;
+  if (lazy < 0) { const char* e = getenv("LION_AFFINE_PREP"); lazy = (e && atoi(e) != 0) ? 0 : 1; }   // LION_AFFINE_PREP=1: always precompute
+  if (!se1 && lazy) return 0;
+  float* scale = f.c->alloc_n<float>((size_t)f.B * g.C);
+  float* shift = f.c->alloc_n<float>((size_t)f.B * g.C);
   size_t smem = se1 ? (g.C + g.C / 8) * sizeof(float) : 0;
   LION_LAUNCH(f.c, k_affine_prep, f.B, g.C, smem, ssum, ssq, stat_stride, g.gamma, g.beta, f.aff + g.style_off,
-              f.m->style_total, se1, se2, a.scale, a.shift, g.C, count);
+              f.m->style_total, se1, se2, scale, shift, g.C, count);
+  a.scale = scale; a.shift = shift;
   return check_launch(f.c, "affine_prep");
 }
 static int stat_pool_begin(Fwd& f, size_t bytes) {
@@ -333,19 +340,19 @@ static int shared_mlp_fwd(Fwd& f, const SharedMLPBlk& m, PF in, int pool, float4
     double *ssum, *ssq;
     LION_TRY(alloc_stats(f, w.cout_pad, &ssum, &ssq));
     LION_TRY(run_conv(f, w, cur.p, cur.G, raw.p, Gout, ssum, ssq, geom_rows(cur.R)));
-    Affine a;
+    AffSrc a;
     LION_TRY(run_affine(f, m.gn[i], ssum, ssq, w.cout_pad, (double)cur.R, nullptr, nullptr, a));
     bool last = (i == n - 1);
     if (last && pool > 1) {
       if (pool != 32 || cur.R % 32) { set_error("shared_mlp: unsupported pooling %d", pool); return LION_ERR_ARG; }
       int Ro = cur.R / 32;
-      LION_LAUNCH(f.c, k_act_rows_pool32, dim3(cdiv(Ro, 8 * 4), Gout, f.B), 256, 0, raw.p, dst, a.scale, a.shift, Gout, w.cout, Ro, Gd, g_off);
+      LION_LAUNCH(f.c, k_act_rows_pool32, dim3(cdiv(Ro, 8 * 4), Gout, f.B), 256, 0, raw.p, dst, a, Gout, w.cout, Ro, Gd, g_off);
     } else {
       PF nxt;
       float4* o; int gd, go;
       if (last) { o = dst; gd = Gd; go = g_off; }
       else { nxt = alloc_pf(f, Gout, cur.R); o = nxt.p; gd = Gout; go = 0; }
-      LION_LAUNCH(f.c, k_act_rows<1>, dim3(cdiv(cur.R, 256), Gout, f.B), 256, 0, raw.p, o, a.scale, a.shift, Gout, w.cout, cur.R, gd, go, last ? 0 : 1);
+      LION_LAUNCH(f.c, k_act_rows<1>, dim3(cdiv(cur.R, 256), Gout, f.B), 256, 0, raw.p, o, a, Gout, w.cout, cur.R, gd, go, last ? 0 : 1);
       cur = nxt;
     }
     LION_TRY(check_launch(f.c, "shared_mlp act"));
@@ -406,17 +413,17 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   geo1.occ = vp->occ; geo1.occ_stride = vp->occ_stride;
   LION_TRY(run_conv(f, p.c1, g_in, Gin, raw1, Gout, s1, q1, geo1));
   LION_LAUNCH(f.c, k_unscatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, vp->ppos, g_in, Gin, N, P);
-  Affine a1;
+  AffSrc a1;
   double V = (double)r * r * r;
   LION_TRY(run_affine(f, p.g1, s1, q1, p.c1.cout_pad, V, nullptr, nullptr, a1));
   float4* act1 = alloc_vg(f, Gout, r);
-  LION_LAUNCH(f.c, k_act_grid, dim3(cdiv(P, 256 * ACT_U), Gout, f.B), 256, 0, raw1, act1, a1.scale, a1.shift, Gout, p.cout, rp, P);
+  LION_LAUNCH(f.c, k_act_grid, dim3(cdiv(P, 256 * ACT_U), Gout, f.B), 256, 0, raw1, act1, a1, Gout, p.cout, rp, P);
   // conv2 -> (stats) -> AdaGN + SE folded into one affine
   float4* raw2 = alloc_vg(f, Gout, r);
   double *s2, *q2;
   LION_TRY(alloc_stats(f, p.c2.cout_pad, &s2, &q2));
   LION_TRY(run_conv(f, p.c2, act1, Gout, raw2, Gout, s2, q2, geo));
-  Affine a2;
+  AffSrc a2;
   LION_TRY(run_affine(f, p.g2, s2, q2, p.c2.cout_pad, V, p.se1, p.se2, a2));
   // point branch: conv1x1 -> stats -> affine (activation applied inside the devox kernel)
   const ConvW& pw = p.point.conv[0];
@@ -424,13 +431,13 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   double *sp, *qp;
   LION_TRY(alloc_stats(f, pw.cout_pad, &sp, &qp));
   LION_TRY(run_conv(f, pw, feat.p, feat.G, rawp.p, Gout, sp, qp, geom_rows(N)));
-  Affine ap;
+  AffSrc ap;
   LION_TRY(run_affine(f, p.point.gn[0], sp, qp, pw.cout_pad, (double)N, nullptr, nullptr, ap));
   // voxel -> point gather (+ point branch)
   if (p.has_attn) {
     PF fused = alloc_pf(f, Gout, N);
-    LION_LAUNCH(f.c, k_devox_fuse, dim3(cdiv(N, 128), Gout, f.B), 128, 0, raw2, vp->nc, a2.scale, a2.shift, rawp.p, ap.scale,
-                ap.shift, fused.p, Gout, p.cout, N, r, P, Gout, 0);
+    LION_LAUNCH(f.c, k_devox_fuse, dim3(cdiv(N, 128), Gout, f.B), 128, 0, raw2, vp->nc, a2.scale, a2.shift, rawp.p, ap,
+                fused.p, Gout, p.cout, N, r, P, Gout, 0);
     LION_TRY(check_launch(f.c, "pvconv"));
     if (Gd != Gout || g_off != 0) {
       PF t = alloc_pf(f, Gout, N);
@@ -440,8 +447,8 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
       LION_TRY(attn_fwd(f, p.attn, fused, dst, Gd, g_off));
     }
   } else {
-    LION_LAUNCH(f.c, k_devox_fuse, dim3(cdiv(N, 128), Gout, f.B), 128, 0, raw2, vp->nc, a2.scale, a2.shift, rawp.p, ap.scale,
-                ap.shift, dst, Gout, p.cout, N, r, P, Gd, g_off);
+    LION_LAUNCH(f.c, k_devox_fuse, dim3(cdiv(N, 128), Gout, f.B), 128, 0, raw2, vp->nc, a2.scale, a2.shift, rawp.p, ap,
+                dst, Gout, p.cout, N, r, P, Gd, g_off);
   }
   LION_TRY(check_launch(f.c, "pvconv"));
   f.c->release(mk);   // grids are dead once the output PF is written (stream order keeps this safe)
@@ -1023,10 +1030,10 @@ extern "C" int lion_adagn_fwd(LionModel* h, const float* x, const float* style, 
     double *ssum, *ssq;
     LION_TRY(alloc_stats(f, g.C, &ssum, &ssq));
     LION_LAUNCH(f.c, k_row_stats, dim3(cdiv(R, 1024) > 64 ? 64 : cdiv(R, 1024), xi.G, B), 256, 0, xi.p, ssum, ssq, xi.G, R, g.C);
-    Affine a;
+    AffSrc a;
     LION_TRY(run_affine(f, g, ssum, ssq, g.C, (double)R, nullptr, nullptr, a));
     PF o = alloc_pf(f, xi.G, R);
-    LION_LAUNCH(f.c, k_act_rows<1>, dim3(cdiv(R, 256), xi.G, B), 256, 0, xi.p, o.p, a.scale, a.shift, xi.G, g.C, R, xi.G, 0, 2);
+    LION_LAUNCH(f.c, k_act_rows<1>, dim3(cdiv(R, 256), xi.G, B), 256, 0, xi.p, o.p, a, xi.G, g.C, R, xi.G, 0, 2);
     from_pf(f, o, out, g.C);
     return check_launch(f.c, "lion_adagn_fwd");
   });

@@ -371,16 +371,54 @@ __global__ void k_time_sinusoid(const float* __restrict__ t, const float* __rest
 // ------------------------------------------------------------------------------------
 // elementwise passes
 // ------------------------------------------------------------------------------------
+// Where a consumer gets the folded AdaGN affine of its (b, 4-channel group): either the arrays
+// k_affine_prep wrote (scale != null; the SE-gated case), or -- saving that launch on the critical
+// path -- straight from the GroupNorm statistics the producing convolution accumulated: the block
+// computes its four (scale, shift) pairs once (same formulas as k_affine_prep, group sums in channel
+// order) and shares them through shared memory.  Must be called by ALL threads of the block.
+struct AffSrc {
+  const float* scale; const float* shift;
+  const double* ssum; const double* ssq; int stat_stride;
+  const float* gamma; const float* beta; const float* fb; int fb_stride;
+  double count;
+};
+__device__ __forceinline__ void aff_block_load(const AffSrc& a, int b, int g, int C, float4& s, float4& t) {
+  if (a.scale) {
+    s = *reinterpret_cast<const float4*>(a.scale + (size_t)b * C + g * 4);
+    t = *reinterpret_cast<const float4*>(a.shift + (size_t)b * C + g * 4);
+    return;
+  }
+  __shared__ float s_aff[8];
+  if (threadIdx.x < 4) {
+    const int c = g * 4 + threadIdx.x, cpg = C / 8, c0 = (c / cpg) * cpg;
+    const double* ps = a.ssum + (size_t)b * a.stat_stride + c0;
+    const double* pq = a.ssq + (size_t)b * a.stat_stride + c0;
+    double gs = 0.0, gq = 0.0;
+    for (int k = 0; k < cpg; ++k) { gs += ps[k]; gq += pq[k]; }
+    const double n = a.count * cpg;
+    const double mean = gs / n;
+    double var = gq / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float f = a.fb[(size_t)b * a.fb_stride + c], bb = a.fb[(size_t)b * a.fb_stride + C + c];
+    const float ga = a.gamma[c], be = a.beta[c];
+    s_aff[threadIdx.x] = rstd * ga * f;
+    s_aff[4 + threadIdx.x] = (be - (float)mean * rstd * ga) * f + bb;
+  }
+  __syncthreads();
+  s = make_float4(s_aff[0], s_aff[1], s_aff[2], s_aff[3]);
+  t = make_float4(s_aff[4], s_aff[5], s_aff[6], s_aff[7]);
+}
+
 // VG: y = swish(scale*x + shift) on interior voxels, 0 on every halo position (incl. x planes).
 // ACT_U positions per thread, loads issued before any use: a 16-byte access per thread leaves too
 // few bytes in flight per SM to cover HBM latency (4.3 TB/s measured with one access per thread).
 constexpr int ACT_U = 4;
-__global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
-                           const float* __restrict__ shift, int G, int C, int rp, int P) {
+__global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ out, AffSrc aff, int G, int C, int rp, int P) {
   pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
-  const float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
-  const float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
+  float4 s, t;
+  aff_block_load(aff, b, g, C, s, t);
   const float4* src = in + ((size_t)b * G + g) * P;
   float4* dst = out + ((size_t)b * G + g) * P;
   const int p0 = blockIdx.x * (blockDim.x * ACT_U) + threadIdx.x;
@@ -408,14 +446,14 @@ __global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ o
 // PF: y = swish(scale*x + shift); written at group offset g_off of a destination with Gd groups.
 // POOL > 1: max over POOL consecutive rows (neighbours of one centre) after the activation.
 template <int POOL>
-__global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
-                           const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off, int flags) {
+__global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ out, AffSrc aff, int G, int C, int R_out, int Gd,
+                           int g_off, int flags) {
   pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 s, t;
+  aff_block_load(aff, b, g, C, s, t);
   if (i >= R_out) return;
-  float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
-  float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
   const float4* src = in + ((size_t)b * G + g) * (size_t)R_out * POOL + (size_t)i * POOL;
   float4 r = f4_affine(src[0], s, t);
   if (!(flags & 2)) r = f4_swish(r);
@@ -429,13 +467,13 @@ __global__ void k_act_rows(const float4* __restrict__ in, float4* __restrict__ o
 // one warp per output row, lane k reads neighbour k (one coalesced 512-byte access per warp instead
 // of 32 strided ones per thread), butterfly max.  The result is the same set maximum as
 // k_act_rows<32>, bit for bit.
-__global__ void k_act_rows_pool32(const float4* __restrict__ in, float4* __restrict__ out, const float* __restrict__ scale,
-                                  const float* __restrict__ shift, int G, int C, int R_out, int Gd, int g_off) {
+__global__ void k_act_rows_pool32(const float4* __restrict__ in, float4* __restrict__ out, AffSrc aff, int G, int C, int R_out,
+                                  int Gd, int g_off) {
   pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const float4 s = *reinterpret_cast<const float4*>(scale + (size_t)b * C + g * 4);
-  const float4 t = *reinterpret_cast<const float4*>(shift + (size_t)b * C + g * 4);
+  float4 s, t;
+  aff_block_load(aff, b, g, C, s, t);
   const float4* src = in + ((size_t)b * G + g) * (size_t)R_out * 32;
   constexpr int ROWS = 4;                                  // rows per warp, loads issued together
   const int i0 = (blockIdx.x * wpb + (threadIdx.x >> 5)) * ROWS;
@@ -534,12 +572,13 @@ __global__ void k_fill_groups(const float* __restrict__ v, int v_stride, float4*
 // + the point branch swish(AdaGN(conv1x1)) (PVConv.forward, models/pvcnn2_ada.py:267-277)
 // ------------------------------------------------------------------------------------
 __global__ void k_devox_fuse(const float4* __restrict__ raw, const float4* __restrict__ nc, const float* __restrict__ scale,
-                             const float* __restrict__ shift, const float4* __restrict__ rawp,
-                             const float* __restrict__ scale_p, const float* __restrict__ shift_p,
+                             const float* __restrict__ shift, const float4* __restrict__ rawp, AffSrc aff_p,
                              float4* __restrict__ out, int G, int C, int N, int r, int P, int Gd, int g_off) {
   pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 sp = make_float4(0.f, 0.f, 0.f, 0.f), tp = sp;
+  if (rawp) aff_block_load(aff_p, b, g, C, sp, tp);
   if (i >= N) return;
   float4 c = nc[(size_t)b * N + i];
   int rp = r + 2;
@@ -556,11 +595,7 @@ __global__ void k_devox_fuse(const float4* __restrict__ raw, const float4* __res
   float4 acc = f4_scale(f4_affine(__ldg(rg + idx[0]), s, t), w[0]);
 #pragma unroll
   for (int k = 1; k < 8; ++k) acc = f4_fma(f4_affine(__ldg(rg + idx[k]), s, t), w[k], acc);
-  if (rawp) {
-    float4 sp = *reinterpret_cast<const float4*>(scale_p + (size_t)b * C + g * 4);
-    float4 tp = *reinterpret_cast<const float4*>(shift_p + (size_t)b * C + g * 4);
-    acc = f4_add(acc, f4_swish(f4_affine(rawp[((size_t)b * G + g) * N + i], sp, tp)));
-  }
+  if (rawp) acc = f4_add(acc, f4_swish(f4_affine(rawp[((size_t)b * G + g) * N + i], sp, tp)));
   out[((size_t)b * Gd + g_off + g) * N + i] = acc;
 }
 
