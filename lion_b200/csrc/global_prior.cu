@@ -54,7 +54,8 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return u;
 }
-// FUSED: the K-slices of one output tile form a thread-block cluster (1, nsplit, 1); the partial sums
+// FUSED (LION_GP_CLUSTER=1; measured slower than the two-kernel form, see gp_linear): the K-slices of one
+// output tile form a thread-block cluster (1, nsplit, 1); the partial sums
 // stay in shared memory and CTA r of the cluster reduces the r-th share of the tile's outputs over
 // distributed shared memory, in the same fixed order as k_gp_reduce, then applies the epilogue --
 // no `part` round trip through L2 and half the launches of a step.
@@ -279,7 +280,9 @@ static int gp_linear(Ctx* c, const GPLin& l, const float* x, int xs, const float
     attr_set = true;
   }
   static int use_cluster = -1;
-  if (use_cluster < 0) { const char* e = getenv("LION_GP_CLUSTER"); use_cluster = e ? atoi(e) : 1; }
+  // measured on B200 (graph-replayed 1000-step loop, B=32): 0.63-0.75 s with clusters vs 0.39 s with the two-kernel
+  // form -- 16 clusters of 8 CTAs with 150 KB of shared memory each do not co-schedule well -- so OFF by default
+  if (use_cluster < 0) { const char* e = getenv("LION_GP_CLUSTER"); use_cluster = e ? atoi(e) : 0; }
   GpEpi epi{l.b, out, os, mul, ms, res, rs, act};
   const bool pow2 = (nsplit & (nsplit - 1)) == 0;
   if (use_cluster && pow2 && nsplit <= 8) {
