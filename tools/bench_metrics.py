@@ -7,7 +7,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from lion_b200.utils.evaluation_metrics_fast import pairwise_CD, distChamferCUDAnograd
+from lion_b200.utils.evaluation_metrics_fast import pairwise_CD, pairwise_EMD, distChamferCUDAnograd
 
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 nr = int(sys.argv[2]) if len(sys.argv) > 2 else 405
@@ -43,3 +43,8 @@ for name, fn in (("fused lion_chamfer_pairwise", lambda: pairwise_CD(s, r)), ("d
     print(json.dumps({"what": name, "n_sample": ns, "n_ref": nr, "points": N, "ms": round(ms, 3),
                       "cloud_pairs_per_s": round(ns * nr / (ms * 1e-3)), "gflops_8_per_point_pair": round(8 * pair_evals / (ms * 1e-3) / 1e9)}))
 assert torch.allclose(pairwise_CD(s, r), composed(), rtol=1e-5, atol=0)
+# approximate EMD: 30 exp-weighted N x M passes per pair (MUFU-bound); a smaller block of the matrix
+ne = max(1, ns // 8)
+ms = timed(lambda: pairwise_EMD(s[:ne], r), iters=1)
+print(json.dumps({"what": "fused lion_emd_pairwise", "n_sample": ne, "n_ref": nr, "points": N, "ms": round(ms, 3),
+                  "cloud_pairs_per_s": round(ne * nr / (ms * 1e-3)), "gexp_per_s": round(30.0 * ne * nr * N * N / (ms * 1e-3) / 1e9)}))
