@@ -192,3 +192,31 @@ def model_for(module, kind, desc, params):
             m.refresh()
             m.versions = vers
     return m
+
+
+class capture_graph:
+    """`with capture_graph() as g: ...; g.replay()` -- CUDA-graph capture of the enclosed launches on a
+    side stream, like `torch.cuda.graph`, minus its `gc.collect()` + `torch.cuda.empty_cache()` +
+    device-wide synchronize on entry: with two captures per sampling pass those cost more than the
+    capture itself (and empty_cache makes the next pass cudaMalloc its gigabyte of history again)."""
+
+    def __init__(self):
+        self.graph = torch.cuda.CUDAGraph()
+        self.stream = torch.cuda.Stream()
+
+    def __enter__(self):
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self._ctx = torch.cuda.stream(self.stream)
+        self._ctx.__enter__()
+        self.graph.capture_begin()
+        return self.graph
+
+    def __exit__(self, et, ev, tb):
+        try:
+            if et is None:
+                self.graph.capture_end()
+        finally:
+            self._ctx.__exit__(et, ev, tb)
+        if et is None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        return False

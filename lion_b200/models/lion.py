@@ -73,9 +73,7 @@ class LION(object):
             per_step = L.last_launches(dev) + 2
             graph = None
             if self.use_cuda_graph and getattr(prior, 'lion_graph_safe', True) and T > 3:
-                graph = torch.cuda.CUDAGraph()
-                torch.cuda.synchronize(dev)
-                with torch.cuda.graph(graph):
+                with L.capture_graph() as graph:
                     body(True)
             for t in reversed(range(1, T - 1)):          # t = T-2 .. 1
                 if graph is not None:

@@ -135,11 +135,9 @@ class DiffusionDiscretized(object):
             launches += per_step
             graph = None
             if graph_ok:
-                graph = torch.cuda.CUDAGraph()
                 if given_noise is not None:
                     draw_noise(T - 2)
-                torch.cuda.synchronize(dev)
-                with torch.cuda.graph(graph):
+                with L.capture_graph() as graph:
                     body(given_noise is None)
             for t in reversed(range(0, T - 1)):
                 if t % 500 == 0:
@@ -235,9 +233,7 @@ class DiffusionDiscretized(object):
             launches += per_step
             graph = None
             if self.use_cuda_graph and getattr(model, 'lion_graph_safe', True) and S > 2:
-                graph = torch.cuda.CUDAGraph()
-                torch.cuda.synchronize(dev)
-                with torch.cuda.graph(graph):
+                with L.capture_graph() as graph:
                     body()
             for _ in range(1, S):
                 if graph is not None:
