@@ -1,0 +1,72 @@
+"""Round-2 groundwork (CPU only): the algebra of *tap stacking along N* for the tensor-core
+convolution.  A numpy model of the implicit GEMM on the zero-haloed packed
+grid shows that stacking the S weight taps (dy, dz=0..S-1) of one (dx, dy) into ONE B operand of
+N = S*Cout columns, multiplying it with the single A view shifted by off(dy, dz=0), and folding the
+column blocks back with a row shift  out[q] = sum_c D_c[q + c]  reproduces the 3x3x3 convolution,
+provided row tiles advance by 128 - (S-1) rows (the last S-1 rows of a tile are incomplete and are
+recomputed as the first rows of the next tile)."""
+import numpy as np
+import pytest
+
+
+def packed_grid(x):                    # x [C, r, r, r] -> rows [(r+2)^3, C] with a zero halo
+    C, r = x.shape[0], x.shape[1]
+    g = np.zeros((r + 2, r + 2, r + 2, C), np.float64)
+    g[1:-1, 1:-1, 1:-1] = np.transpose(x, (1, 2, 3, 0))
+    return g.reshape(-1, C)
+
+
+def conv_reference(x, w):              # direct 3x3x3, padding 1: x [C,r,r,r], w [O,C,3,3,3] -> [O,r,r,r]
+    C, r = x.shape[0], x.shape[1]
+    xp = np.zeros((C, r + 2, r + 2, r + 2))
+    xp[:, 1:-1, 1:-1, 1:-1] = x
+    out = np.zeros((w.shape[0], r, r, r))
+    for dx in range(3):
+        for dy in range(3):
+            for dz in range(3):
+                out += np.einsum('oc,cxyz->oxyz', w[:, :, dx, dy, dz], xp[:, dx:dx + r, dy:dy + r, dz:dz + r])
+    return out
+
+
+@pytest.mark.parametrize("S", [2, 3])
+@pytest.mark.parametrize("r,C,O", [(6, 8, 4), (9, 4, 8)])
+def test_stacked_taps_reproduce_the_convolution(S, r, C, O):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((C, r, r, r))
+    w = rng.standard_normal((O, C, 3, 3, 3))
+    rows = packed_grid(x)
+    rp = r + 2
+    P = rp ** 3
+    guard = 128 + rp * rp + rp + 8            # (the kernel reads up to one tile past p_end: masked rows)
+    buf = np.zeros((P + 2 * guard, C))
+    buf[guard:guard + P] = rows                                   # guard rows like alloc_vg()
+    off = lambda dx, dy, dz: (dx - 1) * rp * rp + (dy - 1) * rp + (dz - 1)
+    p_begin, p_end = rp * rp, (rp - 1) * rp * rp                  # geom_grid(): interior x planes
+    M, pitch = 128, 128 - (S - 1)
+    out_rows = np.zeros((P, O))
+    ntile = -(-(p_end - p_begin) // pitch)
+    for t in range(ntile):
+        p0 = p_begin + t * pitch
+        D = np.zeros((M, 3 * O))                                  # accumulator: column block c <-> tap dz = c
+        for dx in range(3):
+            for dy in range(3):
+                # stacked MMA over dz = 0..S-1: ONE A view, shifted by the offset of the first tap of the stack
+                a = buf[guard + p0 + off(dx, dy, 0): guard + p0 + off(dx, dy, 0) + M]
+                for c in range(S):
+                    D[:, c * O:(c + 1) * O] += a @ w[:, :, dx, dy, c].T
+                # taps that did not fit the stack (S = 2: dz = 2) run as single MMAs on block 0's alignment
+                for dz in range(S, 3):
+                    a1 = buf[guard + p0 + off(dx, dy, dz): guard + p0 + off(dx, dy, dz) + M]
+                    D[:, 0:O] += a1 @ w[:, :, dx, dy, dz].T
+        # epilogue: out[q] = D_0[q] + D_1[q+1] (+ D_2[q+2]); lanes >= pitch are incomplete -> next tile
+        for lane in range(pitch):
+            q = p0 + lane
+            if q >= p_end:
+                break
+            v = D[lane, 0:O].copy()
+            for c in range(1, S):
+                v += D[lane + c, c * O:(c + 1) * O]
+            out_rows[q] = v
+    got = out_rows.reshape(rp, rp, rp, O)[1:-1, 1:-1, 1:-1]
+    ref = np.transpose(conv_reference(x, w), (1, 2, 3, 0))
+    assert np.allclose(got, ref, rtol=1e-10, atol=1e-10)
