@@ -366,7 +366,7 @@ def main():
         pass
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
         cpu_reference_sample(1, 1)                       # warm-up (oneDNN primitive creation)
         v, detail = cpu_reference_sample(2, 2)
         cpu = {"value": v, "unit": "shapes/s", "cores": cpu_threads(), "kind": "port", "sample": CPU_SAMPLE % (2, 2), "detail": detail}
