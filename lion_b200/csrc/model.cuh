@@ -14,6 +14,8 @@ struct ConvTcW {
   int ck = 0;        // input channels per pipeline chunk (8, 16 or 32)
   int nchunk = 0;
   int n = 0;         // UMMA N (= padded output channels)
+  float* ws = nullptr;   // experimental tap-stacked packing (LION_TC_STACK=1), else null
+  int stack = 0;         // taps stacked along N (2 or 3)
 };
 
 struct Cursor {
