@@ -19,6 +19,10 @@ Printed JSON line (rank 0): the base contract plus
   cpu_baseline  the CPU oracle (oracle/) on the host cores, bounded sample, extrapolated
   e2e           the same pass with all noise supplied from pinned HOST memory (H2D inside the
                 timed region) and the point clouds copied back to pinned host memory
+  gpu_baseline  (N=1, informational) a GPU port of the reference's EAGER path -- oracle/net.py on CUDA
+                tensors (cuDNN/cuBLAS through torch, TF32 convs) + the reference's own pvcnn kernels from
+                oracle/_ref -- on a bounded sample, run in a child process (`--impl reference-gpu`).  The
+                reference's Python modules themselves cannot travel to the GPU box.
 --impl reference times the reference's own CPU implementation of the path (the oracle port,
 restated from the reference and pinned to its goldens) on all host threads.
 """
@@ -43,11 +47,12 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=32, help="shapes per GPU")
     ap.add_argument("--ddpm-steps", type=int, default=T_STEPS, help="(debug) DDPM steps; the metric is defined at 1000")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -161,6 +166,69 @@ CPU_SAMPLE = ("%d PVCNN2Prior + %d global-prior denoising step(s) at B=1 on the 
               "path), decoder costed as one PVCNN2Prior step, extrapolated to 1000 + 1000 + 1 evaluations")
 
 
+def run_gpu_reference(args):
+    """--impl reference-gpu (informational, not part of the driver's contract): a GPU port of the
+    reference's eager PyTorch path -- oracle/net.py on CUDA tensors (cuDNN / cuBLAS through torch, TF32
+    convolutions and cudnn.benchmark as the reference runs them, utils/utils.py:472) with the reference's
+    OWN point kernels (oracle/_ref/_pvcnn_backend.so).  The reference's Python modules themselves cannot
+    travel to the GPU box.  Bounded sample: a few denoising steps of both priors at batch B, timed with
+    CUDA events after a warm-up step, extrapolated to 1000 + 1000 + 1 network evaluations."""
+    import torch
+    from oracle import diffusion as OD
+    from oracle import net as ON
+    from oracle import ref_cuda_ops
+    from tests.synth import synth_state_dict
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda", 0)
+    torch.backends.cudnn.benchmark = True
+    ON.set_point_ops(ref_cuda_ops)
+    B = args.batch
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "keys.json")))
+    sd_l = {k: v.to(dev) for k, v in synth_state_dict(keys["prior"], 11).items()}
+    sd_g = {k: v.to(dev) for k, v in synth_state_dict(keys["global"], 14).items()}
+    spec = ON.prior_spec()
+    sched = OD.make_schedule(T_STEPS, 1e-4, 0.02)
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(B, 8192, 1, 1, device=dev, generator=g)
+    xg = torch.randn(B, 128, 1, 1, device=dev, generator=g)
+    style = torch.randn(B, 128, device=dev, generator=g)
+    n_steps = 3
+
+    def local_step(x, t):
+        tt = torch.ones(B, device=dev) * (t + 1)
+        eps = ON.prior_forward(sd_l, spec, x, tt, style)
+        return OD.ddpm_step(sched, x, eps, t, torch.randn(x.shape, device=dev, generator=g))
+
+    def global_step(xg, t):
+        tt = torch.ones(B, device=dev) * (t + 1)
+        eps = ON.global_prior_forward(sd_g, xg, tt)
+        return OD.ddpm_step(sched, xg, eps, t, torch.randn(xg.shape, device=dev, generator=g))
+
+    def timed(step, x0):
+        with torch.no_grad():
+            x1 = step(x0, T_STEPS - 1)                      # warm-up: cuDNN algorithm search, allocator
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for k in range(n_steps):
+                x1 = step(x1, T_STEPS - 2 - k)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            assert torch.isfinite(x1).all()
+        return max(e0.elapsed_time(e1) / 1000.0, time.perf_counter() - t0) / n_steps
+
+    tl = timed(local_step, x)
+    tg = timed(global_step, xg)
+    total = T_STEPS * (tl + tg) + tl                        # seconds per batch of B shapes
+    print(json.dumps({"impl": "reference-gpu", "metric": "shapes/sec (1000-step DDPM, 2048 latent pts, B=32)", "value": B / total,
+                      "unit": "shapes/s", "n_gpus": 1, "kind": "port: oracle/net.py on CUDA (torch cuDNN/cuBLAS, TF32 convs, eager) + "
+                      "the reference's own pvcnn kernels (oracle/_ref)",
+                      "sample": "%d + %d denoising steps at batch %d after one warm-up step, extrapolated to 1000 + 1000 + 1 "
+                                "network evaluations" % (n_steps, n_steps, B),
+                      "detail": {"s_per_local_step": tl, "s_per_global_step": tg}}))
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -186,6 +254,9 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.impl == "reference-gpu":
+        run_gpu_reference(args)
+        return
     if args.impl == "reference":
         return run_reference_arm(args)
     import torch
@@ -371,6 +442,19 @@ def main():
         v, detail = cpu_reference_sample(2, 2)
         cpu = {"value": v, "unit": "shapes/s", "cores": cpu_threads(), "kind": "port", "sample": CPU_SAMPLE % (2, 2), "detail": detail}
 
+    # GPU-side reference port (informational): oracle/net.py on CUDA + the reference's own point kernels, in a
+    # child process (the reference kernels exit() on a launch error; nothing there may take this line down)
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_baseline:
+        try:
+            import subprocess
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--batch", str(B)],
+                               capture_output=True, text=True, timeout=300)
+            rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            gpu_ref = json.loads(rows[-1]) if rows else {"unavailable": (r.stderr or "no output")[-300:]}
+        except Exception as e:      # noqa: BLE001
+            gpu_ref = {"unavailable": repr(e)[:300]}
+
     line = {"metric": "shapes/sec (1000-step DDPM, 2048 latent pts, B=32)", "value": value, "unit": "shapes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage/accumulate)",
@@ -382,7 +466,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch,
             "ms_per_denoise_step_pair": ms / args.steps / T,
             "tensor_roofline_frac_whole_job": (value * GFLOP_PER_SHAPE / 1e3 / world / (bf16_peak / 2.0)) if T == T_STEPS else None,
-            "phases": phases, "roofline": roofline, "cpu_baseline": cpu}
+            "phases": phases, "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_ref}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

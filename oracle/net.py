@@ -23,6 +23,13 @@ import torch.nn.functional as TF
 
 from . import point_ops as P
 
+
+def set_point_ops(ops):
+    """Swap the point-operator backend (default: oracle/point_ops.py on the CPU).  oracle/ref_cuda_ops.py plugs
+    in the reference's own CUDA kernels for the GPU-side baseline of bench.py."""
+    global P
+    P = ops
+
 # ----------------------------------------------------------------------------------------
 # architecture tables
 # ----------------------------------------------------------------------------------------
@@ -215,7 +222,7 @@ def timestep_embedding(t, dim, scale=1.0):
     float64 numpy, cast to fp32, sin | cos."""
     t = torch.as_tensor(t, dtype=torch.float32) * scale
     half = dim // 2
-    f = torch.from_numpy(np.exp(np.arange(0, half) * -(np.log(10000) / (half - 1)))).float()
+    f = torch.from_numpy(np.exp(np.arange(0, half) * -(np.log(10000) / (half - 1)))).float().to(t.device)
     e = t[:, None] * f[None, :]
     return torch.cat([torch.sin(e), torch.cos(e)], dim=1)
 
@@ -301,7 +308,7 @@ def positional_embedding(t, dim, scale=1.0):
     """models/utils.py:16-31 (fp32 frequencies, unlike the U-Net's)."""
     t = torch.as_tensor(t, dtype=torch.float32) * scale
     half = dim // 2
-    f = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    f = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).to(t.device)
     e = t[:, None] * f[None, :]
     return torch.cat([torch.sin(e), torch.cos(e)], dim=1)
 
