@@ -449,7 +449,7 @@ def main():
         try:
             import subprocess
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--batch", str(B)],
-                               capture_output=True, text=True, timeout=300)
+                               capture_output=True, text=True, timeout=200)
             rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
             gpu_ref = json.loads(rows[-1]) if rows else {"unavailable": (r.stderr or "no output")[-300:]}
         except Exception as e:      # noqa: BLE001
