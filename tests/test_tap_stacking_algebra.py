@@ -70,3 +70,57 @@ def test_stacked_taps_reproduce_the_convolution(S, r, C, O):
     got = out_rows.reshape(rp, rp, rp, O)[1:-1, 1:-1, 1:-1]
     ref = np.transpose(conv_reference(x, w), (1, 2, 3, 0))
     assert np.allclose(got, ref, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("S,NT,KG,cin_pad,cout_pad", [(3, 64, 8, 64, 64), (3, 32, 8, 36, 32), (2, 128, 4, 128, 256)])
+def test_stacked_weight_packing_matches_the_issuers_addressing(S, NT, KG, cin_pad, cout_pad):
+    """Python transcription of tc::k_pack_tc_stack's index decode and of the B-operand addresses the
+    UMMA issuers of tc::k_conv_stack form (16-byte units: one unit = 4 input channels of one output
+    channel): every element the tensor core would read must be the weight of the tap / channel pair
+    the algebra above assumes."""
+    rng = np.random.default_rng(1)
+    nchunk = -(-(cin_pad // 4) // KG)
+    wt = rng.standard_normal((27, cin_pad, cout_pad))            # SIMT packing wt[tap][ci][co]
+    per_dy = 3 * KG * NT
+    n_nt = cout_pad // NT
+    total = n_nt * nchunk * 3 * 3 * per_dy * 4
+    w = np.zeros(total)
+    for i in range(total):                                       # == k_pack_tc_stack
+        jj = i % 4
+        r = i // 4
+        e = r % per_dy; r //= per_dy
+        dy = r % 3; r //= 3
+        dx = r % 3; r //= 3
+        cc = r % nchunk; r //= nchunk
+        nt = r
+        if e < KG * S * NT:
+            kg, n2 = divmod(e, S * NT)
+            dz, n = divmod(n2, NT)
+        else:
+            e2 = e - KG * S * NT
+            dz = S + e2 // (KG * NT)
+            kg, n = divmod(e2 % (KG * NT), NT)
+        tap = (dx * 3 + dy) * 3 + dz
+        ci = (cc * KG + kg) * 4 + jj
+        w[i] = wt[tap, ci, nt * NT + n] if ci < cin_pad else 0.0
+    stage_units = 9 * KG * NT                                    # one (chunk, dx) stage, in 16-byte units
+    SN = S * NT
+    for nt in range(n_nt):
+        for cc in range(nchunk):
+            for dx in range(3):
+                base = ((nt * nchunk + cc) * 3 + dx) * stage_units   # producer: wsrc + (cc*3 + tg) * stage
+                for dy in range(3):
+                    b_dy = base + dy * per_dy
+                    for k2 in range(0, KG, 2):
+                        for k in range(8):                          # K = 8 of one UMMA: two k-groups
+                            kg = k2 + k // 4
+                            ci = (cc * KG + kg) * 4 + k % 4
+                            for n2 in (0, 1, NT - 1, NT, SN - 1):   # stacked MMA: start b_dy + k2*SN, LBO = SN
+                                unit = b_dy + kg * SN + n2
+                                want = wt[(dx * 3 + dy) * 3 + n2 // NT, ci, nt * NT + n2 % NT] if ci < cin_pad else 0.0
+                                assert w[unit * 4 + k % 4] == want
+                            for dz in range(S, 3):                  # single taps: start ... + KG*SN + (dz-S)*KG*NT, LBO = NT
+                                for n in (0, NT - 1):
+                                    unit = b_dy + KG * SN + (dz - S) * KG * NT + kg * NT + n
+                                    want = wt[(dx * 3 + dy) * 3 + dz, ci, nt * NT + n] if ci < cin_pad else 0.0
+                                    assert w[unit * 4 + k % 4] == want
