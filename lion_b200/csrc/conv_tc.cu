@@ -900,7 +900,11 @@ static int stack_mode() {   // LION_TC_STACK=1: experimental tap-stacked kernel 
   if (mode < 0) { const char* e = getenv("LION_TC_STACK"); mode = (e && atoi(e) != 0) ? 1 : 0; }
   return mode;
 }
-static int stack_factor(int NT) { return NT <= 64 ? 3 : 2; }    // UMMA N = S*NT <= 256
+static int stack_factor(int NT) {   // UMMA N = S*NT <= 256;  LION_TC_STACK=2 forces pairs (+ single dz=2 taps) for NT <= 64 as well
+  const char* e = getenv("LION_TC_STACK");
+  const int want = e ? atoi(e) : 3;
+  return (NT <= 64 && want != 2) ? 3 : 2;
+}
 
 static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, int& tpg) {
   NT = w.cout_pad < 128 ? w.cout_pad : 128;
