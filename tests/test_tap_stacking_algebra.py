@@ -124,3 +124,35 @@ def test_stacked_weight_packing_matches_the_issuers_addressing(S, NT, KG, cin_pa
                                     unit = b_dy + KG * SN + (dz - S) * KG * NT + kg * NT + n
                                     want = wt[(dx * 3 + dy) * 3 + dz, ci, nt * NT + n] if ci < cin_pad else 0.0
                                     assert w[unit * 4 + k % 4] == want
+
+
+@pytest.mark.parametrize("S", [2, 3])
+def test_epilogue_fold_via_shuffles_and_quarter_exchange(S):
+    """Transcription of the epilogue of tc::k_conv_stack for one 16-column chunk: four warps (TMEM lane
+    quarters) of 32 lanes; lane l of quarter q folds D_c from lane l+c -- __shfl_down inside the warp, the
+    rows that cross a quarter come from the next quarter through the shared-memory exchange (slot 0 =
+    block 1 / lane 0, slots 1, 2 = block 2 / lanes 0, 1)."""
+    rng = np.random.default_rng(2)
+    D = rng.standard_normal((S, 128, 16))                         # [column block][tile row][column]
+    TP = 128 - (S - 1)
+    xch = np.full((4, 3, 16), np.nan)
+    for q in range(4):                                            # writers (before the barrier)
+        for c in range(1, S):
+            for lane in range(32):
+                if q > 0 and lane < c:
+                    slot = 0 if c == 1 else 1 + lane
+                    xch[q, slot] = D[c, q * 32 + lane]
+    for q in range(4):                                            # readers
+        for lane in range(32):
+            acc = D[0, q * 32 + lane].copy()
+            for c in range(1, S):
+                if lane + c < 32:
+                    sh = D[c, q * 32 + lane + c]                  # __shfl_down_sync(v, c)
+                else:
+                    slot = 0 if c == 1 else 1 + (lane + c - 32)
+                    sh = xch[q + 1, slot] if q < 3 else np.zeros(16)
+                acc = acc + sh
+            lt = q * 32 + lane
+            if lt < TP:                                           # rows >= TP are recomputed by the next tile
+                want = sum(D[c, lt + c] for c in range(S))
+                assert np.allclose(acc, want)
