@@ -61,3 +61,38 @@ def test_state_dict_key_contract():
     assert shp(PriorSEDrop(cfg.sde, 128, cfg)) == keys["global"]
     assert shp(PriorSEClip(cc.sde, 128, cc)) == keys["global_clip"]
     assert shp(Model(cfg)) == keys["vae_decoder"]
+
+
+def _header_prototypes():
+    """{name: number of parameters} parsed from include/lion_b200.h"""
+    src = open(os.path.join(ROOT, "include", "lion_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(lion_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_ctypes_prototypes_match_the_header():
+    """The host side binds every entry point with an explicit ctypes prototype (lion_b200/_lib.py);
+    its arity must be the header's -- a drifted argument list would corrupt the call silently."""
+    from lion_b200 import _lib
+    lib = _lib.lib()
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib.EXPORTS)
+    for name, n in protos.items():
+        fn = getattr(lib, name)
+        assert fn.argtypes is not None and len(fn.argtypes) == n, "%s: header has %d parameters, ctypes prototype %s" % (
+            name, n, None if fn.argtypes is None else len(fn.argtypes))
+
+
+def test_integration_shim_names_exist():
+    """Every lion_* symbol the reference-side binding in INTEGRATION.md calls is exported."""
+    from lion_b200 import _lib
+    lib = _lib.lib()
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    used = sorted(set(re.findall(r"_lib\.(lion_[a-z0-9_]+)", text)))
+    assert len(used) >= 7
+    for n in used:
+        assert hasattr(lib, n), n
