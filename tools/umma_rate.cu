@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_rate(int N, int iters, int two_
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar[me])) : "memory");
     // wait for the MMAs to retire
     uint32_t ok = 0;
-    while (!ok) {
+    for (long long spin = 0; !ok && spin < 400000000LL; ++spin) {          // bounded: never hang the box
       asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                    : "=r"(ok) : "r"(smem_u32(&bar[me])), "r"(0u) : "memory");
     }
