@@ -9,3 +9,4 @@ for s in 3 2; do
 done
 TAPS=27 python tools/bench_convs.py | cut -c1-160
 timeout 300 python bench.py --impl reference-gpu | tee gpurun_out/gpu_baseline.json | cut -c1-600
+LION_EXTRA_GPU_TESTS=1 timeout 300 python -m pytest tests/test_fullsize_gpu.py -m gpu -q > gpurun_out/pytest_fullsize.log 2>&1; echo "fullsize rc=$?"; tail -5 gpurun_out/pytest_fullsize.log
