@@ -73,39 +73,9 @@ k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restri
   const float4* c = c4 + (size_t)b * N;
   __shared__ float s_stat[4];
   __shared__ unsigned s_key[VOXP_MAXN];
-  // statistics with the first VOX_THREADS threads' partition of the work (vox_stats_block uses blockDim)
-  {
-    __shared__ double s_red[3][VOXP_THREADS / 32];
-    __shared__ float s_max[VOXP_THREADS / 32];
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double sx = 0, sy = 0, sz = 0;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) { float4 v = c[k]; sx += v.x; sy += v.y; sz += v.z; }
-    sx = warp_sum_d(sx); sy = warp_sum_d(sy); sz = warp_sum_d(sz);
-    if (lane == 0) { s_red[0][wid] = sx; s_red[1][wid] = sy; s_red[2][wid] = sz; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-      double t = 0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[threadIdx.x][w];
-      s_stat[threadIdx.x] = (float)(t / (double)N);
-    }
-    __syncthreads();
-    float mx = s_stat[0], my = s_stat[1], mz = s_stat[2];
-    float best = 0.0f;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) {
-      float4 v = c[k];
-      float dx = __fsub_rn(v.x, mx), dy = __fsub_rn(v.y, my), dz = __fsub_rn(v.z, mz);
-      best = fmaxf(best, __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))));
-    }
-    best = warp_max(best);
-    if (lane == 0) s_max[wid] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.0f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, s_max[w]);
-      s_stat[3] = t;
-    }
-    __syncthreads();
-  }
+  // mean (torch-CUDA summation order: bit-exact voxel indices, point_core.cuh) and max centred norm
+  vox_stats_block<VOXP_THREADS / 32>([&](int k, float& x, float& y, float& z) { float4 v = c[k]; x = v.x; y = v.y; z = v.z; }, N,
+                                     3 * (int)gridDim.x, 3LL * b, s_stat);
   float mx = s_stat[0], my = s_stat[1], mz = s_stat[2], nrm = s_stat[3];
   int n2 = 1;
   while (n2 < N) n2 <<= 1;

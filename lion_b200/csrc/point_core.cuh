@@ -37,27 +37,107 @@ __device__ __forceinline__ void trilinear_corners(float x, float y, float z, int
 // ---------------------------------------------------------------------------------------
 constexpr int VOX_THREADS = 256;
 
-// s_out[0..2] = mean over points (double accumulation, rounded once), s_out[3] = max_k ||c_k - mean||_2
-template <typename Load>
-__device__ __forceinline__ void vox_stats_block(Load load, int N, float* s_out) {
-  __shared__ double s_red[3][VOX_THREADS / 32];
-  __shared__ float s_max[VOX_THREADS / 32];
+// --- coords.mean(2) with the BITS of torch's CUDA reduction ---------------------------------------------
+// The voxel index is round(f(coords - mean)): a 1-ulp difference in the mean moves points that sit on a
+// rounding boundary into the neighbouring voxel, so "bit-exact voxel index assignment" needs the reference's
+// summation ORDER, which is torch's at::native::reduce_kernel<512, 1, ReduceOp<float, MeanOps>> (ATen/native/
+// cuda/Reduce.cuh, vt0 = 4; restated in oracle/point_ops.py::cuda_mean_lastdim and pinned against torch on the
+// GPU by tests/test_point_ops_gpu.py).  For a contiguous [n_out = 3B, N] fp32 input reduced over N:
+//   vectorised by 4 when N > 128 (dim0 = N/4, else N);  W0 = min(last_pow2(dim0), 32),
+//   H = min(last_pow2(n_out), 512 / W0),  W = min(last_pow2(dim0), 512 / H) lanes share one row;
+//   lane x keeps 4 accumulators (vectorised: accumulator j <- elements 4*(x + k*W) + j; scalar: accumulator i <-
+//   element x + (4k + i)*W), folds them ((a0 + a1) + a2) + a3; lanes fold through a shared-memory tree
+//   (offsets W/2 .. 32) and a shuffle-down tree (1 .. 16); result * (float(n_out) / float(n_out * N)).
+//   Rows that do not start on a 16-byte boundary (N % 4 != 0) take Reduce.cuh's head / tail path.
+// Yes: the bits depend on the batch size.  Called by all threads of the block (blockDim.x >= 256);
+// elem(a, i) returns axis a of point i;  row0 = index of this shape's first row (3 * b).
+__device__ __forceinline__ int vox_last_pow2(int n) { return 1 << (31 - __clz(n)); }
+
+template <typename Elem>
+__device__ __forceinline__ void vox_mean_torch_cuda(Elem elem, int N, int n_out, long long row0, float* s_mean /*[3]*/) {
+  __shared__ float s_tree[3][256];
+  const bool vec = N > 128;
+  const int dim0 = vec ? N / 4 : N;
+  const int d0p = dim0 < 512 ? vox_last_pow2(dim0) : 512;
+  const int d1p = n_out < 512 ? vox_last_pow2(n_out) : 512;
+  int W = min(d0p, 32);
+  const int H = min(d1p, 512 / W);
+  W = min(d0p, 512 / H);
+  const int x = threadIdx.x;
+  float v[3] = {0.f, 0.f, 0.f};
+  if (x < W) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (vec) {
+        int shift = (int)(((row0 + a) * (long long)N) & 3);
+        int base = 0, end = N;
+        if (shift > 0) {
+          if (x >= shift && x < 4) a0 = __fadd_rn(a0, elem(a, x - shift));
+          base = 4 - shift;
+          end = N + shift - 4;
+        }
+        for (int idx = x; idx * 4 + 3 < end; idx += W) {
+          a0 = __fadd_rn(a0, elem(a, base + 4 * idx));
+          a1 = __fadd_rn(a1, elem(a, base + 4 * idx + 1));
+          a2 = __fadd_rn(a2, elem(a, base + 4 * idx + 2));
+          a3 = __fadd_rn(a3, elem(a, base + 4 * idx + 3));
+        }
+        const int i = end - (end & 3) + x;
+        if (i < end) a0 = __fadd_rn(a0, elem(a, base + i));
+      } else {
+        int idx = x;
+        while (idx + 3 * W < N) {
+          a0 = __fadd_rn(a0, elem(a, idx));
+          a1 = __fadd_rn(a1, elem(a, idx + W));
+          a2 = __fadd_rn(a2, elem(a, idx + 2 * W));
+          a3 = __fadd_rn(a3, elem(a, idx + 3 * W));
+          idx += 4 * W;
+        }
+        if (idx < N) { a0 = __fadd_rn(a0, elem(a, idx)); idx += W; }
+        if (idx < N) { a1 = __fadd_rn(a1, elem(a, idx)); idx += W; }
+        if (idx < N) { a2 = __fadd_rn(a2, elem(a, idx)); idx += W; }
+        if (idx < N) { a3 = __fadd_rn(a3, elem(a, idx)); idx += W; }
+      }
+      v[a] = __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+    }
+  }
+  if (W > 32) {
+    if (x < W) { s_tree[0][x] = v[0]; s_tree[1][x] = v[1]; s_tree[2][x] = v[2]; }
+    for (int off = W >> 1; off >= 32; off >>= 1) {
+      __syncthreads();
+      if (x < off) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { v[a] = __fadd_rn(v[a], s_tree[a][x + off]); s_tree[a][x] = v[a]; }
+      }
+    }
+  }
+  if (x < 32) {
+    const int lim = W < 32 ? W : 32;
+    for (int off = 1; off < lim; off <<= 1) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        float o = __shfl_down_sync(0xffffffffu, v[a], off);
+        if (x + off >= 32) o = 0.f;      // (never reaches lane 0's dependency cone; keeps the values finite)
+        v[a] = __fadd_rn(v[a], o);
+      }
+    }
+    if (x == 0) {
+      const float factor = __fdiv_rn((float)n_out, (float)((long long)n_out * N));
+#pragma unroll
+      for (int a = 0; a < 3; ++a) s_mean[a] = __fmul_rn(v[a], factor);
+    }
+  }
+  __syncthreads();
+}
+
+// s_out[0..2] = mean over points (torch-CUDA summation order, see above), s_out[3] = max_k ||c_k - mean||_2.
+// load(k, x, y, z) returns point k;  MAXW = blockDim.x / 32 upper bound.
+template <int MAXW, typename Load>
+__device__ __forceinline__ void vox_stats_block(Load load, int N, int n_out, long long row0, float* s_out) {
+  __shared__ float s_max[MAXW];
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double sx = 0, sy = 0, sz = 0;
-  for (int k = threadIdx.x; k < N; k += blockDim.x) {
-    float x, y, z;
-    load(k, x, y, z);
-    sx += x; sy += y; sz += z;
-  }
-  sx = warp_sum_d(sx); sy = warp_sum_d(sy); sz = warp_sum_d(sz);
-  if (lane == 0) { s_red[0][wid] = sx; s_red[1][wid] = sy; s_red[2][wid] = sz; }
-  __syncthreads();
-  if (threadIdx.x < 3) {
-    double t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[threadIdx.x][w];
-    s_out[threadIdx.x] = (float)(t / (double)N);
-  }
-  __syncthreads();
+  vox_mean_torch_cuda([&](int a, int i) { float x, y, z; load(i, x, y, z); return a == 0 ? x : (a == 1 ? y : z); }, N, n_out, row0, s_out);
   float mx = s_out[0], my = s_out[1], mz = s_out[2];
   float best = 0.0f;
   for (int k = threadIdx.x; k < N; k += blockDim.x) {

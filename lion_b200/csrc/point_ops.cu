@@ -184,7 +184,8 @@ k_voxel_coords_soa(const float* __restrict__ coords, float* __restrict__ norm_co
   int b = blockIdx.x;
   const float* c = coords + (size_t)b * 3 * N;
   __shared__ float s_stat[4];
-  vox_stats_block([&](int k, float& x, float& y, float& z) { x = c[k]; y = c[k + N]; z = c[k + 2 * N]; }, N, s_stat);
+  vox_stats_block<VOX_THREADS / 32>([&](int k, float& x, float& y, float& z) { x = c[k]; y = c[k + N]; z = c[k + 2 * N]; }, N,
+                                    3 * (int)gridDim.x, 3LL * b, s_stat);
   float mx = s_stat[0], my = s_stat[1], mz = s_stat[2], nrm = s_stat[3];
   for (int k = threadIdx.x; k < N; k += blockDim.x) {
     float v[3];

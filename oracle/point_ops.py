@@ -61,6 +61,117 @@ def voxel_coords(coords, r, normalize=True, eps=0.0):
     return nc, vox
 
 
+def _last_pow2(n):
+    p = 1
+    while p * 2 <= n:
+        p *= 2
+    return p
+
+
+def cuda_mean_lastdim(x):
+    """`x.mean(2)` of a contiguous fp32 [B,3,N] tensor with the BITS torch's CUDA reduction produces
+    (third-party arithmetic: PyTorch ATen/native/cuda/Reduce.cuh -- `reduce_kernel<512, 1, ReduceOp<float,
+    MeanOps<...>>>`, vt0 = 4 -- restated from its published algorithm; pinned on the GPU box against
+    torch itself by tests/test_point_ops_gpu.py::test_cuda_mean_emulation_matches_torch).
+
+    The summation order depends on the number of outputs (3B) as well as on N:
+      * reduction over the contiguous dimension; vectorised by 4 when N > 128;
+      * block = (W lanes along the reduction) x (H outputs): W0 = min(last_pow2(dim0), 32),
+        H = min(last_pow2(3B), 512 / W0), W = min(last_pow2(dim0), 512 / H), dim0 = N/4 (vectorised) or N;
+      * lane x keeps 4 accumulators: vectorised -> accumulator j sums elements 4*(x + k*W) + j, k = 0, 1, ...;
+        otherwise accumulator (k mod 4) sums element x + k*W; leftovers (N % 4) go to accumulator 0 of lane
+        (element - tail_start); the accumulators are folded ((a0 + a1) + a2) + a3;
+      * lanes are folded by a shared-memory tree for offsets W/2 ... 32 (x += x[+offset]) and then a
+        shuffle-down tree with offsets 1, 2, 4, 8, 16; the result is multiplied by float(3B) / float(3B*N).
+    Rows whose start is not 16-byte aligned (N % 4 != 0) go through Reduce.cuh's head-alignment path; that case
+    is restated too (shift = row offset mod 4)."""
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    B, C, N = x.shape
+    n_out = B * C
+    vec = N > 128
+    dim0 = N // 4 if vec else N
+    d0p = _last_pow2(dim0) if dim0 < 512 else 512
+    d1p = _last_pow2(n_out) if n_out < 512 else 512
+    W = min(d0p, 32)
+    H = min(d1p, 512 // W)
+    W = min(d0p, 512 // H)
+    factor = np.float32(n_out) / np.float32(n_out * N)
+    out = np.zeros((B, C), np.float32)
+    f32 = np.float32
+    for o in range(n_out):
+        row = x.reshape(n_out, N)[o]
+        acc = np.zeros((W, 4), np.float32)
+        if vec:
+            data, end = row, N
+            shift = (o * N) % 4                      # elements past the previous 16-byte boundary (base is aligned)
+            if shift > 0:
+                # head: lanes shift..3 take one element each of the first (partial) vector
+                for lane in range(shift, 4):
+                    if lane < W and lane - shift < N:
+                        acc[lane, 0] = f32(acc[lane, 0] + row[lane - shift])
+                data = row[4 - shift:]
+                end = N + shift - 4
+            nvec = max(end, 0) // 4
+            for idx in range(nvec):
+                lane = idx % W
+                v = data[4 * idx:4 * idx + 4]
+                acc[lane] = (acc[lane] + v).astype(np.float32)
+            tail_start = end - end % 4 if end > 0 else 0
+            for i in range(tail_start, max(end, 0)):
+                lane = i - tail_start
+                acc[lane, 0] = f32(acc[lane, 0] + data[i])
+        else:
+            for lane in range(min(W, N)):
+                k = 0
+                idx = lane
+                while idx + 3 * W < N:               # unrolled by vt0 = 4: accumulator i takes element idx + i*W
+                    for i in range(4):
+                        acc[lane, i] = f32(acc[lane, i] + row[idx + i * W])
+                    idx += 4 * W
+                i = 0
+                while idx < N and i < 4:
+                    acc[lane, i] = f32(acc[lane, i] + row[idx])
+                    idx += W
+                    i += 1
+        v = acc[:, 0].copy()
+        for j in range(1, 4):
+            v = (v + acc[:, j]).astype(np.float32)
+        off = W // 2
+        while off >= 32:                             # shared-memory tree
+            v[:off] = (v[:off] + v[off:2 * off]).astype(np.float32)
+            off //= 2
+        w = v[:min(W, 32)].copy()
+        if len(w) < 32:
+            w = np.concatenate([w, np.zeros(32 - len(w), np.float32)])   # lanes >= W hold the identity
+        off = 1
+        lim = min(W, 32)
+        while off < lim:                             # shuffle-down tree (lane i += lane i+off)
+            sh = np.concatenate([w[off:], w[-off:]])
+            w = (w + sh).astype(np.float32)
+            off *= 2
+        out[o // C, o % C] = f32(w[0] * factor)
+    return out
+
+
+def voxel_coords_cuda_order(coords, r, normalize=True, eps=0.0):
+    """Voxelization.forward (models/pvcnn2_ada.py:173-188) with the bits torch produces ON CUDA: only the mean
+    depends on the device (summation order); the 3-term norm, max, division, scale, clamp and round are
+    order-free.  coords [B,3,N] -> (norm_coords, vox int32)."""
+    c = np.ascontiguousarray(np.asarray(coords, dtype=np.float32))
+    mean = cuda_mean_lastdim(c)[:, :, None]
+    nc = (c - mean).astype(np.float32)
+    if normalize:
+        sq = (nc * nc).astype(np.float32)
+        nrm = np.sqrt(((sq[:, 0] + sq[:, 1]).astype(np.float32) + sq[:, 2]).astype(np.float32)).astype(np.float32)
+        den = (nrm.max(axis=1) * np.float32(2.0) + np.float32(eps)).astype(np.float32)[:, None, None]
+        nc = ((nc / den).astype(np.float32) + np.float32(0.5)).astype(np.float32)
+    else:
+        nc = ((nc + np.float32(1.0)) / np.float32(2.0)).astype(np.float32)
+    nc = np.clip((nc * np.float32(r)).astype(np.float32), np.float32(0), np.float32(r - 1))
+    t = torch.from_numpy(nc)
+    return t, torch.round(t).to(torch.int32)
+
+
 def round_to_voxel(norm_coords):
     """The integer part only: round-half-even of already normalised coordinates."""
     return torch.round(torch.as_tensor(norm_coords, dtype=torch.float32)).to(torch.int32)

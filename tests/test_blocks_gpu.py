@@ -140,3 +140,37 @@ def test_conv3d_standalone(cin, cout, r, B):
     assert_close(ssum, o64.sum(-1), 1e-5, "fused GroupNorm sum")
     assert_close(ssq, (o64 * o64).sum(-1), 1e-5, "fused GroupNorm sum of squares")
     assert torch.equal(m(x.cuda()), out), "conv3d is not bit-reproducible"
+
+
+# the eight (r, C_in, C_out) classes of one PVCNN2Prior step at the BENCHMARKED batch
+B32_CONV_SHAPES = [(4, 32, 32), (32, 32, 32), (64, 64, 32), (128, 64, 16), (64, 64, 16), (128, 128, 16), (192, 128, 8), (128, 128, 8)]
+
+
+@pytest.mark.parametrize("cin,cout,r", B32_CONV_SHAPES)
+def test_conv3d_b32_vs_cudnn(cin, cout, r):
+    """a7 at B = 32 (BASELINE configs[1]): the tcgen05 convolution against torch's conv3d evaluated ON THE GPU
+    (the CPU would need minutes): (i) cuDNN with TF32 allowed = the reference's own path under default torch
+    flags (models/pvcnn2_ada.py:211-222) -- both sides round operands to TF32, tolerance 2e-3; (ii) full-fp32
+    cuDNN on TF32(rna)-rounded operands, which isolates indexing / accumulation order: 2e-5; (iii) the fused
+    GroupNorm statistics against float64 sums of the kernel's own output."""
+    from lion_b200.models.pvcnn2_ada import Conv3d
+    B = 32
+    m = Conv3d(cin, cout, 3, stride=1, padding=1)
+    w, b = gen(61, cout, cin, 3, 3, 3, scale=(27 * cin) ** -0.5), gen(62, cout, scale=0.1)
+    m.load_state_dict({"weight": w, "bias": b})
+    m = m.cuda().eval()
+    x = gen(63, B, cin, r, r, r).cuda()
+    out, ssum, ssq = m(x, return_gn_stats=True)
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        ref_tf32 = torch.nn.functional.conv3d(x, w.cuda(), b.cuda(), padding=1)
+        torch.backends.cudnn.allow_tf32 = False
+        ref_t = torch.nn.functional.conv3d(_tf32_rna(x.cpu()).cuda(), _tf32_rna(w).cuda(), b.cuda(), padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert_close(out, ref_tf32, TOL, "conv3d B=32 vs cuDNN TF32")
+    assert_close(out, ref_t, 2e-5, "conv3d B=32 vs fp32 cuDNN on TF32-rounded operands")
+    o64 = out.double().view(B, cout, -1)
+    assert_close(ssum, o64.sum(-1), 1e-5, "fused GroupNorm sum, B=32")
+    assert_close(ssq, (o64 * o64).sum(-1), 1e-5, "fused GroupNorm sum of squares, B=32")

@@ -3,8 +3,7 @@ a GPU evaluation of the oracle: oracle/net.py on CUDA tensors with the REFERENCE
 (oracle/ref_cuda_ops.py -> oracle/_ref/_pvcnn_backend.so) and torch's cuDNN / cuBLAS layers, i.e. the
 reference's eager path.  The CPU oracle needs ~10 s per shape for this, the GPU one a fraction of a second.
 
-Written after the round-1 GPU budget was spent: opt-in (LION_EXTRA_GPU_TESTS=1) until it has run once
-on hardware; then the guard goes away."""
+First run on hardware in round 2 (gpurun_out/pytest_fullsize.log: 1 passed); always on since."""
 import json
 import os
 
@@ -14,8 +13,7 @@ import torch
 from tests.synth import synth_state_dict
 from tests.util import assert_close, rms_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("LION_EXTRA_GPU_TESTS"), reason="opt-in until first run on hardware")]
+pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(__file__), "golden")
 KEYS = json.load(open(os.path.join(G, "keys.json")))
 

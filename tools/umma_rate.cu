@@ -19,7 +19,7 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(128, 1) k_umma_rate(int N, int iters, int two_issuers, unsigned long long* cycles) {
+__global__ void __launch_bounds__(128, 1) k_umma_rate(int N, int iters, int two_issuers, int nacc, int blk, unsigned long long* cycles) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar[2];
   __shared__ uint32_t s_tmem;
@@ -49,7 +49,10 @@ __global__ void __launch_bounds__(128, 1) k_umma_rate(int N, int iters, int two_
   long long t0 = 0;
   if ((warp == 1 || (two_issuers && warp == 2)) && (tid & 31) == 0) {
     const int me = warp - 1;
-    const uint32_t d = tmem + (uint32_t)(me * 256);          // each issuer its own accumulator
+    const uint32_t d0 = tmem + (uint32_t)(me * 256);         // each issuer its own accumulator(s)
+    // nacc > 1: consecutive UMMAs of ONE issuer rotate over nacc accumulators (independent dependency chains)
+    const uint32_t dstep = (nacc > 1) ? (uint32_t)(256 / nacc) : 0u;
+    uint32_t cnt = 0;
     t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -61,6 +64,8 @@ __global__ void __launch_bounds__(128, 1) k_umma_rate(int N, int iters, int two_
           uint64_t ad = ((uint64_t)d_hi << 32) | a_lo_c | ((a_t + k2 * a_rows) & 0x3fff);
           uint64_t bd = ((uint64_t)d_hi << 32) | b_lo_c | ((b_t + k2 * N) & 0x3fff);
           uint32_t acc = (it | t | k2) ? 1u : 0u;
+          const uint32_t d = d0 + ((cnt / (uint32_t)blk) % (uint32_t)nacc) * dstep;   // blk = 36: one accumulator per burst of 36 (block-sequential)
+          ++cnt;
           asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
                        ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
         }
@@ -91,14 +96,17 @@ int main() {
   CK(cudaMalloc(&d_cyc, 8));
   const int iters = 2000;
   printf("SMs %d, max clock %.0f MHz; M=128, K=8, kind::tf32, SS mode, %d x 36 UMMAs per issuer\n", sms, khz / 1000.0, iters);
+  for (int blk : {1, 36})
+  for (int nacc : {1, 2, 4})
   for (int two = 0; two <= 1; ++two)
     for (int N : {32, 64, 96, 128, 192, 256}) {
+      if ((nacc > 1 && N * nacc > 256) || (blk > 1 && nacc == 1)) continue;                      // each issuer owns 256 TMEM columns
       size_t smem = 8 * 200 * 16 + (size_t)3 * 8 * N * 16;
       cudaEvent_t e0, e1;
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-      k_umma_rate<<<sms, 128, smem>>>(N, 10, two, d_cyc);           // warm-up
+      k_umma_rate<<<sms, 128, smem>>>(N, 10, two, nacc, blk, d_cyc);           // warm-up
       CK(cudaEventRecord(e0));
-      k_umma_rate<<<sms, 128, smem>>>(N, iters, two, d_cyc);
+      k_umma_rate<<<sms, 128, smem>>>(N, iters, two, nacc, blk, d_cyc);
       CK(cudaEventRecord(e1));
       CK(cudaEventSynchronize(e1));
       float ms = 0;
@@ -107,7 +115,7 @@ int main() {
       CK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
       double n_mma = (double)iters * 36 * (two ? 2 : 1);
       double flops = 2.0 * 128 * N * 8 * n_mma * sms;
-      printf("issuers %d  N %3d : %8.3f ms  %7.1f TFLOP/s  %6.1f clk/UMMA (SM0)  operand bytes/clk %.0f\n", two + 1, N, ms,
+      printf("rotate-every %2d  accumulators/issuer %d  issuers %d  N %3d : %8.3f ms  %7.1f TFLOP/s  %6.1f clk/UMMA (SM0)  operand bytes/clk %.0f\n", blk, nacc, two + 1, N, ms,
              flops / (ms * 1e-3) / 1e12, (double)cyc / (iters * 36.0), (4096.0 + 32.0 * N) * (two ? 2 : 1) / ((double)cyc / (iters * 36.0)));
     }
   return 0;
