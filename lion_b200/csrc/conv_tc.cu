@@ -93,6 +93,60 @@ __device__ __forceinline__ void mbar_arrive_w(uint32_t bar) {
   asm volatile("{\n.reg .pred q;\nelect.sync _|q, 0xffffffff;\n"
                "@q mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];\n}" ::"r"(bar) : "memory");
 }
+// ---- one pipeline stage's UMMAs as ONE asm block ------------------------------------------------------------
+// Round-2 finding (tools/umma_issue.cu, profiles/r02_umma_issue.txt): issuing tcgen05.mma one asm statement at a
+// time costs ~64-140 clk per UMMA per warp -- every MMA drags an ELECT, five R2UR.BROADCAST (descriptor halves and
+// the TMEM address have to reach uniform registers) and two VOTEU through the issue slot, serialised by the
+// volatile statement boundaries -- which is MORE than the 32 clk an M128 x N64 x K8 UMMA occupies the tensor pipe:
+// the round-1 kernel was instruction-issue bound, not operand- or tensor-bound.  Emitting a whole stage (TPG taps
+// x KS k-steps) as one block with a single elect.sync and descriptors derived by in-asm adds lets ptxas software-
+// pipeline the R2URs of later MMAs under earlier UTCHMMAs (~6 instructions per MMA).
+//   operands: %0 TMEM accumulator, %1 A descriptor low word (LBO<<16 | addr16 of the un-shifted view), %2 B ditto,
+//   %3 idesc, %4 accumulate flag of the FIRST MMA, %5 descriptor high word, %6 A k-step (2 groups), %7 B k-step,
+//   %8 B tap pitch, %9.. row offset of tap t.  Low-word adds never carry out of the 14-bit address field
+//   (all views lie inside this CTA's shared memory).
+#define LION_MMA1(AL, BL, PRED) "mov.b64 ad, {" AL ", %5};\n mov.b64 bd, {" BL ", %5};\n @q tcgen05.mma.cta_group::1.kind::tf32 [%0], ad, bd, %3, " PRED ";\n"
+#define LION_TAP4(TOP, FP)                                                                 \
+  "add.u32 a0, %1, " TOP ";\n" LION_MMA1("a0", "bt", FP)                                   \
+  "add.u32 a1, a0, %6;\n add.u32 b1, bt, %7;\n" LION_MMA1("a1", "b1", "pt")                \
+  "add.u32 a2, a1, %6;\n add.u32 b2, b1, %7;\n" LION_MMA1("a2", "b2", "pt")                \
+  "add.u32 a3, a2, %6;\n add.u32 b3, b2, %7;\n" LION_MMA1("a3", "b3", "pt")                \
+  "add.u32 bt, bt, %8;\n"
+#define LION_TAP2(TOP, FP)                                                                 \
+  "add.u32 a0, %1, " TOP ";\n" LION_MMA1("a0", "bt", FP)                                   \
+  "add.u32 a1, a0, %6;\n add.u32 b1, bt, %7;\n" LION_MMA1("a1", "b1", "pt")                \
+  "add.u32 bt, bt, %8;\n"
+#define LION_TAP1(TOP, FP)                                                                 \
+  "add.u32 a0, %1, " TOP ";\n" LION_MMA1("a0", "bt", FP)                                   \
+  "add.u32 bt, bt, %8;\n"
+#define LION_STAGE_HEAD                                                                    \
+  "{\n.reg .pred q, p, pt;\n.reg .b32 a0, a1, a2, a3, b1, b2, b3, bt;\n.reg .b64 ad, bd;\n" \
+  "elect.sync _|q, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\nsetp.eq.b32 pt, 0, 0;\nmov.b32 bt, %2;\n"
+#define LION_STAGE9(TAP)                                                                   \
+  asm volatile(LION_STAGE_HEAD TAP("%9", "p") TAP("%10", "pt") TAP("%11", "pt") TAP("%12", "pt") TAP("%13", "pt")     \
+               TAP("%14", "pt") TAP("%15", "pt") TAP("%16", "pt") TAP("%17", "pt") "}\n"                                 \
+               ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(hi), "r"(a_k2), "r"(b_k2), "r"(b_tap),          \
+                 "r"(to[0]), "r"(to[1]), "r"(to[2]), "r"(to[3]), "r"(to[4]), "r"(to[5]), "r"(to[6]), "r"(to[7]), "r"(to[8]) : "memory")
+#define LION_STAGE1(TAP)                                                                   \
+  asm volatile(LION_STAGE_HEAD TAP("%9", "p") "}\n"                                                                     \
+               ::"r"(d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(acc), "r"(hi), "r"(a_k2), "r"(b_k2), "r"(b_tap), "r"(to[0]) : "memory")
+
+// all UMMAs of one (row tile, channel chunk, tap group): TPG taps x KG/2 k-steps.  Warp-collective (elect inside).
+template <int KG, int TPG>
+__device__ __forceinline__ void issue_stage(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc, uint32_t hi,
+                                            uint32_t a_k2, uint32_t b_k2, uint32_t b_tap, const int* to) {
+  static_assert((KG == 2 || KG == 4 || KG == 8) && (TPG == 1 || TPG == 9), "unsupported stage shape");
+  if constexpr (TPG == 9) {
+    if constexpr (KG == 8) LION_STAGE9(LION_TAP4);
+    else if constexpr (KG == 4) LION_STAGE9(LION_TAP2);
+    else LION_STAGE9(LION_TAP1);
+  } else {
+    if constexpr (KG == 8) LION_STAGE1(LION_TAP4);
+    else if constexpr (KG == 4) LION_STAGE1(LION_TAP2);
+    else LION_STAGE1(LION_TAP1);
+  }
+}
+
 // no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -347,18 +401,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
               const uint32_t d = tmem_base + (uint32_t)(jt * P.NT);
               const bool fresh = ((started >> jt) & 1u) == 0;
               started |= 1u << jt;
-#pragma unroll
-              for (int t = 0; t < TPG; ++t) {
-                const uint32_t a_t = a_base16 + (uint32_t)P.tap_off[t];
-                const uint32_t b_t = b_base16 + t * b_tap16;
-#pragma unroll
-                for (int k2 = 0; k2 < KG; k2 += 2) {
-                  uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
-                  uint32_t blo = b_lo_c | ((b_t + k2 * b_pitch16) & 0x3fff);
-                  uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
-                  if (!(P.debug & 2)) umma_tf32_w(d, ad, bd, idesc, (fresh && t == 0 && k2 == 0) ? 0u : 1u);
-                }
-              }
+              issue_stage<KG, TPG>(d, a_lo_c | (a_base16 & 0x3fff), b_lo_c | (b_base16 & 0x3fff), idesc, fresh ? 0u : 1u, d_hi,
+                                   2u * a_pitch16, 2u * b_pitch16, b_tap16, P.tap_off);
               if (last) umma_commit_w(bar_accf + 8 * jt);   // accumulator jt complete -> epilogue may drain it
               issued = true;
             }

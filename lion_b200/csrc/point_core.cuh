@@ -43,11 +43,11 @@ constexpr int VOX_THREADS = 256;
 // summation ORDER, which is torch's at::native::reduce_kernel<512, 1, ReduceOp<float, MeanOps>> (ATen/native/
 // cuda/Reduce.cuh, vt0 = 4; restated in oracle/point_ops.py::cuda_mean_lastdim and pinned against torch on the
 // GPU by tests/test_point_ops_gpu.py).  For a contiguous [n_out = 3B, N] fp32 input reduced over N:
-//   vectorised by 4 when N > 128 (dim0 = N/4, else N);  W0 = min(last_pow2(dim0), 32),
+//   vectorised by 4 when N >= 128 (dim0 = N/4, else N);  W0 = min(last_pow2(dim0), 32),
 //   H = min(last_pow2(n_out), 512 / W0),  W = min(last_pow2(dim0), 512 / H) lanes share one row;
 //   lane x keeps 4 accumulators (vectorised: accumulator j <- elements 4*(x + k*W) + j; scalar: accumulator i <-
 //   element x + (4k + i)*W), folds them ((a0 + a1) + a2) + a3; lanes fold through a shared-memory tree
-//   (offsets W/2 .. 32) and a shuffle-down tree (1 .. 16); result * (float(n_out) / float(n_out * N)).
+//   (offsets W/2 .. 32) and a shuffle-down tree (16 .. 1); result * (float(n_out) / float(n_out * N)).
 //   Rows that do not start on a 16-byte boundary (N % 4 != 0) take Reduce.cuh's head / tail path.
 // Yes: the bits depend on the batch size.  Called by all threads of the block (blockDim.x >= 256);
 // elem(a, i) returns axis a of point i;  row0 = index of this shape's first row (3 * b).
@@ -56,7 +56,7 @@ __device__ __forceinline__ int vox_last_pow2(int n) { return 1 << (31 - __clz(n)
 template <typename Elem>
 __device__ __forceinline__ void vox_mean_torch_cuda(Elem elem, int N, int n_out, long long row0, float* s_mean /*[3]*/) {
   __shared__ float s_tree[3][256];
-  const bool vec = N > 128;
+  const bool vec = N >= 128;
   const int dim0 = vec ? N / 4 : N;
   const int d0p = dim0 < 512 ? vox_last_pow2(dim0) : 512;
   const int d1p = n_out < 512 ? vox_last_pow2(n_out) : 512;
@@ -114,7 +114,7 @@ __device__ __forceinline__ void vox_mean_torch_cuda(Elem elem, int N, int n_out,
   }
   if (x < 32) {
     const int lim = W < 32 ? W : 32;
-    for (int off = 1; off < lim; off <<= 1) {
+    for (int off = lim >> 1; off > 0; off >>= 1) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         float o = __shfl_down_sync(0xffffffffu, v[a], off);

@@ -75,20 +75,20 @@ def cuda_mean_lastdim(x):
     torch itself by tests/test_point_ops_gpu.py::test_cuda_mean_emulation_matches_torch).
 
     The summation order depends on the number of outputs (3B) as well as on N:
-      * reduction over the contiguous dimension; vectorised by 4 when N > 128;
+      * reduction over the contiguous dimension; vectorised by 4 when N >= 128;
       * block = (W lanes along the reduction) x (H outputs): W0 = min(last_pow2(dim0), 32),
         H = min(last_pow2(3B), 512 / W0), W = min(last_pow2(dim0), 512 / H), dim0 = N/4 (vectorised) or N;
       * lane x keeps 4 accumulators: vectorised -> accumulator j sums elements 4*(x + k*W) + j, k = 0, 1, ...;
         otherwise accumulator (k mod 4) sums element x + k*W; leftovers (N % 4) go to accumulator 0 of lane
         (element - tail_start); the accumulators are folded ((a0 + a1) + a2) + a3;
       * lanes are folded by a shared-memory tree for offsets W/2 ... 32 (x += x[+offset]) and then a
-        shuffle-down tree with offsets 1, 2, 4, 8, 16; the result is multiplied by float(3B) / float(3B*N).
+        shuffle-down tree with offsets 16, 8, 4, 2, 1; the result is multiplied by float(3B) / float(3B*N).
     Rows whose start is not 16-byte aligned (N % 4 != 0) go through Reduce.cuh's head-alignment path; that case
     is restated too (shift = row offset mod 4)."""
     x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
     B, C, N = x.shape
     n_out = B * C
-    vec = N > 128
+    vec = N >= 128
     dim0 = N // 4 if vec else N
     d0p = _last_pow2(dim0) if dim0 < 512 else 512
     d1p = _last_pow2(n_out) if n_out < 512 else 512
@@ -143,12 +143,11 @@ def cuda_mean_lastdim(x):
         w = v[:min(W, 32)].copy()
         if len(w) < 32:
             w = np.concatenate([w, np.zeros(32 - len(w), np.float32)])   # lanes >= W hold the identity
-        off = 1
-        lim = min(W, 32)
-        while off < lim:                             # shuffle-down tree (lane i += lane i+off)
+        off = min(W, 32) // 2
+        while off > 0:                               # shuffle-down tree, offsets DEcreasing (lane i += lane i+off)
             sh = np.concatenate([w[off:], w[-off:]])
             w = (w + sh).astype(np.float32)
-            off *= 2
+            off //= 2
         out[o // C, o % C] = f32(w[0] * factor)
     return out
 
