@@ -19,10 +19,17 @@ Printed JSON line (rank 0): the base contract plus
   cpu_baseline  the CPU oracle (oracle/) on the host cores, bounded sample, extrapolated
   e2e           the same pass with all noise supplied from pinned HOST memory (H2D inside the
                 timed region) and the point clouds copied back to pinned host memory
-  gpu_baseline  (N=1, informational) a GPU port of the reference's EAGER path -- oracle/net.py on CUDA
-                tensors (cuDNN/cuBLAS through torch, TF32 convs) + the reference's own pvcnn kernels from
-                oracle/_ref -- on a bounded sample, run in a child process (`--impl reference-gpu`).  The
-                reference's Python modules themselves cannot travel to the GPU box.
+  gpu_baseline  (N=1, informational) the UNMODIFIED reference on the same GPU: baseline/ref_gpu_arm.py runs the
+                reference's own generate_samples_vada_2prior (copy under baseline/_ref/LION, its JIT-built pvcnn
+                kernels, torch cuDNN/cuBLAS) for a FULL 1000+1000-step pass at the same batch, in a child process.
+                Falls back to the oracle's eager port (`--impl reference-gpu`) when baseline/_ref is absent.
+  parity        (N=1) teacher-forced B=32 parity of one denoising step of both priors against the reference's
+                eager path on the GPU (oracle/net.py + the reference's own point kernels), child process
+  extra_configs BASELINE configs[3] (CLIP-conditioned prior, B=32, 1 GPU) and, at N=4, configs[2] (64 shapes over
+                4 GPUs, 16 per rank): one timed pass each
+  per_rank      (N>1) per-rank pass times and the time the sampling stream waited in the all_gather
+  env           every LION_* variable that was set (performance knobs); bench refuses to run with any set unless
+                --allow-knobs
 --impl reference times the reference's own CPU implementation of the path (the oracle port,
 restated from the reference and pinned to its goldens) on all host threads.
 """
@@ -47,12 +54,15 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu", "parity"])
     ap.add_argument("--batch", type=int, default=32, help="shapes per GPU")
     ap.add_argument("--ddpm-steps", type=int, default=T_STEPS, help="(debug) DDPM steps; the metric is defined at 1000")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--allow-knobs", action="store_true", help="run although LION_* performance knobs are set (they are recorded in the line)")
     return ap.parse_args()
 
 
@@ -104,14 +114,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_models(cfg, device):
+def build_models(cfg, device, clip=False):
     import torch
     from lion_b200.models.latent_points_ada_localprior import PVCNN2Prior
-    from lion_b200.models.score_sde.resnet import PriorSEDrop
+    from lion_b200.models.score_sde.resnet import PriorSEDrop, PriorSEClip
     from lion_b200.models.vae_adain import Model
     from tests.synth import synth_state_dict
     shp = lambda m: {k: list(v.shape) for k, v in m.state_dict().items()}
-    gp = PriorSEDrop(cfg.sde, cfg.latent_pts.style_dim, cfg)
+    gp = (PriorSEClip if clip else PriorSEDrop)(cfg.sde, cfg.latent_pts.style_dim, cfg)
     gp.load_state_dict(synth_state_dict(shp(gp), 14))
     lp = PVCNN2Prior(cfg.sde, 1, cfg)
     lp.load_state_dict(synth_state_dict(shp(lp), 11))
@@ -229,6 +239,60 @@ def run_gpu_reference(args):
                       "detail": {"s_per_local_step": tl, "s_per_global_step": tg}}))
 
 
+
+def run_parity(args):
+    """--impl parity (child process of the default run; SURVEY.md 8d "parity checks reported with the number"):
+    teacher-forced parity AT THE BENCHMARKED BATCH of one denoising step of both priors against the reference's eager
+    path on the GPU (oracle/net.py on CUDA tensors = torch cuDNN/cuBLAS + the reference's OWN point kernels from
+    oracle/_ref), plus the exactness of the index-producing operators.  The oracle is the checker here, never timed."""
+    import torch
+    from oracle import net as ON
+    from oracle import point_ops, ref_cuda_ops
+    from oracle.build_ref import load_ref
+    from lion_b200.config import default_prior_cfg
+    from lion_b200.models.latent_points_ada_localprior import PVCNN2Prior
+    from lion_b200.models.score_sde.resnet import PriorSEDrop
+    from lion_b200.third_party.pvcnn import functional as F
+    from lion_b200.third_party.pvcnn.functional import furthest_point_sample_indices
+    from tests.synth import synth_state_dict
+    from tests.util import rel_err, rms_err
+    B = args.batch
+    dev = torch.device("cuda", 0)
+    keys = json.load(open(os.path.join(ROOT, "tests", "golden", "keys.json")))
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 8192, 1, 1, generator=g)
+    style = torch.randn(B, 128, 1, 1, generator=g)
+    t = torch.randint(1, 1001, (B,), generator=g).float()
+    sd_l, sd_g = synth_state_dict(keys["prior"], 11), synth_state_dict(keys["global"], 14)
+    cfg = default_prior_cfg()
+    lp = PVCNN2Prior(cfg.sde, 1, cfg); lp.load_state_dict(sd_l)
+    gp = PriorSEDrop(cfg.sde, 128, cfg); gp.load_state_dict(sd_g)
+    lp, gp = lp.cuda().eval(), gp.cuda().eval()
+    eps = lp(x=x.cuda(), t=t.cuda(), condition_input=style.cuda())
+    eg = gp(x=style.cuda(), t=t.cuda(), condition_input=None)
+    ON.set_point_ops(ref_cuda_ops)
+    try:
+        with torch.no_grad():
+            ref = ON.prior_forward({k: v.to(dev) for k, v in sd_l.items()}, ON.prior_spec(), x.to(dev), t.to(dev), style.to(dev))
+            refg = ON.global_prior_forward({k: v.to(dev) for k, v in sd_g.items()}, style.to(dev), t.to(dev))
+    finally:
+        ON.set_point_ops(point_ops)
+    coords = x.view(B, 2048, 4).permute(0, 2, 1)[:, :3].contiguous().cuda()
+    nc = coords - coords.mean(2, keepdim=True)
+    nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 0.0) + 0.5
+    vox_t = torch.round(torch.clamp(nc * 32, 0, 31)).to(torch.int32)
+    _, vox = F.voxel_coords(coords, 32)
+    rk = load_ref()
+    fps_ok = bool(torch.equal(furthest_point_sample_indices(coords, 1024).cpu(), rk.furthest_point_sampling(coords, 1024).cpu()))
+    print(json.dumps({"impl": "parity", "batch": B,
+                      "against": "reference eager path on the same GPU: oracle/net.py on CUDA (torch cuDNN TF32 convs, cuBLAS) + the reference's own pvcnn kernels (oracle/_ref)",
+                      "pvcnn2prior_step": {"max_abs_err_over_max_abs": rel_err(eps, ref), "rms_rel": rms_err(eps, ref), "tolerance": {"max": 1e-2, "rms": 4e-3}},
+                      "global_prior_step": {"max_abs_err_over_max_abs": rel_err(eg, refg), "tolerance": {"max": 2e-3}},
+                      "voxel_indices_equal_torch_cuda_level0": bool(torch.equal(vox, vox_t)),
+                      "fps_indices_equal_reference_kernel_level0": fps_ok,
+                      "note": "teacher-forced single step, random timesteps; the free-running 10-step loop is checked against the reference-generated golden in tests (0.2 max / 5e-2 rms: round / arg-max discontinuities amplify 1-ulp differences)"}))
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -257,8 +321,14 @@ def main():
     if args.impl == "reference-gpu":
         run_gpu_reference(args)
         return
+    if args.impl == "parity":
+        return run_parity(args)
     if args.impl == "reference":
         return run_reference_arm(args)
+    knobs = {k: v for k, v in os.environ.items() if k.startswith("LION_")}
+    if knobs and not args.allow_knobs:
+        sys.exit("bench.py: refusing to run with LION_* knobs set (%s); unset them or pass --allow-knobs "
+                 "(they are recorded in the JSON line either way)" % ", ".join(sorted(knobs)))
     import torch
     import torch.distributed as dist
     from lion_b200 import _lib as L
@@ -282,16 +352,39 @@ def main():
     dae, vae = build_models(cfg, dev)
     diff = DiffusionDiscretized(cfg.sde, None, cfg)
     shape = vae.latent_shape()
-    gathered = [torch.empty(B, N_POINTS, 3, device=dev) for _ in range(world)] if world > 1 else None
+    # the path's single collective: all_gather of the finished clouds, once per pass.  It is issued asynchronously
+    # (NCCL's own stream, double-buffered destination) and only waited for before the buffer is reused / at the end
+    # of the timed region, so a rank never idles at another rank's pass boundary (round 1 lost 1.7 % to rank skew
+    # absorbed there).
+    gathered = [[torch.empty(B, N_POINTS, 3, device=dev) for _ in range(world)] for _ in range(2)] if world > 1 else None
     launches = {"n": 0}
+    pending = [None, None]
+    pass_events = []                                      # (start, end of sampling, end of gather wait) per pass
 
-    def one_pass(seed):
+    def one_pass(seed, record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if record else None
+        if record:
+            ev[0].record()
         torch.manual_seed(seed * 1000 + rank)             # distinct noise per rank
         img, *_ = generate_samples_vada_2prior(shape, dae, diff, vae, B, False)
         launches["n"] += L.last_launches(dev)             # decoder pass (the sampling loops count themselves)
+        if record:
+            ev[1].record()
         if world > 1:
-            dist.all_gather(gathered, img.contiguous())   # the single collective of the path
+            slot = seed & 1
+            if pending[slot] is not None:
+                pending[slot].wait()                      # the buffer's previous gather (two passes ago) is done
+            pending[slot] = dist.all_gather(gathered[slot], img.contiguous(), async_op=True)
+        if record:
+            ev[2].record()
+            pass_events.append(ev)
         return img
+
+    def drain():
+        for i in (0, 1):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     def barrier():
         if world > 1:
@@ -301,6 +394,7 @@ def main():
     # ---- device-resident timing: K passes, CUDA events, max over ranks --------------------------
     for i in range(args.warmup):
         one_pass(i)
+    drain()
     barrier()
     launches["n"] = 0
     diff.total_gpu_launches = 0
@@ -311,7 +405,9 @@ def main():
     barrier()
     e0.record()
     for i in range(args.steps):
-        img = one_pass(100 + i)
+        img = one_pass(100 + i, record=True)
+    t_d0 = torch.cuda.Event(enable_timing=True); t_d0.record()
+    drain()                                               # every gather has landed: inside the timed region
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -323,6 +419,24 @@ def main():
     value = world * B * args.steps / (ms / 1000.0)
     n_launch = launches["n"] + diff.total_gpu_launches
     assert torch.isfinite(img).all()
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([[ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])] for ev in pass_events] +
+                            [[t_d0.elapsed_time(e1), 0.0]], device=dev)            # [steps+1, 2]
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        if rank == 0:
+            import statistics
+            samp = [[float(v) for v in r[:-1, 0]] for r in allr]
+            tot = [sum(x) for x in samp]
+            per_rank = {"pass_ms_per_rank_mean": [round(sum(x) / len(x), 2) for x in samp],
+                        "pass_ms_min_median_max_over_ranks": [round(min(map(min, samp)), 2), round(statistics.median([v for x in samp for v in x]), 2),
+                                                              round(max(map(max, samp)), 2)],
+                        "sampling_ms_total_per_rank": [round(v, 1) for v in tot],
+                        "skew_ms_total_max_minus_min": round(max(tot) - min(tot), 2),
+                        "allgather_enqueue_ms_per_rank_total": [round(float(r[:-1, 1].sum()), 3) for r in allr],
+                        "final_gather_drain_ms_per_rank": [round(float(r[-1, 0]), 3) for r in allr],
+                        "note": "the all_gather is asynchronous; ranks only meet in the final drain + barrier"}
 
     # ---- end to end: all noise from pinned host memory, result back to pinned host --------------
     e2e = None
@@ -375,7 +489,7 @@ def main():
                                                   given_noise=(dl[0], zl))
             pts = vae.sample(num_samples=B, decomposed_eps=vae.decompose_eps(vae.compose_eps([z_g, z_l])))
             if world > 1:
-                dist.all_gather(gathered, pts.contiguous())
+                dist.all_gather(gathered[0], pts.contiguous())
             hout.copy_(pts, non_blocking=True)
             torch.cuda.synchronize(dev)
 
@@ -407,6 +521,39 @@ def main():
         torch.cuda.synchronize(dev)
         phases = {"global_prior_loop_ms": ev[0].elapsed_time(ev[1]), "local_prior_loop_ms": ev[1].elapsed_time(ev[2]),
                   "decoder_ms": ev[2].elapsed_time(ev[3])}
+    # ---- the other single-node BASELINE configs: one timed pass each (after a 5-step warm-up run of the same modules)
+    extra = {}
+    if not args.no_extra_configs and T == T_STEPS:
+        def timed_pass(dae_, vae_, diff_, b, clip_feat=None):
+            cfg_w = default_prior_cfg(clip=clip_feat is not None, num_steps=5)
+            torch.manual_seed(77 + rank)
+            generate_samples_vada_2prior(shape, dae_, DiffusionDiscretized(cfg_w.sde, None, cfg_w), vae_, b, False, clip_feat=clip_feat)
+            barrier()
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            im, *_ = generate_samples_vada_2prior(shape, dae_, diff_, vae_, b, False, clip_feat=clip_feat)
+            if world > 1:
+                dist.all_gather([torch.empty_like(im) for _ in range(world)], im.contiguous())
+            z.record()
+            barrier()
+            assert torch.isfinite(im).all()
+            tt = torch.tensor([a.elapsed_time(z)], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return tt.item()
+        if world == 1:
+            cfg_c = default_prior_cfg(clip=True, num_steps=T)
+            dae_c, vae_c = build_models(cfg_c, dev, clip=True)
+            cf = torch.randn(B, 512, generator=torch.Generator().manual_seed(7)).to(dev)
+            ms_c = timed_pass(dae_c, vae_c, DiffusionDiscretized(cfg_c.sde, None, cfg_c), B, clip_feat=cf)
+            extra["configs[3] car prior + CLIP-conditioned AdaGN (PriorSEClip, clip_feat = randn[B,512]), batch %d, 1 GPU" % B] = {
+                "value": B / (ms_c / 1000.0), "unit": "shapes/s", "ms_per_pass": ms_c, "passes": 1}
+            del dae_c, vae_c
+        if world == 4:
+            ms_4 = timed_pass(dae, vae, diff, 16)
+            extra["configs[2] chair prior, batch 64 over 4 GPUs (16 per rank), 1000 steps"] = {
+                "value": 64 / (ms_4 / 1000.0), "unit": "shapes/s", "ms_per_pass": ms_4, "passes": 1,
+                "note": "chair / car / airplane priors share one architecture (SURVEY.md 8d); weights are synthetic either way"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -442,18 +589,32 @@ def main():
         v, detail = cpu_reference_sample(2, 2)
         cpu = {"value": v, "unit": "shapes/s", "cores": cpu_threads(), "kind": "port", "sample": CPU_SAMPLE % (2, 2), "detail": detail}
 
-    # GPU-side reference port (informational): oracle/net.py on CUDA + the reference's own point kernels, in a
-    # child process (the reference kernels exit() on a launch error; nothing there may take this line down)
+    def child(cmd, timeout):
+        """run a helper in a child process (the reference's kernels exit() on a launch error; nothing there may take
+        this line down) and parse its last JSON line"""
+        try:
+            env = {k: v for k, v in os.environ.items() if not k.startswith(("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_", "TORCHELASTIC", "GROUP_"))}
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+            rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            return json.loads(rows[-1]) if rows else {"unavailable": (r.stderr or "no output")[-400:]}
+        except Exception as e:      # noqa: BLE001
+            return {"unavailable": repr(e)[:300]}
+
+    # the UNMODIFIED reference on this GPU (full 1000 + 1000 steps at the same batch), else the oracle's eager port
     gpu_ref = None
     if world == 1 and not args.no_gpu_baseline:
-        try:
-            import subprocess
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--batch", str(B)],
-                               capture_output=True, text=True, timeout=200)
-            rows = [l for l in r.stdout.splitlines() if l.startswith("{")]
-            gpu_ref = json.loads(rows[-1]) if rows else {"unavailable": (r.stderr or "no output")[-300:]}
-        except Exception as e:      # noqa: BLE001
-            gpu_ref = {"unavailable": repr(e)[:300]}
+        torch.cuda.empty_cache()
+        if os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "LION", "models")) and T == T_STEPS:
+            gpu_ref = child([sys.executable, os.path.join(ROOT, "baseline", "ref_gpu_arm.py"), "--batch", str(B), "--steps", str(T)], 600)
+        if gpu_ref is None or "unavailable" in gpu_ref:
+            port = child([sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu", "--batch", str(B)], 200)
+            if gpu_ref is not None:
+                port["reference_tree_failed"] = gpu_ref["unavailable"]
+            gpu_ref = port
+    parity = None
+    if world == 1 and not args.no_parity:
+        torch.cuda.empty_cache()
+        parity = child([sys.executable, os.path.abspath(__file__), "--impl", "parity", "--batch", str(B)], 300)
 
     line = {"metric": "shapes/sec (1000-step DDPM, 2048 latent pts, B=32)", "value": value, "unit": "shapes/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -466,7 +627,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch,
             "ms_per_denoise_step_pair": ms / args.steps / T,
             "tensor_roofline_frac_whole_job": (value * GFLOP_PER_SHAPE / 1e3 / world / (bf16_peak / 2.0)) if T == T_STEPS else None,
-            "phases": phases, "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_ref}
+            "phases": phases, "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_ref, "parity": parity,
+            "extra_configs": extra, "per_rank": per_rank, "env": knobs}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

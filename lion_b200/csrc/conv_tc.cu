@@ -201,7 +201,6 @@ struct Params {
   int a_stages;          // depth of the A ring
   const unsigned char* occ;   // 64-row occupancy flags of the input (sparse first conv of a PVConv) or null
   int occ_stride;
-  int debug;             // bring-up experiments (LION_TC_DEBUG): 1 no global loads, 2 no MMAs, 4 no epilogue stores/stats
 };
 
 // per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
@@ -340,11 +339,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             const uint32_t full = bar_full_a + 8 * sa;
             if (lane == 0) {
               s_skip[sa] = empty ? 1u : 0u;
-              if (empty || (P.debug & 1)) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
+              if (empty) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
               else mbar_expect_tx(full, nbytes * kg_real);
             }
             __syncwarp();
-            if (!empty && !(P.debug & 1) && lane < kg_real)
+            if (!empty && lane < kg_real)
               bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, nbytes, full);
             if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
           }
@@ -467,7 +466,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = valid ? __uint_as_float(rr[cc][i]) + s_bias[col + i] : 0.0f;
-              if (inrange && !(P.debug & 4)) {
+              if (inrange) {
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
                   int g = (n0 + col) / 4 + g4;
@@ -480,7 +479,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             }
           }
         }
-        if (P.ssum && !(P.debug & 4)) {
+        if (P.ssum) {
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             if (cc * 16 < CH) {
@@ -507,7 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + col), v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = valid ? v[i] + s_bias[col + i] : 0.0f;
-          if (inrange && !(P.debug & 4)) {
+          if (inrange) {
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
               int g = (n0 + col) / 4 + g4;
@@ -515,7 +514,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
                 P.out[((size_t)b * P.Gout_store + g) * P.rows + p] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
             }
           }
-          if (P.ssum && !(P.debug & 4)) {
+          if (P.ssum) {
             float sq[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
@@ -1069,7 +1068,6 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("LION_TC_DEBUG"); dbg = e ? atoi(e) : 0; } P.debug = dbg; }
   const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128;
   long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
   int a_stages = (int)(room / P.a_stage_bytes);

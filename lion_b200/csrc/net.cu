@@ -274,11 +274,6 @@ static ConvGeom geom_grid(int r) {
 static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store,
                     double* ssum, double* ssq, const ConvGeom& geo) {
   if (Gin * 4 != w.cin_pad) { set_error("conv: input has %d channels, weights expect %d", Gin * 4, w.cin_pad); return LION_ERR_ARG; }
-  { // timing experiments only (results are garbage): LION_SKIP_CONV=1 skips 3x3x3 convs, =2 skips all convs
-    static int skip = -1;
-    if (skip < 0) { const char* e = getenv("LION_SKIP_CONV"); skip = e ? atoi(e) : 0; }
-    if (skip == 2 || (skip == 1 && geo.ntaps == 27)) return 0;
-  }
   if (conv_tc_usable(w, geo))
     return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B);
   int span = geo.p_end - geo.p_begin;
