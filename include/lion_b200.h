@@ -24,6 +24,10 @@ int lion_ctx_create(int device, LionCtx** out);
 int lion_ctx_destroy(LionCtx* ctx);
 /* kernels launched by the last network-level call on this context (bench.py: gpu_launches) */
 int lion_ctx_last_launches(LionCtx* ctx);
+/* Scratch-arena generation: bumped whenever a call had to re-allocate the per-device arena or zero grid.  A CUDA graph
+ * captured on this context has the arena addresses baked in; it must not be replayed once the generation changed
+ * (lion_b200._lib.capture_graph checks this and raises). */
+unsigned lion_ctx_generation(LionCtx* ctx);
 size_t lion_ctx_arena_bytes(LionCtx* ctx);
 /* device scratch the context currently owns (arena + persistent zero grid).  Entry points size it with a dry
  * pass and grow it on demand -- outside stream capture: run one eager call per shape before capturing. */
@@ -81,6 +85,11 @@ int lion_model_refresh(LionModel* m);
  * out [B,N,num_classes] point-major. */
 int lion_unet_forward(LionModel* m, const float* x, const float* t, const float* style, const float* clip, float* out,
                       int B, int N, void* stream);
+/* Hoist of the step-invariant part of PVCNN2Unet.forward out of the sampling loop: the CLIP mixing
+ * (models/latent_points_ada.py:132-137) and the 61 AdaGN style Linears (models/adagn.py:59-61) are evaluated once for
+ * style [B,S] (+ clip [B,clip_dim] or NULL) into a buffer owned by the model; lion_unet_forward calls with style == NULL
+ * (same B) then skip them.  Values are identical to recomputing them every step. */
+int lion_unet_cache_style(LionModel* m, const float* style, const float* clip, int B, void* stream);
 /* PVConv.forward (models/pvcnn2_ada.py:235-280): features [B,Cin,N], coords [B,3,N] -> out [B,Cout,N] */
 int lion_pvconv_fwd(LionModel* m, const float* features, const float* coords, const float* style, float* out,
                     int B, int N, void* stream);

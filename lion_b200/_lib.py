@@ -32,6 +32,7 @@ def _proto(lib):
         "lion_ctx_destroy": (P(vp), i),
         "lion_ctx_last_launches": (P(vp), i),
         "lion_ctx_arena_bytes": (P(vp), sz),
+        "lion_ctx_generation": (P(vp), C.c_uint),
         "lion_avg_voxelize": (P(vp, vp, vp, vp, vp, i, i, i, i, vp), i),
         "lion_trilinear_devoxelize": (P(vp, vp, vp, vp, vp, i, i, i, i, i, vp), i),
         "lion_furthest_point_sampling": (P(vp, vp, i, i, i, vp), i),
@@ -44,6 +45,7 @@ def _proto(lib):
         "lion_model_destroy": (P(vp), i),
         "lion_model_refresh": (P(vp), i),
         "lion_unet_forward": (P(vp, vp, vp, vp, vp, vp, i, i, vp), i),
+        "lion_unet_cache_style": (P(vp, vp, vp, i, vp), i),
         "lion_pvconv_fwd": (P(vp, vp, vp, vp, vp, i, i, vp), i),
         "lion_sa_module_fwd": (P(vp, vp, vp, vp, vp, vp, i, i, vp), i),
         "lion_fp_module_fwd": (P(vp, vp, vp, vp, vp, vp, vp, i, i, i, vp), i),
@@ -178,6 +180,14 @@ class Model:
         with torch.cuda.device(self.device):
             check(lib().lion_model_refresh(self.h), "model_refresh")
 
+    # The handle is a per-process device object: copies (copy.deepcopy(module) for an EMA twin, torch.save(module),
+    # pickling) must not carry it.  The copy gets None in place of the Model and rebuilds lazily on its first forward.
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (type(None), ())
+
 
 def model_for(module, kind, desc, params):
     """Cached Model of an nn.Module; tracks load_state_dict / .cuda() / in-place updates."""
@@ -191,6 +201,7 @@ def model_for(module, kind, desc, params):
         if vers != m.versions:
             m.refresh()
             m.versions = vers
+            m.style_key = None        # cached AdaGN style Linears were computed with the old weights
     return m
 
 
@@ -203,20 +214,32 @@ class capture_graph:
     def __init__(self):
         self.graph = torch.cuda.CUDAGraph()
         self.stream = torch.cuda.Stream()
+        self.generation = None
 
     def __enter__(self):
         self.stream.wait_stream(torch.cuda.current_stream())
         self._ctx = torch.cuda.stream(self.stream)
         self._ctx.__enter__()
         self.graph.capture_begin()
-        return self.graph
+        return self
 
     def __exit__(self, et, ev, tb):
         try:
-            if et is None:
-                self.graph.capture_end()
+            try:
+                self.graph.capture_end()          # also on an exception: never leave the stream in capture mode
+            except Exception:
+                if et is None:
+                    raise
         finally:
             self._ctx.__exit__(et, ev, tb)
         if et is None:
             torch.cuda.current_stream().wait_stream(self.stream)
+            self.generation = lib().lion_ctx_generation(ctx())
         return False
+
+    def replay(self):
+        """The captured launches have the scratch-arena addresses baked in: refuse to replay once a later eager call
+        re-allocated the arena (use-after-free otherwise)."""
+        if lib().lion_ctx_generation(ctx()) != self.generation:
+            raise LionError("lion_b200: the scratch arena was re-allocated after this CUDA graph was captured; capture it again")
+        self.graph.replay()

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <mutex>
 
 namespace lion {
 
@@ -61,6 +62,8 @@ struct Ctx {
   size_t cap = 0;
   size_t off = 0;
   size_t peak = 0;
+  unsigned generation = 0;   // bumped whenever the arena / zero grid moves: graphs captured before are stale
+  std::mutex* mu = nullptr;  // one forward at a time per context (ctypes releases the GIL); owned by LionCtx
   bool dry = false;
   bool pdl = false;          // programmatic dependent launch (LION_PDL=1 enables; measured: no gain in graphs)
   int launches = 0;          // kernels launched by the last real pass (gpu_launches evidence)
@@ -124,6 +127,20 @@ inline int check_launch(Ctx* c, const char* what) {
   }
   return 0;
 }
+
+// "opt this kernel into > 48 KB of dynamic shared memory" is a PER-DEVICE attribute: a process-wide once-flag would
+// skip the opt-in on the second GPU of a multi-device process.  DevOnce keeps one flag per device ordinal.
+struct DevOnce {
+  unsigned long long done[4] = {0, 0, 0, 0};     // 256 device ordinals
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 256) return true;
+    unsigned long long bit = 1ull << (d & 63);
+    if (done[d >> 6] & bit) return false;
+    done[d >> 6] |= bit;
+    return true;
+  }
+};
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t cdivz(size_t a, size_t b) { return (a + b - 1) / b; }

@@ -201,7 +201,56 @@ struct Params {
   int a_stages;          // depth of the A ring
   const unsigned char* occ;   // 64-row occupancy flags of the input (sparse first conv of a PVConv) or null
   int occ_stride;
+  AffineJob aff;              // AdaGN fold computed by the last CTA to finish (aff.scale == nullptr: none)
 };
+
+// The AdaGN (+SE) fold of models/adagn.py:45-65 / models/pvcnn2_ada.py:27-41 for all (b, c) of this convolution's
+// output, run by the last CTA once every CTA's GroupNorm statistics have landed: GroupNorm(8, C, eps 1e-5, affine)
+// followed by *factor + bias collapses to y = scale[b][c]*x + shift[b][c]; SE3d needs only the per-channel mean of y,
+// which is affine in the per-channel mean of x, so its gate folds in as well.  Group sums run in channel order
+// (deterministic).  sm: >= B*C + B*C/8 floats of shared memory.  Called by all threads of the CTA.
+__device__ __noinline__ void affine_tail(const AffineJob& J, const double* ssum, const double* ssq, int stat_stride, int B, float* sm) {
+  const int C = J.C, cpg = C / 8, tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < B * C; i += nt) {
+    const int b = i / C, c = i - b * C, c0 = (c / cpg) * cpg;
+    const double* ps = ssum + (size_t)b * stat_stride + c0;
+    const double* pq = ssq + (size_t)b * stat_stride + c0;
+    double gs = 0.0, gq = 0.0;
+    for (int k = 0; k < cpg; ++k) { gs += __ldcg(ps + k); gq += __ldcg(pq + k); }
+    const double n = J.count * cpg;
+    const double mean = gs / n;
+    double var = gq / n - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float f = J.fb[(size_t)b * J.fb_stride + c], bb = J.fb[(size_t)b * J.fb_stride + C + c];
+    const float ga = J.gamma[c], be = J.beta[c];
+    const float sc = rstd * ga * f;
+    const float sh = (be - (float)mean * rstd * ga) * f + bb;
+    J.scale[i] = sc;
+    J.shift[i] = sh;
+    if (J.se_w1) sm[i] = sc * (float)(__ldcg(ssum + (size_t)b * stat_stride + c) / J.count) + sh;   // mean over voxels of the AdaGN output
+  }
+  if (J.se_w1) {
+    const int H = C / 8;
+    float* s_h = sm + B * C;
+    __syncthreads();
+    for (int i = tid; i < B * H; i += nt) {
+      const int b = i / H, h = i - b * H;
+      float a = 0.0f;
+      for (int k = 0; k < C; ++k) a = fmaf(J.se_w1[h * C + k], sm[b * C + k], a);
+      s_h[i] = fmaxf(a, 0.0f);
+    }
+    __syncthreads();
+    for (int i = tid; i < B * C; i += nt) {
+      const int b = i / C, c = i - b * C;
+      float a = 0.0f;
+      for (int k = 0; k < H; ++k) a = fmaf(J.se_w2[c * H + k], s_h[b * H + k], a);
+      const float gate = 1.0f / (1.0f + expf(-a));
+      J.scale[i] *= gate;
+      J.shift[i] *= gate;
+    }
+  }
+}
 
 // per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
 // in: v[32] (this lane's row, 32 channels); cost 31 shuffles instead of 160.
@@ -554,9 +603,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   }
 #undef ITEM_DECODE
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (P.aff.scale) __threadfence();                 // this thread's statistics atomics are visible device-wide
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+  if (P.aff.scale) {
+    // last CTA to arrive folds GroupNorm + style (+ SE) into per-(b, c) scale / shift: saves one launch per layer
+    volatile uint32_t* s_last = s_tmem;
+    if (tid == 0) *s_last = (atomicAdd(P.aff.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (*s_last) {
+      __threadfence();
+      affine_tail(P.aff, P.ssum, P.ssq, P.cout_pad, P.B, (float*)smem);
+    }
   }
 }
 
@@ -585,348 +645,6 @@ __global__ void k_pack_tc(const float* __restrict__ wt, float* __restrict__ w, i
   w[i] = __uint_as_float(u);
 }
 
-// =====================================================================================
-// EXPERIMENTAL, OFF BY DEFAULT (LION_TC_STACK=1) -- NOT YET RUN ON HARDWARE (written after the
-// round-1 GPU budget was spent; first item of round 2).  Tap stacking along N, see DESIGN.md
-// section 7 and tests/test_tap_stacking_algebra.py (numpy model of exactly this scheme).
-//
-// The validated kernel above is bound by the tensor core's shared-memory operand reads: one
-// M128 x N64 x K8 UMMA reads 4 KB of A + 2 KB of B per 32 cycles (192 B/clk against 128 B/clk).
-// Here the S taps (dy, dz = 0..S-1) of one (dx, dy) share ONE A view (shifted by the offset of
-// the dz = 0 tap) and their weights are concatenated along N (UMMA N = S*NT <= 256), so the A
-// bytes are read once per S taps.  Column block c of the accumulator then holds the contribution
-// of tap dz = c to output row (p - c); the epilogue folds out[q] = sum_c D_c[q + c] with lane
-// shuffles plus a small shared-memory exchange between the four TMEM lane quarters.  The last
-// S-1 rows of a tile are incomplete, so row tiles advance by 128-(S-1) rows.  Taps that do not
-// fit the stack (S = 2: dz = 2) run as plain N = NT UMMAs into column block 0.
-// Everything else (producer, barrier protocol, sparse-slab skipping, statistics) follows k_conv_tc.
-// =====================================================================================
-struct ParamsS {
-  const float4* in; const float* w; const float* bias; float4* out; double* ssum; double* ssq;
-  int Gin, Gout_store, cout_pad;
-  int rows, p_begin, p_end, rp;
-  int tg_off[3];
-  int halo;
-  int KG, nchunk, NT;
-  int G, B;
-  int a_stage_bytes, b_stage_bytes, stage_rows, a_stages;
-  const unsigned char* occ; int occ_stride;
-};
-
-constexpr int XCH_FLOATS = 2 * 4 * 2 * 3 * 16;      // [parity][lane quarter][column half][exchanged row][16 columns]
-
-template <int KG, int S>
-__global__ void __launch_bounds__(THREADS, 1) k_conv_stack(ParamsS P) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sA = smem;
-  const int A_STAGES = P.a_stages;
-  uint8_t* sB = sA + (size_t)A_STAGES * P.a_stage_bytes;
-  float* s_bias = (float*)(sB + (size_t)B_STAGES * P.b_stage_bytes);
-  float* s_stat = s_bias + 128;                 // [8 epilogue warps][2][64]
-  float* s_xch = s_stat + 8 * 2 * 64;           // [XCH_FLOATS]
-  uint64_t* bars = (uint64_t*)(s_xch + XCH_FLOATS);
-  uint32_t* s_tmem = (uint32_t*)(bars + 64);
-  volatile uint32_t* s_skip = s_tmem + 1;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int TP = 128 - (S - 1);             // row pitch of the tiles
-  const int SN = S * P.NT;                      // accumulator columns per tile
-
-  const uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + MAX_A_STAGES);
-  const uint32_t bar_full_b = smem_u32(bars + 2 * MAX_A_STAGES), bar_empty_b = smem_u32(bars + 2 * MAX_A_STAGES + B_STAGES);
-  const uint32_t bar_accf = smem_u32(bars + 2 * MAX_A_STAGES + 2 * B_STAGES);
-  const uint32_t bar_tfree = bar_accf + 8 * MAX_ACC;
-
-  if (P.Gin % KG != 0)
-    for (int i = tid; i < A_STAGES * P.a_stage_bytes / 16; i += THREADS) ((float4*)sA)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (tid == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(bar_full_a + 8 * i, 1); mbar_init(bar_empty_a + 8 * i, 2); }
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(bar_full_b + 8 * i, 1); mbar_init(bar_empty_b + 8 * i, 2); }
-    for (int i = 0; i < MAX_ACC; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_tfree + 8 * i, EPI_WARPS); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *s_tmem;
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  const int ntile_total = (P.p_end - P.p_begin + TP - 1) / TP;
-  const int ngrp = (ntile_total + P.G - 1) / P.G;
-  const int n_nt = P.cout_pad / P.NT;
-  const int n_items = ngrp * n_nt * P.B;
-#define ITEM_DECODE_S(w)                                                \
-  const int grp = (w) % ngrp; const int nt = ((w) / ngrp) % n_nt; const int b = (w) / (ngrp * n_nt); \
-  const int tile0 = grp * P.G; const int ntile = min(P.G, ntile_total - tile0); const int n0 = nt * P.NT;
-
-  if (warp == 0) {
-    // ===================== producer: identical to k_conv_tc except for the tile pitch ==========
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
-    const uint32_t bytes = (uint32_t)P.stage_rows * 16u;
-    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      ITEM_DECODE_S(w)
-      (void)n0;
-      const float* wsrc = P.w + (size_t)nt * P.nchunk * 3 * (P.b_stage_bytes / 4);
-      const unsigned char* occ_b = P.occ ? P.occ + (size_t)b * P.occ_stride : nullptr;
-      const long long row_item = (long long)P.p_begin + (long long)tile0 * TP - P.halo;
-      const float4* in_item = P.in + (size_t)b * P.Gin * P.rows;
-      for (int cc = 0; cc < P.nchunk; ++cc) {
-        const int kg_real = min(KG, P.Gin - cc * KG);
-        const float4* in_lane = in_item + (size_t)(cc * KG + (lane < kg_real ? lane : 0)) * P.rows;
-        for (int tg = 0; tg < 3; ++tg) {
-          const bool may_skip = occ_b && !(cc == P.nchunk - 1 && tg == 2);
-          mbar_wait(bar_empty_b + 8 * sb, pb ^ 1);
-          if (lane == 0) {
-            mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
-            bulk_g2s(sB_addr + sb * (uint32_t)P.b_stage_bytes, wsrc + (size_t)(cc * 3 + tg) * (P.b_stage_bytes / 4),
-                     P.b_stage_bytes, bar_full_b + 8 * sb);
-          }
-          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
-          long long row0 = row_item + P.tg_off[tg];
-          for (int j = 0; j < ntile; ++j, row0 += TP) {
-            mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
-            bool empty = false;
-            if (may_skip) {
-              long long lo = row0 < 0 ? 0 : row0, hi = row0 + P.stage_rows - 1;
-              if (hi > P.rows - 1) hi = P.rows - 1;
-              unsigned any = 0;
-              for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(occ_b + k);
-              empty = (any == 0);
-            }
-            const uint32_t full = bar_full_a + 8 * sa;
-            if (lane == 0) {
-              s_skip[sa] = empty ? 1u : 0u;
-              if (empty) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
-              else mbar_expect_tx(full, bytes * kg_real);
-            }
-            __syncwarp();
-            if (!empty && lane < kg_real)
-              bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, bytes, full);
-            if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1 || warp == 2) {
-    // ===================== MMA issuers (even / odd row tiles) ================================
-    const int me = warp - 1;
-    const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SN >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc_1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t a_pitch16 = (uint32_t)P.stage_rows;
-    const uint32_t bs_pitch16 = (uint32_t)SN;            // k-group pitch inside a stacked block
-    const uint32_t b1_pitch16 = (uint32_t)P.NT;          // ... inside a single-tap block
-    const uint32_t b_dy16 = 3u * KG * (uint32_t)P.NT;    // one dy: [stack KG x S*NT][singles (3-S) x KG x NT]
-    const uint32_t d_hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_lo_c = (a_pitch16 & 0x3fff) << 16, bs_lo_c = (bs_pitch16 & 0x3fff) << 16, b1_lo_c = (b1_pitch16 & 0x3fff) << 16;
-    const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4;
-    const uint32_t a_ring16 = (smem_u32(sA) >> 4) + (uint32_t)P.halo;
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      ITEM_DECODE_S(w)
-      (void)b; (void)n0; (void)tile0;
-      uint32_t started = 0;
-      for (int j = me; j < MAX_ACC; j += 2)
-        if (j >= ntile) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);
-      for (int cc = 0; cc < P.nchunk; ++cc) {
-        for (int tg = 0; tg < 3; ++tg) {
-          mbar_wait(bar_full_b + 8 * sb, pb);
-          const uint32_t b_base16 = smem_u32(sB + (size_t)sb * P.b_stage_bytes) >> 4;
-          const bool first = (cc | tg) == 0;
-          const bool last = (cc == P.nchunk - 1) && (tg == 2);
-          for (int j = 0; j < ntile; ++j) {
-            const uint32_t my_sa = sa, my_pa = pa;
-            if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
-            mbar_wait(bar_full_a + 8 * my_sa, my_pa);     // both issuers observe every phase (see k_conv_tc)
-            if ((j & 1) != me) { mbar_arrive_w(bar_empty_a + 8 * my_sa); continue; }
-            if (first) mbar_wait(bar_tfree + 8 * j, (it & 1) ^ 1);
-            if (s_skip[my_sa]) { mbar_arrive_w(bar_empty_a + 8 * my_sa); continue; }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_base16 = a_ring16 + my_sa * a_stage16;
-            const uint32_t d = tmem_base + (uint32_t)(j * SN);
-            const bool fresh = ((started >> j) & 1u) == 0;
-            started |= 1u << j;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const uint32_t b_dy = b_base16 + dy * b_dy16;
-              {   // taps dz = 0..S-1 stacked along N; A view of the dz = 0 tap
-                const uint32_t a_t = a_base16 + (uint32_t)((dy - 1) * P.rp - 1);
-#pragma unroll
-                for (int k2 = 0; k2 < KG; k2 += 2) {
-                  uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
-                  uint32_t blo = bs_lo_c | ((b_dy + k2 * bs_pitch16) & 0x3fff);
-                  uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
-                  umma_tf32_w(d, ad, bd, idesc_s, (fresh && dy == 0 && k2 == 0) ? 0u : 1u);
-                }
-              }
-#pragma unroll
-              for (int dz = S; dz < 3; ++dz) {   // taps outside the stack: plain N = NT UMMAs into column block 0
-                const uint32_t a_t = a_base16 + (uint32_t)((dy - 1) * P.rp + (dz - 1));
-                const uint32_t b_t = b_dy + (uint32_t)KG * bs_pitch16 + (uint32_t)(dz - S) * KG * b1_pitch16;
-#pragma unroll
-                for (int k2 = 0; k2 < KG; k2 += 2) {
-                  uint32_t alo = a_lo_c | ((a_t + k2 * a_pitch16) & 0x3fff);
-                  uint32_t blo = b1_lo_c | ((b_t + k2 * b1_pitch16) & 0x3fff);
-                  uint64_t ad = ((uint64_t)d_hi << 32) | alo, bd = ((uint64_t)d_hi << 32) | blo;
-                  umma_tf32_w(d, ad, bd, idesc_1, 1u);
-                }
-              }
-            }
-            umma_commit_w(bar_empty_a + 8 * my_sa);
-            if (last) umma_commit_w(bar_accf + 8 * j);
-          }
-          umma_commit_w(bar_empty_b + 8 * sb);
-          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
-        }
-      }
-      for (int j = me; j < MAX_ACC; j += 2)
-        if (j >= ntile) umma_commit_w(bar_accf + 8 * j);
-    }
-  } else {
-    // ===================== epilogue: 4 TMEM lane quarters x 2 column halves ====================
-    const int ew = warp - 3, et = tid - 96;
-    const int q = warp & 3;
-    const int h = ew >> 2;
-    const int CH = P.NT / 2;
-    const int hcol = h * CH;
-    uint32_t it = 0, xpar = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      ITEM_DECODE_S(w)
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et < P.NT) s_bias[et] = P.bias ? P.bias[n0 + et] : 0.0f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};
-      for (int j = 0; j < ntile; ++j) {
-        const int lt = q * 32 + lane;                               // row inside the tile
-        const int p = P.p_begin + (tile0 + j) * TP + lt;
-        const bool inrange = (lt < TP) && (p < P.p_end);
-        bool valid = inrange;
-        if (P.rp > 0 && inrange) {
-          int z = p % P.rp, y = (p / P.rp) % P.rp;
-          valid = (z >= 1 && z <= P.rp - 2 && y >= 1 && y <= P.rp - 2);
-        }
-        mbar_wait(bar_accf + 8 * j, it & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int c16 = 0; c16 < CH; c16 += 16, xpar ^= 1u) {
-          const int col = hcol + c16;
-          uint32_t rr[S][16];
-#pragma unroll
-          for (int c = 0; c < S; ++c)
-            tmem_ld16_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * SN + c * P.NT + col), rr[c]);
-#pragma unroll
-          for (int c = 0; c < S; ++c) tmem_ld16_wait(rr[c]);
-          // rows (lane < c) of column block c belong to the previous lane quarter's last rows
-          float* xw = s_xch + ((xpar * 4 + q) * 2 + h) * 48;          // [3 rows][16]
-#pragma unroll
-          for (int c = 1; c < S; ++c) {
-            if (q > 0 && lane < c) {
-              const int slot = (c == 1) ? 0 : 1 + lane;               // c = 1: row 0;  c = 2: rows 0, 1
-#pragma unroll
-              for (int i = 0; i < 16; ++i) xw[slot * 16 + i] = __uint_as_float(rr[c][i]);
-            }
-          }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const float* xr = s_xch + ((xpar * 4 + (q + 1)) * 2 + h) * 48;   // next quarter's rows (q < 3 only)
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float acc = __uint_as_float(rr[0][i]);
-#pragma unroll
-            for (int c = 1; c < S; ++c) {
-              float sh = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[c][i]), c);
-              if (lane + c >= 32) {
-                const int slot = (c == 1) ? 0 : 1 + (lane + c - 32);
-                sh = (q < 3) ? xr[slot * 16 + i] : 0.0f;             // q == 3: rows >= TP, never stored
-              }
-              acc += sh;
-            }
-            v[i] = valid ? acc + s_bias[col + i] : 0.0f;
-          }
-          if (inrange) {
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-              int g = (n0 + col) / 4 + g4;
-              if (g < P.Gout_store)
-                P.out[((size_t)b * P.Gout_store + g) * P.rows + p] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
-            }
-          }
-          if (P.ssum) {
-            float sq[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
-            run_s[c16 >> 4] += warp_transpose_sum16(v, lane);
-            run_q[c16 >> 4] += warp_transpose_sum16(sq, lane);
-          }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree + 8 * j) : "memory");
-      }
-      if (P.ssum) {
-        if ((lane & 1) == 0) {
-          for (int k = 0; k < CH / 16; ++k) {
-            s_stat[(ew * 2 + 0) * 64 + k * 16 + ch16_of_lane(lane)] = run_s[k];
-            s_stat[(ew * 2 + 1) * 64 + k * 16 + ch16_of_lane(lane)] = run_q[k];
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et < P.NT) {
-          const int half = et / CH, ch = et % CH;
-          float s = 0.f, qq = 0.f;
-#pragma unroll
-          for (int ww = 0; ww < 4; ++ww) { s += s_stat[((half * 4 + ww) * 2 + 0) * 64 + ch]; qq += s_stat[((half * 4 + ww) * 2 + 1) * 64 + ch]; }
-          atomicAdd(P.ssum + (size_t)b * P.cout_pad + n0 + et, (double)s);
-          atomicAdd(P.ssq + (size_t)b * P.cout_pad + n0 + et, (double)qq);
-        }
-      }
-      for (int j = ntile; j < MAX_ACC; ++j) {
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree + 8 * j) : "memory");
-      }
-    }
-  }
-#undef ITEM_DECODE_S
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-  }
-}
-
-// stacked weight layout: w[nt][chunk][dx][dy]{ stack [kg][dz < S][n][4] with n fastest inside dz, then
-// singles dz = S..2: [kg][n][4] }, TF32 (rna)
-__global__ void k_pack_tc_stack(const float* __restrict__ wt, float* __restrict__ w, int cin_pad, int cout_pad,
-                                int NT, int nchunk, int KG, int S) {
-  pdl_prologue();
-  const size_t per_dy = (size_t)3 * KG * NT;                      // (kg, n) pairs per dy
-  size_t total = (size_t)(cout_pad / NT) * nchunk * 3 * 3 * per_dy * 4;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int jj = i % 4;
-  size_t r = i / 4;
-  int e = (int)(r % per_dy); r /= per_dy;
-  int dy = r % 3; r /= 3;
-  int dx = r % 3; r /= 3;
-  int cc = r % nchunk; r /= nchunk;
-  int nt = (int)r;
-  int kg, n, dz;
-  if (e < KG * S * NT) { kg = e / (S * NT); int n2 = e % (S * NT); dz = n2 / NT; n = n2 % NT; }
-  else { int e2 = e - KG * S * NT; dz = S + e2 / (KG * NT); int e3 = e2 % (KG * NT); kg = e3 / NT; n = e3 % NT; }
-  int tap = (dx * 3 + dy) * 3 + dz;
-  int ci = (cc * KG + kg) * 4 + jj;
-  float v = 0.0f;
-  if (ci < cin_pad) v = wt[((size_t)tap * cin_pad + ci) * cout_pad + nt * NT + n];
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  w[i] = __uint_as_float(u);
-}
-
 }  // namespace tc
 
 static int tc_mode() {      // 1 = tensor cores (default), 0 = SIMT only (LION_CONV_IMPL=simt; bring-up/debug)
@@ -936,17 +654,6 @@ static int tc_mode() {      // 1 = tensor cores (default), 0 = SIMT only (LION_C
     mode = (e && strcmp(e, "simt") == 0) ? 0 : 1;
   }
   return mode;
-}
-
-static int stack_mode() {   // LION_TC_STACK=1: experimental tap-stacked kernel for the 3x3x3 convolutions (not yet run on hardware)
-  static int mode = -1;
-  if (mode < 0) { const char* e = getenv("LION_TC_STACK"); mode = (e && atoi(e) != 0) ? 1 : 0; }
-  return mode;
-}
-static int stack_factor(int NT) {   // UMMA N = S*NT <= 256;  LION_TC_STACK=2 forces pairs (+ single dz=2 taps) for NT <= 64 as well
-  const char* e = getenv("LION_TC_STACK");
-  const int want = e ? atoi(e) : 3;
-  return (NT <= 64 && want != 2) ? 3 : 2;
 }
 
 static void tc_shape(const ConvW& w, int& NT, int& KG, int& nchunk, int& ntg, int& tpg) {
@@ -979,12 +686,6 @@ int conv_tc_prepare(Model* m, ConvW& w) {
   PackJob j{2, w.wt, nullptr, w.tc.w, w.ntaps, w.cin_pad, w.cout_pad, NT, 0};
   j.kmap = nullptr;
   m->jobs.push_back(j);
-  if (stack_mode() && w.ntaps == 27) {      // same size, different order
-    LION_TRY(m->dmalloc(&w.tc.ws, total));
-    w.tc.stack = stack_factor(NT);
-    PackJob js{3, w.wt, nullptr, w.tc.ws, w.ntaps, w.cin_pad, w.cout_pad, NT, w.tc.stack};
-    m->jobs.push_back(js);
-  }
   return 0;
 }
 
@@ -994,10 +695,6 @@ int conv_tc_pack_job(const PackJob& j) {
   int NT, KG, nchunk, ntg, tpg;
   tc_shape(tmp, NT, KG, nchunk, ntg, tpg);
   size_t total = (size_t)(j.c / NT) * nchunk * ntg * tpg * KG * NT * 4;
-  if (j.type == 3) {
-    tc::k_pack_tc_stack<<<(unsigned)cdivz(total, 256), 256>>>(j.src, j.dst, j.b, j.c, NT, nchunk, KG, j.e);
-    return 0;
-  }
   tc::k_pack_tc<<<(unsigned)cdivz(total, 256), 256>>>(j.src, j.dst, j.a, j.b, j.c, NT, nchunk, ntg, tpg, KG);
   return 0;
 }
@@ -1008,12 +705,8 @@ bool conv_tc_usable(const ConvW& w, const ConvGeom& geo) {
   return true;
 }
 
-static int conv_stack_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum,
-                          double* ssq, const ConvGeom& geo, int B);
-
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum, double* ssq,
-                const ConvGeom& geo, int B) {
-  if (w.tc.ws && w.ntaps == 27) return conv_stack_run(c, w, in, Gin, out, Gout_store, ssum, ssq, geo, B);
+                const ConvGeom& geo, int B, const AffineJob* aff) {
   tc::Params P{};
   int NT, KG, nchunk, ntg, tpg;
   tc_shape(w, NT, KG, nchunk, ntg, tpg);
@@ -1066,6 +759,13 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
     P.stage_rows = 128 * mt;
     P.a_stage_bytes = KG * P.stage_rows * 16;
   }
+  if (aff) {
+    if (!ssum || aff->C > w.cout_pad || (size_t)B * aff->C * 9 / 8 * sizeof(float) > 96 * 1024) {
+      set_error("conv_tc: fused AdaGN fold needs statistics and B*C <= 21k (B=%d, C=%d)", B, aff->C);
+      return LION_ERR_ARG;
+    }
+    P.aff = *aff;
+  }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
   const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128;
@@ -1081,73 +781,15 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   int grid = (int)(n_items < c->num_sms ? n_items : c->num_sms);      // persistent: one CTA per SM
 #define LION_TC_CASE(kg, tpg_)                                                                            \
   if (KG == kg && tpg == tpg_) {                                                                          \
-    static bool attr_set = false;                                                                         \
-    if (!attr_set) {                                                                                      \
+    static DevOnce attr_once;                                                                         \
+    if (attr_once.need()) {                                                                                      \
       LION_CHECK_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<kg, tpg_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr_set = true;                                                                                    \
     }                                                                                                     \
     LION_LAUNCH(c, (tc::k_conv_tc<kg, tpg_>), grid, tc::THREADS, smem, P);                                \
   }
   LION_TC_CASE(2, 1) LION_TC_CASE(4, 1) LION_TC_CASE(8, 1) LION_TC_CASE(2, 9) LION_TC_CASE(4, 9) LION_TC_CASE(8, 9)
 #undef LION_TC_CASE
   return check_launch(c, "conv_tc");
-}
-
-// experimental tap-stacked path (LION_TC_STACK=1), see tc::k_conv_stack
-static int conv_stack_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum,
-                          double* ssq, const ConvGeom& geo, int B) {
-  tc::ParamsS P{};
-  int NT, KG, nchunk, ntg, tpg;
-  tc_shape(w, NT, KG, nchunk, ntg, tpg);
-  const int S = w.tc.stack;
-  P.in = in; P.w = w.tc.ws; P.bias = w.bias; P.out = out; P.ssum = ssum; P.ssq = ssq;
-  P.Gin = Gin; P.Gout_store = Gout_store; P.cout_pad = w.cout_pad;
-  P.rows = geo.rows; P.p_begin = geo.p_begin; P.p_end = geo.p_end; P.rp = geo.rp;
-  P.KG = KG; P.nchunk = nchunk; P.NT = NT;
-  const int rp = geo.rp;
-  for (int dx = 0; dx < 3; ++dx) P.tg_off[dx] = (dx - 1) * rp * rp;
-  P.halo = rp + 1;
-  P.stage_rows = 128 + 2 * P.halo;
-  P.a_stage_bytes = KG * P.stage_rows * 16;
-  P.b_stage_bytes = 9 * KG * NT * 16;
-  const int TP = 128 - (S - 1);
-  const int ntile = cdiv(geo.p_end - geo.p_begin, TP);
-  const int n_tiles_n = w.cout_pad / NT;
-  int gmax = 512 / (S * NT);
-  if (gmax > 4) gmax = 4;
-  int G = 1;
-  {   // as in conv_tc_run: fewest rounds of work items, then the largest weight-slab reuse
-    double best = 1e30;
-    for (int g = 1; g <= gmax; g <<= 1) {
-      long long items = (long long)cdiv(ntile, g) * n_tiles_n * B;
-      double rounds = (double)((items + c->num_sms - 1) / c->num_sms);
-      double cost = rounds * g + 0.25 / g;
-      if (cost < best * 0.999) { best = cost; G = g; }
-    }
-  }
-  P.G = G; P.B = B;
-  P.occ = geo.occ; P.occ_stride = geo.occ_stride;
-  const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + tc::XCH_FLOATS * 4 + 64 * 8 + 128;
-  long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
-  int a_stages = (int)(room / P.a_stage_bytes);
-  if (a_stages > tc::MAX_A_STAGES) a_stages = tc::MAX_A_STAGES;
-  if (a_stages < 2) { set_error("conv_stack: shared memory cannot hold the operand pipeline (N=%d, KG=%d)", NT, KG); return LION_ERR_ARG; }
-  P.a_stages = a_stages;
-  size_t smem = (size_t)a_stages * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + fixed;
-  long long n_items = (long long)cdiv(ntile, G) * n_tiles_n * B;
-  int grid = (int)(n_items < c->num_sms ? n_items : c->num_sms);
-#define LION_TCS_CASE(kg, s_)                                                                             \
-  if (KG == kg && S == s_) {                                                                              \
-    static bool attr_set = false;                                                                         \
-    if (!attr_set) {                                                                                      \
-      LION_CHECK_CUDA(cudaFuncSetAttribute(tc::k_conv_stack<kg, s_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr_set = true;                                                                                    \
-    }                                                                                                     \
-    LION_LAUNCH(c, (tc::k_conv_stack<kg, s_>), grid, tc::THREADS, smem, P);                               \
-  }
-  LION_TCS_CASE(2, 3) LION_TCS_CASE(4, 3) LION_TCS_CASE(8, 3) LION_TCS_CASE(2, 2) LION_TCS_CASE(4, 2) LION_TCS_CASE(8, 2)
-#undef LION_TCS_CASE
-  return check_launch(c, "conv_stack");
 }
 
 }  // namespace lion

@@ -17,8 +17,8 @@
 
 namespace lion {
 
-__global__ void k_ddpm_update(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
-                              float* __restrict__ xo, const float4* __restrict__ tables, const int* __restrict__ step,
+__global__ void k_ddpm_update(const float* x /* may alias xo (in-place update) */, const float* __restrict__ eps, const float* __restrict__ noise,
+                              float* xo, const float4* __restrict__ tables, const int* __restrict__ step,
                               float temp, size_t n, float* __restrict__ hist, int T) {
   pdl_prologue();
   int t = *step;
@@ -49,8 +49,8 @@ __global__ void k_ddpm_set_step(int* step, float* t_out, int B, int t_index, int
 // with the 0-dim fp32 scalars a = sqrt(abar_next/abar_t), c, sigma of step i (host-built table
 // row { a, c, sigma, t+1 }, see DiffusionDiscretized._ddim_tables); same operation order, no FMA.
 // noise is the whole [S][n] block of the run's draws; row i is consumed at step i.
-__global__ void k_ddim_update(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
-                              float* __restrict__ xo, const float4* __restrict__ tables, const int* __restrict__ step,
+__global__ void k_ddim_update(const float* x /* may alias xo (in-place update) */, const float* __restrict__ eps, const float* __restrict__ noise,
+                              float* xo, const float4* __restrict__ tables, const int* __restrict__ step,
                               size_t n, float* __restrict__ hist) {
   pdl_prologue();
   int s = *step;
@@ -79,8 +79,8 @@ __global__ void k_ddim_set_step(int* step, float* t_out, const float4* __restric
 //   prev = c0 * x0 + c1 * x,   c0 = sqrt(abar_{t-1}) * beta_t / (1-abar_t),  c1 = sqrt(alpha_t) * (1-abar_{t-1}) / (1-abar_t)
 //   x'   = prev + sqrt(var_t) * z   for t > 0,   x' = prev   at t = 0
 // table row t (8 floats): { sqrt(1-abar_t), sqrt(abar_t), c0, c1, sqrt(var_t), 0, 0, 0 }.
-__global__ void k_sched_step(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
-                             float* __restrict__ xo, const float4* __restrict__ tables, const int* __restrict__ step, size_t n) {
+__global__ void k_sched_step(const float* x /* may alias xo (in-place update) */, const float* __restrict__ eps, const float* __restrict__ noise,
+                             float* xo, const float4* __restrict__ tables, const int* __restrict__ step, size_t n) {
   pdl_prologue();
   int t = *step;
   float4 c = tables[2 * t];

@@ -273,12 +273,11 @@ static int gp_linear(Ctx* c, const GPLin& l, const float* x, int xs, const float
   int nsplit = cdiv(l.K, GP_KS);
   if (nsplit > GP_MAXSPLIT) { set_error("global prior: K=%d too large", l.K); return LION_ERR_ARG; }
   const size_t smem = (size_t)(GP_OB + GP_BT) * GP_PITCH * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DevOnce attr_once;
+  if (attr_once.need()) {
     LION_CHECK_CUDA(cudaFuncSetAttribute(k_gp_partial<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LION_CHECK_CUDA(cudaFuncSetAttribute(k_gp_partial<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+}
   static int use_cluster = -1;
   // measured on B200 (graph-replayed 1000-step loop, B=32): 0.63-0.75 s with clusters vs 0.39 s with the two-kernel
   // form -- 16 clusters of 8 CTAs with 150 KB of shared memory each do not co-schedule well -- so OFF by default

@@ -156,11 +156,10 @@ extern "C" int lion_chamfer_pairwise(const float* samples, const float* refs, fl
   Ctx c;
   c.stream = (cudaStream_t)stream;
   const size_t smem = (6 * CD_PW_MAX + 2 * (CD_PW_THREADS / 32)) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DevOnce attr_once;
+  if (attr_once.need()) {
     LION_CHECK_CUDA(cudaFuncSetAttribute(k_chamfer_pairwise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+}
   LION_LAUNCH(&c, k_chamfer_pairwise, dim3(n_ref, n_sample), CD_PW_THREADS, smem, samples, refs, out, N, M, n_ref);
   return check_launch(&c, "lion_chamfer_pairwise");
 }
@@ -319,11 +318,10 @@ static int emd_launch(const float* a, const float* b, float* out, int pairs, int
   Ctx c;
   c.stream = (cudaStream_t)stream;
   const size_t smem = (size_t)EMD_MAX * (2 * sizeof(float4) + 3 * sizeof(float)) + EMD_THREADS * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DevOnce attr_once;
+  if (attr_once.need()) {
     LION_CHECK_CUDA(cudaFuncSetAttribute(k_emd_approx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+}
   LION_LAUNCH(&c, k_emd_approx, pairs, EMD_THREADS, smem, a, b, out, n, m, nb, pairwise);
   return check_launch(&c, "lion_emd_approx");
 }

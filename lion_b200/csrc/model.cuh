@@ -14,8 +14,6 @@ struct ConvTcW {
   int ck = 0;        // input channels per pipeline chunk (8, 16 or 32)
   int nchunk = 0;
   int n = 0;         // UMMA N (= padded output channels)
-  float* ws = nullptr;   // experimental tap-stacked packing (LION_TC_STACK=1), else null
-  int stack = 0;         // taps stacked along N (2 or 3)
 };
 
 struct Cursor {
@@ -105,6 +103,8 @@ struct Model {
   StyleLayer* d_style_layers = nullptr;
   int style_total = 0;
   int S = 128;
+  float* aff_cache = nullptr;  // [aff_cache_B][style_total]: the AdaGN style Linears of a step-invariant style (lion_unet_cache_style)
+  int aff_cache_B = 0;
   std::unique_ptr<UnetBlk> unet;
   std::unique_ptr<Block> block;
   std::unique_ptr<AttnBlk> attn;
@@ -123,6 +123,7 @@ struct Model {
   }
   ~Model() {
     for (void* q : owned) cudaFree(q);
+    if (aff_cache) cudaFree(aff_cache);
     if (gp) global_prior_free(gp);
   }
 };
@@ -144,11 +145,23 @@ struct ConvGeom {
   int occ_stride;
 };
 
+// AdaGN (+ SE gate) folded into y = scale*x + shift, computed by the LAST CTA of the producing convolution
+// (conv_tc.cu: affine_tail) instead of a separate launch.  scale == nullptr: disabled.
+struct AffineJob {
+  float* scale = nullptr; float* shift = nullptr;      // [B][C]
+  const float* gamma = nullptr; const float* beta = nullptr;
+  const float* fb = nullptr; int fb_stride = 0;        // style Linear output [B][fb_stride]: factor at +c, bias at +C+c
+  const float* se_w1 = nullptr; const float* se_w2 = nullptr;   // SE3d weights or null
+  int C = 0;
+  double count = 0;                                    // rows per (b, channel) in the statistics
+  unsigned* ticket = nullptr;                          // zero-initialised arrival counter of this launch
+};
+
 // conv_tc.cu
 int conv_tc_prepare(Model* m, ConvW& w);
 int conv_tc_pack_job(const PackJob& j);
 bool conv_tc_usable(const ConvW& w, const ConvGeom& geo);
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum,
-                double* ssq, const ConvGeom& geo, int B);
+                double* ssq, const ConvGeom& geo, int B, const AffineJob* aff = nullptr);
 
 }  // namespace lion

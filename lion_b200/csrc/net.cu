@@ -58,6 +58,7 @@ int ctx_reserve(Ctx* c, size_t bytes) {
     return LION_ERR_OOM;
   }
   c->cap = want;
+  c->generation++;           // every CUDA graph captured on this context so far has the old addresses baked in
   return 0;
 }
 
@@ -77,6 +78,7 @@ int ctx_reserve_zgrid(Ctx* c, size_t bytes) {
   if (e != cudaSuccess) { set_error("cudaMalloc(%zu) for the zero grid failed: %s", bytes, cudaGetErrorString(e)); return LION_ERR_OOM; }
   LION_CHECK_CUDA(cudaMemset(c->zgrid, 0, bytes));
   c->zgrid_cap = bytes;
+  c->generation++;
   return 0;
 }
 
@@ -272,10 +274,11 @@ static ConvGeom geom_grid(int r) {
 
 // out rows in [p_begin,p_end) of every (b, group < Gout_store); statistics optional
 static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store,
-                    double* ssum, double* ssq, const ConvGeom& geo) {
+                    double* ssum, double* ssq, const ConvGeom& geo, const AffineJob* aff = nullptr) {
   if (Gin * 4 != w.cin_pad) { set_error("conv: input has %d channels, weights expect %d", Gin * 4, w.cin_pad); return LION_ERR_ARG; }
   if (conv_tc_usable(w, geo))
-    return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B);
+    return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B, aff);
+  if (aff) { set_error("conv: the fused AdaGN fold needs the tensor-core kernel"); return LION_ERR_STATE; }
   int span = geo.p_end - geo.p_begin;
   if (w.cout_pad == 4) {
     LION_LAUNCH(f.c, k_conv_simt<4>, dim3(cdiv(span, 128), 1, f.B), 128, geo.ntaps * 16 * sizeof(float),
@@ -287,17 +290,12 @@ static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* o
   return check_launch(f.c, "conv");
 }
 
-// AdaGN (+SE) folded into y = scale*x + shift: k_affine_prep materialises the two arrays per layer
-// (optionally -- LION_AFFINE_LAZY -- consumers derive them from the statistics, AffSrc / aff_block_load).
+// AdaGN (+SE) folded into y = scale*x + shift.  On the network path the fold is computed by the last CTA of the
+// producing convolution (conv_gn below -> conv_tc.cu: affine_tail); k_affine_prep is the stand-alone form for
+// producers that are not the tensor-core kernel (stand-alone AdaGN entry point, SIMT convolution).
 static int run_affine(Fwd& f, const AdaGNW& g, const double* ssum, const double* ssq, int stat_stride, double count,
                       const float* se1, const float* se2, AffSrc& a) {
   a = AffSrc{nullptr, nullptr, ssum, ssq, stat_stride, g.gamma, g.beta, f.aff + g.style_off, f.m->style_total, count};
-  // LION_AFFINE_LAZY=1: consumers fold the statistics themselves (47 fewer launches per step).  Measured on
-  // B200: the local-prior loop gets 1.5-2.7 % SLOWER (every consumer block pays the dependent fp64 prologue),
-  // so the default keeps k_affine_prep.
-  static int lazy = -1;
-  if (lazy < 0) { const char* e = getenv("LION_AFFINE_LAZY"); lazy = (e && atoi(e) != 0) ? 1 : 0; }
-  if (!se1 && lazy) return 0;
   float* scale = f.c->alloc_n<float>((size_t)f.B * g.C);
   float* shift = f.c->alloc_n<float>((size_t)f.B * g.C);
   size_t smem = se1 ? (g.C + g.C / 8) * sizeof(float) : 0;
@@ -325,6 +323,29 @@ static int alloc_stats(Fwd& f, int stride, double** ssum, double** ssq) {
   return memset_async(f.c, s, 0, bytes);
 }
 
+// convolution + GroupNorm statistics + AdaGN(/SE) fold: ONE launch when the tensor-core kernel serves the shape
+static int conv_gn(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, const ConvGeom& geo,
+                   const AdaGNW& g, double count, const float* se1, const float* se2, AffSrc& a) {
+  double *ssum, *ssq;
+  LION_TRY(alloc_stats(f, w.cout_pad, &ssum, &ssq));
+  if (!conv_tc_usable(w, geo) || (size_t)f.B * g.C * 9 / 8 * sizeof(float) > 96 * 1024) {
+    LION_TRY(run_conv(f, w, in, Gin, out, Gout_store, ssum, ssq, geo));
+    return run_affine(f, g, ssum, ssq, w.cout_pad, count, se1, se2, a);
+  }
+  a = AffSrc{nullptr, nullptr, ssum, ssq, w.cout_pad, g.gamma, g.beta, f.aff + g.style_off, f.m->style_total, count};
+  AffineJob J;
+  J.scale = f.c->alloc_n<float>((size_t)f.B * g.C);
+  J.shift = f.c->alloc_n<float>((size_t)f.B * g.C);
+  J.gamma = g.gamma; J.beta = g.beta; J.fb = f.aff + g.style_off; J.fb_stride = f.m->style_total;
+  J.se_w1 = se1; J.se_w2 = se2; J.C = g.C; J.count = count;
+  double *t0, *t1;
+  LION_TRY(alloc_stats(f, 1, &t0, &t1));                 // 2*B zeroed doubles from the statistics pool: the arrival counter
+  (void)t1;
+  J.ticket = (unsigned*)t0;
+  a.scale = J.scale; a.shift = J.shift;
+  return run_conv(f, w, in, Gin, out, Gout_store, ssum, ssq, geo, &J);
+}
+
 // SharedMLP on a PF.  pool: 1, or 32 = max over neighbour rows after the last activation.
 // The activated result goes to dst (Gd groups, offset g_off, R/pool rows).
 static int shared_mlp_fwd(Fwd& f, const SharedMLPBlk& m, PF in, int pool, float4* dst, int Gd, int g_off) {
@@ -334,11 +355,8 @@ static int shared_mlp_fwd(Fwd& f, const SharedMLPBlk& m, PF in, int pool, float4
     const ConvW& w = m.conv[i];
     int Gout = w.cout / 4;
     PF raw = alloc_pf(f, Gout, cur.R);
-    double *ssum, *ssq;
-    LION_TRY(alloc_stats(f, w.cout_pad, &ssum, &ssq));
-    LION_TRY(run_conv(f, w, cur.p, cur.G, raw.p, Gout, ssum, ssq, geom_rows(cur.R)));
     AffSrc a;
-    LION_TRY(run_affine(f, m.gn[i], ssum, ssq, w.cout_pad, (double)cur.R, nullptr, nullptr, a));
+    LION_TRY(conv_gn(f, w, cur.p, cur.G, raw.p, Gout, geom_rows(cur.R), m.gn[i], (double)cur.R, nullptr, nullptr, a));
     bool last = (i == n - 1);
     if (last && pool > 1) {
       if (pool != 32 || cur.R % 32) { set_error("shared_mlp: unsupported pooling %d", pool); return LION_ERR_ARG; }
@@ -404,32 +422,23 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   LION_LAUNCH(f.c, k_scatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, feat.p, vp->order, vp->ppos, vp->len, g_in, Gin, N, P);
   // conv1 (sparse input: empty 64-row blocks are skipped) -> (stats) -> AdaGN + Swish
   float4* raw1 = alloc_vg(f, Gout, r);
-  double *s1, *q1;
-  LION_TRY(alloc_stats(f, p.c1.cout_pad, &s1, &q1));
   ConvGeom geo1 = geo;
   geo1.occ = vp->occ; geo1.occ_stride = vp->occ_stride;
-  LION_TRY(run_conv(f, p.c1, g_in, Gin, raw1, Gout, s1, q1, geo1));
-  LION_LAUNCH(f.c, k_unscatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, vp->ppos, g_in, Gin, N, P);
   AffSrc a1;
   double V = (double)r * r * r;
-  LION_TRY(run_affine(f, p.g1, s1, q1, p.c1.cout_pad, V, nullptr, nullptr, a1));
+  LION_TRY(conv_gn(f, p.c1, g_in, Gin, raw1, Gout, geo1, p.g1, V, nullptr, nullptr, a1));
+  LION_LAUNCH(f.c, k_unscatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, vp->ppos, g_in, Gin, N, P);
   float4* act1 = alloc_vg(f, Gout, r);
   LION_LAUNCH(f.c, k_act_grid, dim3(cdiv(P, 256 * ACT_U), Gout, f.B), 256, 0, raw1, act1, a1, Gout, p.cout, rp, P);
   // conv2 -> (stats) -> AdaGN + SE folded into one affine
   float4* raw2 = alloc_vg(f, Gout, r);
-  double *s2, *q2;
-  LION_TRY(alloc_stats(f, p.c2.cout_pad, &s2, &q2));
-  LION_TRY(run_conv(f, p.c2, act1, Gout, raw2, Gout, s2, q2, geo));
   AffSrc a2;
-  LION_TRY(run_affine(f, p.g2, s2, q2, p.c2.cout_pad, V, p.se1, p.se2, a2));
+  LION_TRY(conv_gn(f, p.c2, act1, Gout, raw2, Gout, geo, p.g2, V, p.se1, p.se2, a2));
   // point branch: conv1x1 -> stats -> affine (activation applied inside the devox kernel)
   const ConvW& pw = p.point.conv[0];
   PF rawp = alloc_pf(f, Gout, N);
-  double *sp, *qp;
-  LION_TRY(alloc_stats(f, pw.cout_pad, &sp, &qp));
-  LION_TRY(run_conv(f, pw, feat.p, feat.G, rawp.p, Gout, sp, qp, geom_rows(N)));
   AffSrc ap;
-  LION_TRY(run_affine(f, p.point.gn[0], sp, qp, pw.cout_pad, (double)N, nullptr, nullptr, ap));
+  LION_TRY(conv_gn(f, pw, feat.p, feat.G, rawp.p, Gout, geom_rows(N), p.point.gn[0], (double)N, nullptr, nullptr, ap));
   // voxel -> point gather (+ point branch)
   if (p.has_attn) {
     PF fused = alloc_pf(f, Gout, N);
@@ -617,6 +626,24 @@ __global__ void k_pm4_to_pm(const float4* __restrict__ src, float* __restrict__ 
   for (int j = 0; j < C; ++j) dst[(size_t)i * C + j] = vv[j];
 }
 
+// style -> (CLIP mixing, latent_points_ada.py:132-137) -> all 61 AdaGN style Linears in one launch; result in f.aff
+static int unet_style_affine(Fwd& f, const float* style, const float* clip) {
+  UnetBlk& u = *f.m->unet;
+  Ctx* c = f.c;
+  int B = f.B, E = u.embed_dim;
+  if (u.clip) {
+    if (!clip) { set_error("unet: this network needs clip_feat"); return LION_ERR_ARG; }
+    float* cat = c->alloc_n<float>((size_t)B * (u.S + E));
+    float* st2 = c->alloc_n<float>((size_t)B * u.S);
+    if (!c->dry) LION_CHECK_CUDA(cudaMemcpy2DAsync(cat, (u.S + E) * sizeof(float), style, u.S * sizeof(float), u.S * sizeof(float), B, cudaMemcpyDeviceToDevice, c->stream));
+    LION_LAUNCH(c, k_small_linear, B, 128, u.clip_dim * sizeof(float), u.cfw, u.cfb, clip, u.clip_dim, cat + u.S, u.S + E, u.clip_dim, E, 0);
+    LION_LAUNCH(c, k_small_linear, B, 128, (u.S + E) * sizeof(float), u.scw, u.scb, cat, u.S + E, st2, u.S, u.S + E, u.S, 0);
+    style = st2;
+  }
+  LION_TRY(check_launch(c, "unet style"));
+  return style_affine_all(f, style);
+}
+
 static int unet_forward(Fwd& f, const float* x, const float* t, const float* style, const float* clip, float* out, int N) {
   UnetBlk& u = *f.m->unet;
   int B = f.B, E = u.embed_dim;
@@ -632,19 +659,16 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
     LION_LAUNCH(c, k_small_linear, B, 128, E * sizeof(float), u.e0w, u.e0b, sinu, E, h, E, E, E, 1);
     LION_LAUNCH(c, k_small_linear, B, 128, E * sizeof(float), u.e2w, u.e2b, h, E, temb, E, E, E, 0);
   }
-  // CLIP conditioning: style <- style_clip([style | clip_forge_mapping(clip)])  (:132-137)
-  if (u.clip) {
-    if (!clip) { set_error("unet: this network needs clip_feat"); return LION_ERR_ARG; }
-    float* cat = c->alloc_n<float>((size_t)B * (u.S + E));
-    float* st2 = c->alloc_n<float>((size_t)B * u.S);
-    if (!c->dry) LION_CHECK_CUDA(cudaMemcpy2DAsync(cat, (u.S + E) * sizeof(float), style, u.S * sizeof(float), u.S * sizeof(float), B, cudaMemcpyDeviceToDevice, c->stream));
-    LION_LAUNCH(c, k_small_linear, B, 128, u.clip_dim * sizeof(float), u.cfw, u.cfb, clip, u.clip_dim, cat + u.S, u.S + E, u.clip_dim, E, 0);
-    LION_LAUNCH(c, k_small_linear, B, 128, (u.S + E) * sizeof(float), u.scw, u.scb, cat, u.S + E, st2, u.S, u.S + E, u.S, 0);
-    style = st2;
+  // AdaGN style Linears (and the CLIP mixing in front of them) depend on the style only, which is constant over the
+  // 1000 steps of a sampling run: style == nullptr means "use what lion_unet_cache_style computed"
+  if (style) {
+    LION_TRY(unet_style_affine(f, style, clip));
+  } else {
+    if (!f.m->aff_cache || f.m->aff_cache_B != B) { set_error("unet: no cached style for B=%d (call lion_unet_cache_style first)", B); return LION_ERR_STATE; }
+    f.aff = f.m->aff_cache;
   }
   LION_TRY(check_launch(c, "unet prologue"));
-  LION_TRY(style_affine_all(f, style));
-  LION_TRY(stat_pool_begin(f, (size_t)f.m->style_total * f.B * sizeof(double) + 4096));   // sum(2*C) doubles per shape
+  LION_TRY(stat_pool_begin(f, (size_t)f.m->style_total * f.B * sizeof(double) + (size_t)f.m->style_layers.size() * 2 * f.B * sizeof(double) + 4096));   // sum(2*C) doubles per shape + one arrival counter per layer
 
   int n_sa = (int)u.sa.size();
   std::vector<const float4*> coords_list(n_sa);
@@ -758,6 +782,8 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
 template <typename F>
 static int two_pass(Model* m, void* stream, int B, F body) {
   Ctx* c = m->ctx;
+  std::unique_lock<std::mutex> lock;
+  if (c->mu) lock = std::unique_lock<std::mutex>(*c->mu);
   c->stream = (cudaStream_t)stream;
   for (int pass = 0; pass < 2; ++pass) {
     c->dry = (pass == 0);
@@ -780,7 +806,7 @@ static int two_pass(Model* m, void* stream, int B, F body) {
 // =====================================================================================
 using namespace lion;
 
-struct LionCtx { Ctx c; };
+struct LionCtx { Ctx c; std::mutex mu; };
 struct LionModel { Model m; };
 
 extern "C" int lion_version(void) { return 100; }
@@ -791,6 +817,7 @@ extern "C" int lion_ctx_create(int device, LionCtx** out) {
   LION_CHECK_CUDA(cudaSetDevice(device));
   LionCtx* h = new LionCtx();
   h->c.device = device;
+  h->c.mu = &h->mu;
   cudaDeviceProp prop;
   LION_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   h->c.num_sms = prop.multiProcessorCount;
@@ -817,6 +844,7 @@ extern "C" int lion_ctx_destroy(LionCtx* h) {
   return 0;
 }
 extern "C" int lion_ctx_last_launches(LionCtx* h) { return h ? h->c.launches : 0; }
+extern "C" unsigned lion_ctx_generation(LionCtx* h) { return h ? h->c.generation : 0; }
 extern "C" size_t lion_ctx_arena_bytes(LionCtx* h) { return h ? h->c.cap : 0; }
 extern "C" size_t lion_workspace_bytes(LionCtx* h) { return h ? h->c.cap + h->c.zgrid_cap : 0; }
 
@@ -905,9 +933,35 @@ extern "C" int lion_model_refresh(LionModel* h) {
 extern "C" int lion_unet_forward(LionModel* h, const float* x, const float* t, const float* style, const float* clip,
                                  float* out, int B, int N, void* stream) {
   LION_REQUIRE(h && h->m.kind == LION_KIND_UNET, "lion_unet_forward: not a unet model");
-  LION_REQUIRE(x && style && out && B > 0 && N > 0, "lion_unet_forward: bad arguments");
+  LION_REQUIRE(x && out && B > 0 && N > 0, "lion_unet_forward: bad arguments");
   Model* m = &h->m;
   return two_pass(m, stream, B, [&](Fwd& f) { return unet_forward(f, x, t, style, clip, out, N); });
+}
+
+// Hoists everything that depends on the style only out of the denoising loop (the reference recomputes the 61 AdaGN
+// Linears and the CLIP mixing every step, models/adagn.py:59-61, latent_points_ada.py:132-137): computes them once
+// into a buffer owned by the model; later lion_unet_forward calls with style == NULL use it.  Not capturable when the
+// buffer has to grow (first call / larger B).
+extern "C" int lion_unet_cache_style(LionModel* h, const float* style, const float* clip, int B, void* stream) {
+  LION_REQUIRE(h && h->m.kind == LION_KIND_UNET, "lion_unet_cache_style: not a unet model");
+  LION_REQUIRE(style && B > 0, "lion_unet_cache_style: bad arguments");
+  Model* m = &h->m;
+  if (m->aff_cache_B < B) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing((cudaStream_t)stream, &st);
+    LION_REQUIRE(st == cudaStreamCaptureStatusNone, "lion_unet_cache_style: the cache must be sized outside stream capture");
+    LION_CHECK_CUDA(cudaSetDevice(m->ctx->device));
+    LION_CHECK_CUDA(cudaDeviceSynchronize());
+    if (m->aff_cache) LION_CHECK_CUDA(cudaFree(m->aff_cache));
+    m->aff_cache = nullptr; m->aff_cache_B = 0;
+    LION_CHECK_CUDA(cudaMalloc((void**)&m->aff_cache, (size_t)B * m->style_total * sizeof(float) + 16));
+  }
+  m->aff_cache_B = B;
+  return two_pass(m, stream, B, [&](Fwd& f) -> int {
+    LION_TRY(unet_style_affine(f, style, clip));
+    if (!f.c->dry) LION_CHECK_CUDA(cudaMemcpyAsync(m->aff_cache, f.aff, (size_t)B * m->style_total * sizeof(float), cudaMemcpyDeviceToDevice, f.c->stream));
+    return 0;
+  });
 }
 
 // ---- block-level entry points on the reference's channel-major layouts -------------------
