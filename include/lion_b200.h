@@ -71,7 +71,8 @@ int lion_voxel_coords(const float* coords, float* norm_coords, int* vox, int B, 
  * must stay valid (weights are re-packed into kernel layouts at creation).
  * kinds: */
 enum { LION_KIND_UNET = 1, LION_KIND_PVCONV = 2, LION_KIND_SA = 3, LION_KIND_FP = 4, LION_KIND_ATTN = 5,
-       LION_KIND_SHARED_MLP = 6, LION_KIND_GLOBAL_PRIOR = 7, LION_KIND_ADAGN = 8, LION_KIND_CONV3D = 9 };
+       LION_KIND_SHARED_MLP = 6, LION_KIND_GLOBAL_PRIOR = 7, LION_KIND_ADAGN = 8, LION_KIND_CONV3D = 9,
+       LION_KIND_STYLE_ENC = 10 };
 int lion_model_create(LionCtx* ctx, int kind, const int* desc, int ndesc, const float* const* params, int nparams,
                       LionModel** out);
 int lion_model_destroy(LionModel* m);
@@ -90,6 +91,12 @@ int lion_unet_forward(LionModel* m, const float* x, const float* t, const float*
  * style [B,S] (+ clip [B,clip_dim] or NULL) into a buffer owned by the model; lion_unet_forward calls with style == NULL
  * (same B) then skip them.  Values are identical to recomputing them every step. */
 int lion_unet_cache_style(LionModel* m, const float* style, const float* clip, int B, void* stream);
+/* PointNetPlusEncoder.forward (models/shapelatent_modules.py:35-52), the VAE's global style encoder on the non-Ada
+ * PVCNN blocks of models/pvcnn2.py (PVConv :170-247, PointNetSAModule :288-351, SharedMLP :117-138; plain
+ * GroupNorm(8)): x [B,N,3] point-major -> out [B, 2*zdim] = [mu_1d | sigma_1d (log sigma)].  Model kind
+ * LION_KIND_STYLE_ENC, descriptor [input_dim, zdim, use_att, n_sa, {has_conv, oc, nblk, res, m, radius_bits, k,
+ * n_mlp, mlp...}*], parameters in state_dict order (layers.*, mlp.weight, mlp.bias). */
+int lion_style_encoder_forward(LionModel* m, const float* x, float* out, int B, int N, void* stream);
 /* PVConv.forward (models/pvcnn2_ada.py:235-280): features [B,Cin,N], coords [B,3,N] -> out [B,Cout,N] */
 int lion_pvconv_fwd(LionModel* m, const float* features, const float* coords, const float* style, float* out,
                     int B, int N, void* stream);

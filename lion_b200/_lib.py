@@ -46,6 +46,7 @@ def _proto(lib):
         "lion_model_refresh": (P(vp), i),
         "lion_unet_forward": (P(vp, vp, vp, vp, vp, vp, i, i, vp), i),
         "lion_unet_cache_style": (P(vp, vp, vp, i, vp), i),
+        "lion_style_encoder_forward": (P(vp, vp, vp, i, i, vp), i),
         "lion_pvconv_fwd": (P(vp, vp, vp, vp, vp, i, i, vp), i),
         "lion_sa_module_fwd": (P(vp, vp, vp, vp, vp, vp, i, i, vp), i),
         "lion_fp_module_fwd": (P(vp, vp, vp, vp, vp, vp, vp, i, i, i, vp), i),
@@ -139,7 +140,7 @@ def last_launches(device=None):
     return lib().lion_ctx_last_launches(ctx(device))
 
 
-KIND_UNET, KIND_PVCONV, KIND_SA, KIND_FP, KIND_ATTN, KIND_SHARED_MLP, KIND_GLOBAL_PRIOR, KIND_ADAGN, KIND_CONV3D = 1, 2, 3, 4, 5, 6, 7, 8, 9
+KIND_UNET, KIND_PVCONV, KIND_SA, KIND_FP, KIND_ATTN, KIND_SHARED_MLP, KIND_GLOBAL_PRIOR, KIND_ADAGN, KIND_CONV3D, KIND_STYLE_ENC = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 
 def float_bits(x):

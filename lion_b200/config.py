@@ -54,7 +54,10 @@ _DEFAULT = {
             "num_scales_dae": 2, "dropout": 0.2, "learn_mixing_logit": 1, "ode_sample": 0,
             "prior_model": "models.latent_points_ada_localprior.PVCNN2Prior"},
     "clipforge": {"enable": 0, "feat_dim": 512},
-    "data": {"tr_max_sample_points": 2048, "cond_on_cat": 0},
+    "data": {"tr_max_sample_points": 2048, "cond_on_cat": 0, "batch_size_test": 10},
+    "eval": {"need_denoise": 0},
+    "trainer": {"seed": 1},
+    "num_ref": 0,
 }
 
 

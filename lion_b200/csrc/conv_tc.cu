@@ -201,56 +201,7 @@ struct Params {
   int a_stages;          // depth of the A ring
   const unsigned char* occ;   // 64-row occupancy flags of the input (sparse first conv of a PVConv) or null
   int occ_stride;
-  AffineJob aff;              // AdaGN fold computed by the last CTA to finish (aff.scale == nullptr: none)
 };
-
-// The AdaGN (+SE) fold of models/adagn.py:45-65 / models/pvcnn2_ada.py:27-41 for all (b, c) of this convolution's
-// output, run by the last CTA once every CTA's GroupNorm statistics have landed: GroupNorm(8, C, eps 1e-5, affine)
-// followed by *factor + bias collapses to y = scale[b][c]*x + shift[b][c]; SE3d needs only the per-channel mean of y,
-// which is affine in the per-channel mean of x, so its gate folds in as well.  Group sums run in channel order
-// (deterministic).  sm: >= B*C + B*C/8 floats of shared memory.  Called by all threads of the CTA.
-__device__ __noinline__ void affine_tail(const AffineJob& J, const double* ssum, const double* ssq, int stat_stride, int B, float* sm) {
-  const int C = J.C, cpg = C / 8, tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < B * C; i += nt) {
-    const int b = i / C, c = i - b * C, c0 = (c / cpg) * cpg;
-    const double* ps = ssum + (size_t)b * stat_stride + c0;
-    const double* pq = ssq + (size_t)b * stat_stride + c0;
-    double gs = 0.0, gq = 0.0;
-    for (int k = 0; k < cpg; ++k) { gs += __ldcg(ps + k); gq += __ldcg(pq + k); }
-    const double n = J.count * cpg;
-    const double mean = gs / n;
-    double var = gq / n - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-    const float f = J.fb[(size_t)b * J.fb_stride + c], bb = J.fb[(size_t)b * J.fb_stride + C + c];
-    const float ga = J.gamma[c], be = J.beta[c];
-    const float sc = rstd * ga * f;
-    const float sh = (be - (float)mean * rstd * ga) * f + bb;
-    J.scale[i] = sc;
-    J.shift[i] = sh;
-    if (J.se_w1) sm[i] = sc * (float)(__ldcg(ssum + (size_t)b * stat_stride + c) / J.count) + sh;   // mean over voxels of the AdaGN output
-  }
-  if (J.se_w1) {
-    const int H = C / 8;
-    float* s_h = sm + B * C;
-    __syncthreads();
-    for (int i = tid; i < B * H; i += nt) {
-      const int b = i / H, h = i - b * H;
-      float a = 0.0f;
-      for (int k = 0; k < C; ++k) a = fmaf(J.se_w1[h * C + k], sm[b * C + k], a);
-      s_h[i] = fmaxf(a, 0.0f);
-    }
-    __syncthreads();
-    for (int i = tid; i < B * C; i += nt) {
-      const int b = i / C, c = i - b * C;
-      float a = 0.0f;
-      for (int k = 0; k < H; ++k) a = fmaf(J.se_w2[c * H + k], s_h[b * H + k], a);
-      const float gate = 1.0f / (1.0f + expf(-a));
-      J.scale[i] *= gate;
-      J.shift[i] *= gate;
-    }
-  }
-}
 
 // per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
 // in: v[32] (this lane's row, 32 channels); cost 31 shuffles instead of 160.
@@ -603,20 +554,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   }
 #undef ITEM_DECODE
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  if (P.aff.scale) __threadfence();                 // this thread's statistics atomics are visible device-wide
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-  }
-  if (P.aff.scale) {
-    // last CTA to arrive folds GroupNorm + style (+ SE) into per-(b, c) scale / shift: saves one launch per layer
-    volatile uint32_t* s_last = s_tmem;
-    if (tid == 0) *s_last = (atomicAdd(P.aff.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (*s_last) {
-      __threadfence();
-      affine_tail(P.aff, P.ssum, P.ssq, P.cout_pad, P.B, (float*)smem);
-    }
   }
 }
 
@@ -706,7 +646,7 @@ bool conv_tc_usable(const ConvW& w, const ConvGeom& geo) {
 }
 
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum, double* ssq,
-                const ConvGeom& geo, int B, const AffineJob* aff) {
+                const ConvGeom& geo, int B) {
   tc::Params P{};
   int NT, KG, nchunk, ntg, tpg;
   tc_shape(w, NT, KG, nchunk, ntg, tpg);
@@ -758,13 +698,6 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
     P.MT = mt;
     P.stage_rows = 128 * mt;
     P.a_stage_bytes = KG * P.stage_rows * 16;
-  }
-  if (aff) {
-    if (!ssum || aff->C > w.cout_pad || (size_t)B * aff->C * 9 / 8 * sizeof(float) > 96 * 1024) {
-      set_error("conv_tc: fused AdaGN fold needs statistics and B*C <= 21k (B=%d, C=%d)", B, aff->C);
-      return LION_ERR_ARG;
-    }
-    P.aff = *aff;
   }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }

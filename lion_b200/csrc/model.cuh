@@ -85,6 +85,12 @@ struct UnetBlk {
   SharedMLPBlk cls0;
   ConvW cls2;
 };
+// PointNetPlusEncoder (models/shapelatent_modules.py:13-52): SA levels on the non-Ada blocks, max over points, Linear
+struct StyleEncBlk {
+  int input_dim = 3, zdim = 128, cfeat = 0;
+  std::vector<std::vector<Block>> sa;
+  const float* mlp_w = nullptr; const float* mlp_b = nullptr;
+};
 struct GlobalPriorBlk;   // global_prior.cu
 int global_prior_build(Model* m, Cursor& cur);
 int global_prior_forward(Model* m, const float* x, const float* t, const float* clip, float* out, int B);
@@ -109,6 +115,7 @@ struct Model {
   std::unique_ptr<Block> block;
   std::unique_ptr<AttnBlk> attn;
   std::unique_ptr<SharedMLPBlk> mlp;
+  std::unique_ptr<StyleEncBlk> senc;
   GlobalPriorBlk* gp = nullptr;
   AdaGNW gn_single;            // LION_KIND_ADAGN
   ConvW conv_single;           // LION_KIND_CONV3D
@@ -145,23 +152,11 @@ struct ConvGeom {
   int occ_stride;
 };
 
-// AdaGN (+ SE gate) folded into y = scale*x + shift, computed by the LAST CTA of the producing convolution
-// (conv_tc.cu: affine_tail) instead of a separate launch.  scale == nullptr: disabled.
-struct AffineJob {
-  float* scale = nullptr; float* shift = nullptr;      // [B][C]
-  const float* gamma = nullptr; const float* beta = nullptr;
-  const float* fb = nullptr; int fb_stride = 0;        // style Linear output [B][fb_stride]: factor at +c, bias at +C+c
-  const float* se_w1 = nullptr; const float* se_w2 = nullptr;   // SE3d weights or null
-  int C = 0;
-  double count = 0;                                    // rows per (b, channel) in the statistics
-  unsigned* ticket = nullptr;                          // zero-initialised arrival counter of this launch
-};
-
 // conv_tc.cu
 int conv_tc_prepare(Model* m, ConvW& w);
 int conv_tc_pack_job(const PackJob& j);
 bool conv_tc_usable(const ConvW& w, const ConvGeom& geo);
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum,
-                double* ssq, const ConvGeom& geo, int B, const AffineJob* aff = nullptr);
+                double* ssq, const ConvGeom& geo, int B);
 
 }  // namespace lion

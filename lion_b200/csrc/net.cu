@@ -146,10 +146,12 @@ int run_jobs(Model* m) {
   return 0;
 }
 
-int make_adagn(Model* m, AdaGNW& g, Cursor& cur, int C) {
+// plain: nn.GroupNorm(8, C) of the non-Ada blocks (models/pvcnn2.py) = AdaGN whose style Linear is identically
+// (factor, bias) = (1, 0): no `emd` parameters are consumed and k_style_linear writes the constants.
+int make_adagn(Model* m, AdaGNW& g, Cursor& cur, int C, bool plain = false) {
   g.C = C;
   g.gamma = cur.next(); g.beta = cur.next();
-  const float* ew = cur.next(); const float* eb = cur.next();
+  const float* ew = plain ? nullptr : cur.next(); const float* eb = plain ? nullptr : cur.next();
   if (cur.bad) { set_error("model parameters exhausted while building AdaGN(%d)", C); return LION_ERR_ARG; }
   if (C % 8 || C > 512) { set_error("AdaGN channels must be a multiple of 8 and <= 512 (got %d)", C); return LION_ERR_ARG; }
   g.style_off = m->style_total;
@@ -160,7 +162,7 @@ int make_adagn(Model* m, AdaGNW& g, Cursor& cur, int C) {
 
 // SharedMLP: n x (1x1 conv, AdaGN, Swish); first conv's input mapping is given
 int make_shared_mlp(Model* m, SharedMLPBlk& b, Cursor& cur, int cin_ref, const std::vector<int>& kmap0,
-                    const std::vector<int>& outs) {
+                    const std::vector<int>& outs, bool plain = false) {
   int cin = cin_ref;
   b.cin_pad = (int)kmap0.size();
   b.conv.resize(outs.size());
@@ -169,7 +171,7 @@ int make_shared_mlp(Model* m, SharedMLPBlk& b, Cursor& cur, int cin_ref, const s
     const float* w = cur.next(); const float* bi = cur.next();
     if (cur.bad) { set_error("model parameters exhausted in SharedMLP"); return LION_ERR_ARG; }
     LION_TRY(make_conv(m, b.conv[i], w, bi, 1, cin, outs[i], i == 0 ? kmap0 : ident_map(cin)));
-    LION_TRY(make_adagn(m, b.gn[i], cur, outs[i]));
+    LION_TRY(make_adagn(m, b.gn[i], cur, outs[i], plain));
     cin = outs[i];
   }
   return 0;
@@ -183,25 +185,25 @@ int make_attn(Model* m, AttnBlk& a, Cursor& cur, int C, int heads) {
   LION_TRY(make_conv(m, a.out, ow, ob, 1, hid, C, ident_map(hid)));
   return 0;
 }
-int make_pvconv(Model* m, PVConvBlk& p, Cursor& cur, int cin, int cout, int r, bool attn) {
-  p.cin = cin; p.cout = cout; p.r = r; p.has_attn = attn;
-  if (cin % 4) { set_error("PVConv input channels must be a multiple of 4 (got %d)", cin); return LION_ERR_ARG; }
+// cin need not be a multiple of 4: the input PF is padded to whole groups and the padding meets zero weights
+int make_pvconv(Model* m, PVConvBlk& p, Cursor& cur, int cin, int cout, int r, bool attn, bool plain = false) {
+  p.cin = roundup(cin, 4); p.cout = cout; p.r = r; p.has_attn = attn;
   const float* w1 = cur.next(); const float* b1 = cur.next();
   if (cur.bad) { set_error("model parameters exhausted in PVConv"); return LION_ERR_ARG; }
   LION_TRY(make_conv(m, p.c1, w1, b1, 27, cin, cout, ident_map(cin)));
-  LION_TRY(make_adagn(m, p.g1, cur, cout));
+  LION_TRY(make_adagn(m, p.g1, cur, cout, plain));
   const float* w2 = cur.next(); const float* b2 = cur.next();
   if (cur.bad) { set_error("model parameters exhausted in PVConv"); return LION_ERR_ARG; }
   LION_TRY(make_conv(m, p.c2, w2, b2, 27, cout, cout, ident_map(cout)));
-  LION_TRY(make_adagn(m, p.g2, cur, cout));
+  LION_TRY(make_adagn(m, p.g2, cur, cout, plain));
   p.se1 = cur.next(); p.se2 = cur.next();
   // state_dict order of the reference PVConv: voxel_layers, attn, point_features (pvcnn2_ada.py:227-233)
   if (attn) LION_TRY(make_attn(m, p.attn, cur, cout, 4));
-  LION_TRY(make_shared_mlp(m, p.point, cur, cin, ident_map(cin), {cout}));
+  LION_TRY(make_shared_mlp(m, p.point, cur, cin, ident_map(cin), {cout}, plain));
   if (cur.bad) { set_error("model parameters exhausted in PVConv"); return LION_ERR_ARG; }
   return 0;
 }
-int make_sa(Model* m, SABlk& s, Cursor& cur, int cfeat, int mcent, float radius, int k, const std::vector<int>& outs) {
+int make_sa(Model* m, SABlk& s, Cursor& cur, int cfeat, int mcent, float radius, int k, const std::vector<int>& outs, bool plain = false) {
   s.cfeat = cfeat; s.m = mcent; s.radius = radius; s.k = k;
   if (cfeat % 4) { set_error("SA feature channels must be a multiple of 4 (got %d)", cfeat); return LION_ERR_ARG; }
   if (k != 32) { set_error("SA module: num_neighbors must be 32 (got %d)", k); return LION_ERR_ARG; }
@@ -209,7 +211,7 @@ int make_sa(Model* m, SABlk& s, Cursor& cur, int cfeat, int mcent, float radius,
   std::vector<int> kmap(4 + cfeat, -1);
   kmap[0] = 0; kmap[1] = 1; kmap[2] = 2;
   for (int i = 0; i < cfeat; ++i) kmap[4 + i] = 3 + i;
-  return make_shared_mlp(m, s.mlp, cur, cfeat + 3, kmap, outs);
+  return make_shared_mlp(m, s.mlp, cur, cfeat + 3, kmap, outs, plain);
 }
 int make_fp(Model* m, FPBlk& f, Cursor& cur, int cc, int cp, const std::vector<int>& outs) {
   f.cc = cc; f.cp = cp;
@@ -274,11 +276,10 @@ static ConvGeom geom_grid(int r) {
 
 // out rows in [p_begin,p_end) of every (b, group < Gout_store); statistics optional
 static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store,
-                    double* ssum, double* ssq, const ConvGeom& geo, const AffineJob* aff = nullptr) {
+                    double* ssum, double* ssq, const ConvGeom& geo) {
   if (Gin * 4 != w.cin_pad) { set_error("conv: input has %d channels, weights expect %d", Gin * 4, w.cin_pad); return LION_ERR_ARG; }
   if (conv_tc_usable(w, geo))
-    return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B, aff);
-  if (aff) { set_error("conv: the fused AdaGN fold needs the tensor-core kernel"); return LION_ERR_STATE; }
+    return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B);
   int span = geo.p_end - geo.p_begin;
   if (w.cout_pad == 4) {
     LION_LAUNCH(f.c, k_conv_simt<4>, dim3(cdiv(span, 128), 1, f.B), 128, geo.ntaps * 16 * sizeof(float),
@@ -290,9 +291,7 @@ static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* o
   return check_launch(f.c, "conv");
 }
 
-// AdaGN (+SE) folded into y = scale*x + shift.  On the network path the fold is computed by the last CTA of the
-// producing convolution (conv_gn below -> conv_tc.cu: affine_tail); k_affine_prep is the stand-alone form for
-// producers that are not the tensor-core kernel (stand-alone AdaGN entry point, SIMT convolution).
+// AdaGN (+SE) folded into y = scale*x + shift: k_affine_prep materialises the two [B][C] arrays per layer.
 static int run_affine(Fwd& f, const AdaGNW& g, const double* ssum, const double* ssq, int stat_stride, double count,
                       const float* se1, const float* se2, AffSrc& a) {
   a = AffSrc{nullptr, nullptr, ssum, ssq, stat_stride, g.gamma, g.beta, f.aff + g.style_off, f.m->style_total, count};
@@ -323,27 +322,17 @@ static int alloc_stats(Fwd& f, int stride, double** ssum, double** ssq) {
   return memset_async(f.c, s, 0, bytes);
 }
 
-// convolution + GroupNorm statistics + AdaGN(/SE) fold: ONE launch when the tensor-core kernel serves the shape
+// convolution + GroupNorm statistics (epilogue) + AdaGN(/SE) fold (k_affine_prep).
+// Round 2 tried computing the fold in the LAST CTA of the convolution (arrival ticket, no extra launch): measured
+// 1.3-2.0 ms per step SLOWER at B = 32 (profiles/r02_affine_fold_ab.json) -- a single SM folding 2048-4096 (b, c) pairs
+// with cold code on the critical path loses to a 32-CTA kernel whose launch latency the graph mostly hides -- so the
+// separate launch stays.
 static int conv_gn(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, const ConvGeom& geo,
                    const AdaGNW& g, double count, const float* se1, const float* se2, AffSrc& a) {
   double *ssum, *ssq;
   LION_TRY(alloc_stats(f, w.cout_pad, &ssum, &ssq));
-  if (!conv_tc_usable(w, geo) || (size_t)f.B * g.C * 9 / 8 * sizeof(float) > 96 * 1024) {
-    LION_TRY(run_conv(f, w, in, Gin, out, Gout_store, ssum, ssq, geo));
-    return run_affine(f, g, ssum, ssq, w.cout_pad, count, se1, se2, a);
-  }
-  a = AffSrc{nullptr, nullptr, ssum, ssq, w.cout_pad, g.gamma, g.beta, f.aff + g.style_off, f.m->style_total, count};
-  AffineJob J;
-  J.scale = f.c->alloc_n<float>((size_t)f.B * g.C);
-  J.shift = f.c->alloc_n<float>((size_t)f.B * g.C);
-  J.gamma = g.gamma; J.beta = g.beta; J.fb = f.aff + g.style_off; J.fb_stride = f.m->style_total;
-  J.se_w1 = se1; J.se_w2 = se2; J.C = g.C; J.count = count;
-  double *t0, *t1;
-  LION_TRY(alloc_stats(f, 1, &t0, &t1));                 // 2*B zeroed doubles from the statistics pool: the arrival counter
-  (void)t1;
-  J.ticket = (unsigned*)t0;
-  a.scale = J.scale; a.shift = J.shift;
-  return run_conv(f, w, in, Gin, out, Gout_store, ssum, ssq, geo, &J);
+  LION_TRY(run_conv(f, w, in, Gin, out, Gout_store, ssum, ssq, geo));
+  return run_affine(f, g, ssum, ssq, w.cout_pad, count, se1, se2, a);
 }
 
 // SharedMLP on a PF.  pool: 1, or 32 = max over neighbour rows after the last activation.
@@ -524,6 +513,43 @@ static float bits_to_float(int v) { float f; memcpy(&f, &v, 4); return f; }
 //        n_fp, {n_mlp, mlp..., has_conv, oc, nblk, res}*]
 // The level/block structure restates create_pointnet2_sa_components / create_pointnet2_fp_modules
 // (models/pvcnn2_ada.py:448-567) including their quirks.
+// the set-abstraction half of a PVCNN2 network: restates create_pointnet2_sa_components (models/pvcnn2_ada.py:448-517 and
+// the non-Ada twin models/pvcnn2.py:440-509) including their quirk that levels > 0 keep only their first PVConv.
+// Reads n_sa records {has_conv, oc, nblk, res, m, radius_bits, k, n_mlp, mlp...} from d at q.
+static int build_sa_levels(Model* m, Cursor& cur, const std::vector<int>& d, size_t& q, int n_sa, int E, bool use_att, bool plain,
+                           std::vector<std::vector<Block>>& levels, std::vector<int>& sa_in, int& in_ch) {
+  auto rd = [&](int& v) { if (q >= d.size()) return false; v = d[q++]; return true; };
+  for (int c = 0; c < n_sa; ++c) {
+    int has_conv, oc, nblk, res, mc, rbits, kk, nm;
+    if (!(rd(has_conv) && rd(oc) && rd(nblk) && rd(res) && rd(mc) && rd(rbits) && rd(kk) && rd(nm))) { set_error("descriptor truncated (sa)"); return LION_ERR_ARG; }
+    std::vector<int> mlp(nm);
+    for (int i = 0; i < nm; ++i) if (!rd(mlp[i])) { set_error("descriptor truncated (sa mlp)"); return LION_ERR_ARG; }
+    std::vector<Block> blocks;
+    sa_in.push_back(in_ch);
+    int k = 0;
+    if (has_conv) {
+      for (int p = 0; p < nblk; ++p) {
+        bool att = ((c + 1) % 2 == 0) && use_att && p == 0;
+        if (c == 0 || k == 0) {
+          blocks.emplace_back();
+          blocks.back().kind = LION_KIND_PVCONV;
+          LION_TRY(make_pvconv(m, blocks.back().pv, cur, (c == 0 || k > 0) ? in_ch : in_ch + E, oc, res, att, plain));
+        }
+        in_ch = oc;
+        k++;
+      }
+    }
+    int cfeat = in_ch + (k == 0 ? E : 0);
+    blocks.emplace_back();
+    blocks.back().kind = LION_KIND_SA;
+    float radius; memcpy(&radius, &rbits, 4);
+    LION_TRY(make_sa(m, blocks.back().sa, cur, cfeat, mc, radius, kk, mlp, plain));
+    in_ch = mlp.back();
+    levels.push_back(std::move(blocks));
+  }
+  return 0;
+}
+
 static int build_unet(Model* m, Cursor& cur) {
   const std::vector<int>& d = m->desc;
   size_t q = 0;
@@ -535,7 +561,7 @@ static int build_unet(Model* m, Cursor& cur) {
         rd(u.clip_dim) && rd(u.S) && rd(n_sa))) { set_error("unet descriptor too short"); return LION_ERR_ARG; }
   m->S = u.S;
   int E = u.embed_dim;
-  if (u.input_dim != 3 || u.extra + u.input_dim != 4) { set_error("unet: only 3+1 channel latent points are supported"); return LION_ERR_ARG; }
+  if (u.input_dim != 3 || u.extra < 0 || u.extra > 1) { set_error("unet: points must be xyz + at most one extra feature channel"); return LION_ERR_ARG; }
   if (E % 4) { set_error("unet: embed_dim must be a multiple of 4"); return LION_ERR_ARG; }
   if (E > 0) {
     u.e0w = cur.next(); u.e0b = cur.next(); u.e2w = cur.next(); u.e2b = cur.next();
@@ -548,33 +574,7 @@ static int build_unet(Model* m, Cursor& cur) {
   if (u.clip) { u.cfw = cur.next(); u.cfb = cur.next(); u.scw = cur.next(); u.scb = cur.next(); }
   int in_ch = u.extra + u.input_dim;
   std::vector<int> sa_in;
-  for (int c = 0; c < n_sa; ++c) {
-    int has_conv, oc, nblk, res, mc, rbits, kk, nm;
-    if (!(rd(has_conv) && rd(oc) && rd(nblk) && rd(res) && rd(mc) && rd(rbits) && rd(kk) && rd(nm))) { set_error("unet descriptor truncated (sa)"); return LION_ERR_ARG; }
-    std::vector<int> mlp(nm);
-    for (int i = 0; i < nm; ++i) if (!rd(mlp[i])) { set_error("unet descriptor truncated (sa mlp)"); return LION_ERR_ARG; }
-    std::vector<Block> blocks;
-    sa_in.push_back(in_ch);
-    int k = 0;
-    if (has_conv) {
-      for (int p = 0; p < nblk; ++p) {
-        bool att = ((c + 1) % 2 == 0) && u.use_att && p == 0;
-        if (c == 0 || k == 0) {
-          blocks.emplace_back();
-          blocks.back().kind = LION_KIND_PVCONV;
-          LION_TRY(make_pvconv(m, blocks.back().pv, cur, c == 0 ? in_ch : in_ch + E, oc, res, att));
-        }
-        in_ch = oc;
-        k++;
-      }
-    }
-    int cfeat = in_ch + (k == 0 ? E : 0);
-    blocks.emplace_back();
-    blocks.back().kind = LION_KIND_SA;
-    LION_TRY(make_sa(m, blocks.back().sa, cur, cfeat, mc, bits_to_float(rbits), kk, mlp));
-    in_ch = mlp.back();
-    u.sa.push_back(std::move(blocks));
-  }
+  LION_TRY(build_sa_levels(m, cur, d, q, n_sa, E, u.use_att != 0, false, u.sa, sa_in, in_ch));
   int ch_sa = in_ch;
   sa_in[0] = u.extra + u.input_dim - 3;
   if (u.use_att) LION_TRY(make_attn(m, u.gatt, cur, ch_sa, 8));
@@ -617,13 +617,56 @@ __global__ void k_extract_extra(const float4* __restrict__ x, float4* __restrict
   if (i < total) o[i] = make_float4(x[i].w, 0.f, 0.f, 0.f);
 }
 
-__global__ void k_pm4_to_pm(const float4* __restrict__ src, float* __restrict__ dst, int total, int C) {
-  pdl_prologue();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  float4 v = src[i];
-  float vv[4] = {v.x, v.y, v.z, v.w};
-  for (int j = 0; j < C; ++j) dst[(size_t)i * C + j] = vv[j];
+// descriptor [input_dim, zdim, use_att, n_sa, levels...]; parameters: the SA levels in state_dict order, then mlp.weight/bias
+static int build_style_enc(Model* m, Cursor& cur) {
+  const std::vector<int>& d = m->desc;
+  if (d.size() < 4) { set_error("style encoder descriptor: [input_dim, zdim, use_att, n_sa, levels...]"); return LION_ERR_ARG; }
+  m->senc.reset(new StyleEncBlk());
+  StyleEncBlk& e = *m->senc;
+  e.input_dim = d[0]; e.zdim = d[1];
+  if (e.input_dim != 3) { set_error("style encoder: input_dim must be 3"); return LION_ERR_ARG; }
+  size_t q = 4;
+  int in_ch = e.input_dim;
+  std::vector<int> sa_in;
+  LION_TRY(build_sa_levels(m, cur, d, q, d[3], 0, d[2] != 0, true, e.sa, sa_in, in_ch));
+  e.cfeat = in_ch;
+  e.mlp_w = cur.next(); e.mlp_b = cur.next();
+  if (cur.bad || cur.i != cur.n) { set_error("style encoder: %d parameters given, %d consumed", cur.n, cur.i); return LION_ERR_ARG; }
+  if (e.cfeat % 4) { set_error("style encoder: feature width must be a multiple of 4"); return LION_ERR_ARG; }
+  m->S = 4;   // no style input: every normalisation is a plain GroupNorm
+  return 0;
+}
+
+static int style_enc_forward(Fwd& f, const float* x, float* out, int N) {
+  StyleEncBlk& e = *f.m->senc;
+  Ctx* c = f.c;
+  int B = f.B;
+  float4* c0 = c->alloc_n<float4>((size_t)B * N);
+  LION_LAUNCH(c, k_pad3, cdiv(B * N, 256), 256, 0, x, c0, B * N);
+  float* dummy_style = c->alloc_n<float>((size_t)B * 4);      // never read: all style layers are constant
+  LION_TRY(style_affine_all(f, dummy_style));
+  LION_TRY(stat_pool_begin(f, (size_t)f.m->style_total * B * sizeof(double) + 4096));
+  PF feat; feat.p = c0; feat.G = 1; feat.R = N;
+  const float4* coords = c0;
+  int Ncur = N;
+  for (auto& lvl : e.sa) {
+    for (auto& blk : lvl) {
+      if (blk.kind == LION_KIND_PVCONV) {
+        PF o = alloc_pf(f, blk.pv.cout / 4, Ncur);
+        LION_TRY(pvconv_fwd(f, blk.pv, feat, coords, o.p, o.G, 0));
+        feat = o;
+      } else {
+        PF o = alloc_pf(f, blk.sa.mlp.cout() / 4, blk.sa.m);
+        float4* ctr = c->alloc_n<float4>((size_t)B * blk.sa.m);
+        LION_TRY(sa_fwd(f, blk.sa, feat, coords, ctr, o.p, o.G, 0));
+        feat = o; coords = ctr; Ncur = blk.sa.m;
+      }
+    }
+  }
+  float* pooled = c->alloc_n<float>((size_t)B * e.cfeat);
+  LION_LAUNCH(c, k_max_rows, dim3(feat.G, B), 256, 0, feat.p, pooled, feat.G, Ncur);
+  LION_LAUNCH(c, k_small_linear, B, 128, e.cfeat * sizeof(float), e.mlp_w, e.mlp_b, pooled, e.cfeat, out, 2 * e.zdim, e.cfeat, 2 * e.zdim, 0);
+  return check_launch(c, "style encoder");
 }
 
 // style -> (CLIP mixing, latent_points_ada.py:132-137) -> all 61 AdaGN style Linears in one launch; result in f.aff
@@ -668,16 +711,23 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
     f.aff = f.m->aff_cache;
   }
   LION_TRY(check_launch(c, "unet prologue"));
-  LION_TRY(stat_pool_begin(f, (size_t)f.m->style_total * f.B * sizeof(double) + (size_t)f.m->style_layers.size() * 2 * f.B * sizeof(double) + 4096));   // sum(2*C) doubles per shape + one arrival counter per layer
+  LION_TRY(stat_pool_begin(f, (size_t)f.m->style_total * f.B * sizeof(double) + 4096));   // sum(2*C) doubles per shape
 
   int n_sa = (int)u.sa.size();
   std::vector<const float4*> coords_list(n_sa);
   std::vector<PF> feats_list(n_sa);
   std::vector<int> n_list(n_sa);
-  // level-0 inputs: coords = xyz, features = all 4 channels (the latent itself is a PF with G=1)
+  // level-0 inputs: coords = xyz, features = all input channels (the latent x[B,N,4] itself is a PF with G=1; a
+  // 3-channel cloud x[B,N,3] (PointTransPVC) is padded to (x, y, z, 0), which serves as coordinates AND features)
   float4* c0 = c->alloc_n<float4>((size_t)B * N);
-  LION_LAUNCH(c, k_make_coords, cdiv(B * N, 256), 256, 0, (const float4*)x, c0, B * N);
-  PF feat; feat.p = (float4*)x; feat.G = 1; feat.R = N;
+  PF feat; feat.G = 1; feat.R = N;
+  if (u.extra == 0) {
+    LION_LAUNCH(c, k_pad3, cdiv(B * N, 256), 256, 0, x, c0, B * N);
+    feat.p = c0;
+  } else {
+    LION_LAUNCH(c, k_make_coords, cdiv(B * N, 256), 256, 0, (const float4*)x, c0, B * N);
+    feat.p = (float4*)x;
+  }
   // furthest-point sampling of all levels depends on coordinates only: a chain of 1360 latency-
   // bound rounds on 32 SMs.  Fork it onto the side stream so it hides under the first PVConvs.
   std::vector<float4*> fps_centers(n_sa, nullptr);
@@ -738,11 +788,12 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   }
   // skip features of level 0 are the extra channels only (inputs[:, 3:], :153): packed as
   // one group [f, 0, 0, 0]
-  {
+  if (u.extra == 1) {
     PF s0 = alloc_pf(f, 1, N);
-    if (u.extra != 1) { set_error("unet: extra_feature_channels must be 1"); return LION_ERR_ARG; }
     LION_LAUNCH(c, k_extract_extra, cdiv(B * N, 256), 256, 0, (const float4*)x, s0.p, B * N);
     feats_list[0] = s0;
+  } else {
+    feats_list[0] = PF();          // no skip features at level 0
   }
   if (u.use_att) {
     PF o = alloc_pf(f, feat.G, Ncur);
@@ -770,9 +821,9 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   if (u.num_classes == 4) {
     LION_TRY(run_conv(f, u.cls2, h.p, h.G, (float4*)out, 1, nullptr, nullptr, geom_rows(Ncur)));
   } else {
-    PF o4 = alloc_pf(f, 1, Ncur);
-    LION_TRY(run_conv(f, u.cls2, h.p, h.G, o4.p, 1, nullptr, nullptr, geom_rows(Ncur)));
-    LION_LAUNCH(c, k_pm4_to_pm, cdiv(B * Ncur, 256), 256, 0, o4.p, out, B * Ncur, u.num_classes);
+    PF o4 = alloc_pf(f, (u.num_classes + 3) / 4, Ncur);
+    LION_TRY(run_conv(f, u.cls2, h.p, h.G, o4.p, o4.G, nullptr, nullptr, geom_rows(Ncur)));
+    LION_LAUNCH(c, k_pf_to_pm, dim3(cdiv(Ncur, 256), o4.G, B), 256, 0, o4.p, out, o4.G, u.num_classes, Ncur);
   }
   return check_launch(c, "unet epilogue");
 }
@@ -863,18 +914,19 @@ extern "C" int lion_model_create(LionCtx* ctx, int kind, const int* desc, int nd
   auto need = [&](int n) { return (int)d.size() >= n; };
   switch (kind) {
     case LION_KIND_UNET: LION_TRY(build_unet(m, cur)); break;
+    // style_dim == 0 selects the non-Ada blocks of models/pvcnn2.py (plain GroupNorm(8), no `emd` parameters, no style)
     case LION_KIND_PVCONV: {   // [cin, cout, r, attn, S]
       LION_REQUIRE(need(5), "pvconv descriptor: [cin, cout, r, attn, style_dim]");
-      m->S = d[4];
+      m->S = d[4] > 0 ? d[4] : 4;
       m->block.reset(new Block()); m->block->kind = kind;
-      LION_TRY(make_pvconv(m, m->block->pv, cur, d[0], d[1], d[2], d[3] != 0));
+      LION_TRY(make_pvconv(m, m->block->pv, cur, d[0], d[1], d[2], d[3] != 0, d[4] == 0));
       break;
     }
     case LION_KIND_SA: {       // [cfeat, m, radius_bits, k, S, n_mlp, mlp...]
       LION_REQUIRE(need(6) && need(6 + d[5]), "sa descriptor: [cfeat, m, radius_bits, k, style_dim, n, outs...]");
-      m->S = d[4];
+      m->S = d[4] > 0 ? d[4] : 4;
       m->block.reset(new Block()); m->block->kind = kind;
-      LION_TRY(make_sa(m, m->block->sa, cur, d[0], d[1], bits_to_float(d[2]), d[3], std::vector<int>(d.begin() + 6, d.begin() + 6 + d[5])));
+      LION_TRY(make_sa(m, m->block->sa, cur, d[0], d[1], bits_to_float(d[2]), d[3], std::vector<int>(d.begin() + 6, d.begin() + 6 + d[5]), d[4] == 0));
       break;
     }
     case LION_KIND_FP: {       // [cc, cp, S, n_mlp, mlp...]
@@ -893,12 +945,13 @@ extern "C" int lion_model_create(LionCtx* ctx, int kind, const int* desc, int nd
     }
     case LION_KIND_SHARED_MLP: {   // [cin, S, n, outs...]
       LION_REQUIRE(need(3) && need(3 + d[2]), "shared_mlp descriptor: [cin, style_dim, n, outs...]");
-      m->S = d[1];
+      m->S = d[1] > 0 ? d[1] : 4;
       m->mlp.reset(new SharedMLPBlk());
-      LION_TRY(make_shared_mlp(m, *m->mlp, cur, d[0], ident_map(d[0]), std::vector<int>(d.begin() + 3, d.begin() + 3 + d[2])));
+      LION_TRY(make_shared_mlp(m, *m->mlp, cur, d[0], ident_map(d[0]), std::vector<int>(d.begin() + 3, d.begin() + 3 + d[2]), d[1] == 0));
       break;
     }
     case LION_KIND_GLOBAL_PRIOR: LION_TRY(global_prior_build(m, cur)); break;
+    case LION_KIND_STYLE_ENC: LION_TRY(build_style_enc(m, cur)); break;
     case LION_KIND_ADAGN: {        // [C, S]
       LION_REQUIRE(need(2), "adagn descriptor: [C, style_dim]");
       m->S = d[1];
@@ -936,6 +989,13 @@ extern "C" int lion_unet_forward(LionModel* h, const float* x, const float* t, c
   LION_REQUIRE(x && out && B > 0 && N > 0, "lion_unet_forward: bad arguments");
   Model* m = &h->m;
   return two_pass(m, stream, B, [&](Fwd& f) { return unet_forward(f, x, t, style, clip, out, N); });
+}
+
+extern "C" int lion_style_encoder_forward(LionModel* h, const float* x, float* out, int B, int N, void* stream) {
+  LION_REQUIRE(h && h->m.kind == LION_KIND_STYLE_ENC, "lion_style_encoder_forward: not a style-encoder model");
+  LION_REQUIRE(x && out && B > 0 && N > 0, "lion_style_encoder_forward: bad arguments");
+  Model* m = &h->m;
+  return two_pass(m, stream, B, [&](Fwd& f) { return style_enc_forward(f, x, out, N); });
 }
 
 // Hoists everything that depends on the style only out of the denoising loop (the reference recomputes the 61 AdaGN
@@ -984,12 +1044,12 @@ float4* to_c4(Fwd& f, const float* src, int N) {
 extern "C" int lion_pvconv_fwd(LionModel* h, const float* features, const float* coords, const float* style, float* out,
                                int B, int N, void* stream) {
   LION_REQUIRE(h && h->m.kind == LION_KIND_PVCONV, "lion_pvconv_fwd: not a pvconv model");
-  LION_REQUIRE(features && coords && style && out && B > 0 && N > 0, "lion_pvconv_fwd: bad arguments");
+  LION_REQUIRE(features && coords && (style || h->m.desc[4] == 0) && out && B > 0 && N > 0, "lion_pvconv_fwd: bad arguments");
   Model* m = &h->m;
   return two_pass(m, stream, B, [&](Fwd& f) {
     const PVConvBlk& p = m->block->pv;
-    LION_TRY(style_affine_all(f, style));
-    PF x = to_pf(f, features, p.cin, N);
+    LION_TRY(style_affine_all(f, style ? style : f.c->alloc_n<float>((size_t)B * 4)));
+    PF x = to_pf(f, features, m->desc[0], N);
     float4* c4 = to_c4(f, coords, N);
     PF o = alloc_pf(f, p.cout / 4, N);
     LION_TRY(pvconv_fwd(f, p, x, c4, o.p, o.G, 0));
@@ -1001,11 +1061,11 @@ extern "C" int lion_pvconv_fwd(LionModel* h, const float* features, const float*
 extern "C" int lion_sa_module_fwd(LionModel* h, const float* features, const float* coords, const float* style,
                                   float* out_features, float* out_coords, int B, int N, void* stream) {
   LION_REQUIRE(h && h->m.kind == LION_KIND_SA, "lion_sa_module_fwd: not an SA model");
-  LION_REQUIRE(features && coords && style && out_features && out_coords && B > 0 && N > 0, "lion_sa_module_fwd: bad arguments");
+  LION_REQUIRE(features && coords && (style || h->m.desc[4] == 0) && out_features && out_coords && B > 0 && N > 0, "lion_sa_module_fwd: bad arguments");
   Model* m = &h->m;
   return two_pass(m, stream, B, [&](Fwd& f) {
     const SABlk& s = m->block->sa;
-    LION_TRY(style_affine_all(f, style));
+    LION_TRY(style_affine_all(f, style ? style : f.c->alloc_n<float>((size_t)B * 4)));
     PF x = to_pf(f, features, s.cfeat, N);
     float4* c4 = to_c4(f, coords, N);
     float4* ctr = f.c->alloc_n<float4>((size_t)B * s.m);
@@ -1055,11 +1115,11 @@ extern "C" int lion_linear_attention_fwd(LionModel* h, const float* x, float* ou
 
 extern "C" int lion_shared_mlp_fwd(LionModel* h, const float* x, const float* style, float* out, int B, int R, void* stream) {
   LION_REQUIRE(h && h->m.kind == LION_KIND_SHARED_MLP, "lion_shared_mlp_fwd: not a shared-mlp model");
-  LION_REQUIRE(x && style && out && B > 0 && R > 0, "lion_shared_mlp_fwd: bad arguments");
+  LION_REQUIRE(x && (style || h->m.desc[1] == 0) && out && B > 0 && R > 0, "lion_shared_mlp_fwd: bad arguments");
   Model* m = &h->m;
   return two_pass(m, stream, B, [&](Fwd& f) {
     const SharedMLPBlk& s = *m->mlp;
-    LION_TRY(style_affine_all(f, style));
+    LION_TRY(style_affine_all(f, style ? style : f.c->alloc_n<float>((size_t)B * 4)));
     PF xi = to_pf(f, x, s.conv[0].cin_ref, R);
     PF o = alloc_pf(f, s.cout() / 4, R);
     LION_TRY(shared_mlp_fwd(f, s, xi, 1, o.p, o.G, 0));

@@ -297,11 +297,53 @@ __global__ void k_style_linear(const StyleLayer* __restrict__ layers, const floa
   for (int i = threadIdx.x; i < S; i += blockDim.x) s_style[i] = style[(size_t)b * S + i];
   __syncthreads();
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (!L.w) {     // plain GroupNorm (non-Ada blocks): factor = 1, bias = 0
+    for (int o = threadIdx.x; o < L.n_out; o += blockDim.x) out[(size_t)b * out_stride + L.out_off + o] = o < L.n_out / 2 ? 1.0f : 0.0f;
+    return;
+  }
   for (int o = wid; o < L.n_out; o += nw) {
     float a = 0.0f;
     for (int k = lane; k < S; k += 32) a = fmaf(L.w[(size_t)o * S + k], s_style[k], a);
     a = warp_sum(a);
     if (lane == 0) out[(size_t)b * out_stride + L.out_off + o] = a + L.b[o];
+  }
+}
+
+// max over the rows of a PF: out[b][c] = max_i in[b][c/4][i].c%4   (PointNetPlusEncoder: features.max(-1), shapelatent_modules.py:46)
+__global__ void k_max_rows(const float4* __restrict__ in, float* __restrict__ out, int G, int R) {
+  pdl_prologue();
+  int b = blockIdx.y, g = blockIdx.x;
+  const float4* src = in + ((size_t)b * G + g) * R;
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int i = threadIdx.x; i < R; i += blockDim.x) m = f4_max(m, src[i]);
+  m.x = warp_max(m.x); m.y = warp_max(m.y); m.z = warp_max(m.z); m.w = warp_max(m.w);
+  __shared__ float4 s_m[8];
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) s_m[wid] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = f4_max(m, s_m[w]);
+    *reinterpret_cast<float4*>(out + ((size_t)b * G + g) * 4) = m;
+  }
+}
+// [B][N][3] -> PF / C4 [B][N] float4 (x, y, z, 0): networks whose points carry no extra feature channel
+__global__ void k_pad3(const float* __restrict__ x, float4* __restrict__ o, int total) {
+  pdl_prologue();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) o[i] = make_float4(x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2], 0.0f);
+}
+// PF with G groups -> point-major [B][R][C]
+__global__ void k_pf_to_pm(const float4* __restrict__ src, float* __restrict__ dst, int G, int C, int R) {
+  pdl_prologue();
+  int b = blockIdx.z, g = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  float4 v = src[((size_t)b * G + g) * R + i];
+  float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = g * 4 + j;
+    if (c < C) dst[((size_t)b * R + i) * C + c] = vv[j];
   }
 }
 

@@ -4,7 +4,7 @@ models/latent_points_ada.py (PVCNN2Unet :19-173, LatentPointDecPVC :222-272).
 The whole U-Net forward is ONE C-ABI call (`lion_unet_forward`, lion_b200/csrc/net.cu): the
 module tree below only owns the parameters (reference names, so checkpoints load unchanged)
 and describes the architecture to the library.  `PointTransPVC` (the VAE *encoder*, :175-220)
-is not on the sampling path and is not provided.
+runs on the same call with embed_dim = 0 and a 3-channel input.
 """
 import torch
 import torch.nn as nn
@@ -140,8 +140,46 @@ class PVCNN2Unet(nn.Module):
 
 
 class PointTransPVC(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError("lion_b200 covers the sampling path; the VAE encoder (PointTransPVC) is out of scope")
+    """The VAE's latent-point encoder (reference: models/latent_points_ada.py:175-220): the same Ada U-Net with
+    embed_dim = 0, no extra feature channel and 2*zdim + 2*input_dim outputs per point; x [B,N,3], style [B,S] ->
+    {'mu_1d', 'sigma_1d'} [B, N*(input_dim + zdim)].  One lion_unet_forward call; the slicing below is the reference's."""
+    sa_blocks = [
+        ((32, 2, 32), (1024, 0.1, 32, (32, 64))),
+        ((64, 3, 16), (256, 0.2, 32, (64, 128))),
+        ((128, 3, 8), (64, 0.4, 32, (128, 256))),
+        (None, (16, 0.8, 32, (128, 128, 128))),
+    ]
+    fp_blocks = [
+        ((128, 128), (128, 3, 8)),
+        ((128, 128), (128, 3, 8)),
+        ((128, 128), (128, 2, 16)),
+        ((128, 128, 64), (64, 2, 32)),
+    ]
+
+    def __init__(self, zdim, input_dim, args={}):
+        super().__init__()
+        assert zdim > 0
+        self.zdim = zdim
+        self.layers = PVCNN2Unet(2 * zdim + input_dim * 2, embed_dim=0, use_att=1, extra_feature_channels=0,
+                                 input_dim=args.ddpm.input_dim, cfg=args, sa_blocks=self.sa_blocks, fp_blocks=self.fp_blocks,
+                                 dropout=args.ddpm.dropout)
+        self.skip_weight = args.latent_pts.skip_weight
+        self.pts_sigma_offset = args.latent_pts.pts_sigma_offset
+        self.input_dim = input_dim
+
+    @torch.no_grad()
+    def forward(self, inputs):
+        x, style = inputs
+        x = x.detach().to(torch.float32).contiguous()
+        B, N, D = x.shape
+        output = self.layers.forward_point_major(x, style=style)          # [B, N, 2*zdim + 2*input_dim]
+        pt_mu_1d = self.skip_weight * output[:, :, :self.input_dim] + x
+        pt_sigma_1d = output[:, :, self.input_dim:2 * self.input_dim] - self.pts_sigma_offset
+        ft_mu_1d = output[:, :, 2 * self.input_dim:-self.zdim]
+        ft_sigma_1d = output[:, :, -self.zdim:]
+        mu_1d = torch.cat([pt_mu_1d, ft_mu_1d], dim=2).reshape(B, -1).contiguous()
+        sigma_1d = torch.cat([pt_sigma_1d, ft_sigma_1d], dim=2).reshape(B, -1).contiguous()
+        return {'mu_1d': mu_1d, 'sigma_1d': sigma_1d}
 
 
 class LatentPointDecPVC(nn.Module):

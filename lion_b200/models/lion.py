@@ -44,7 +44,7 @@ class LION(object):
     def load_model(self, model_path):
         ckpt = torch.load(model_path, weights_only=False)      # released ckpts carry optimizer state (SURVEY 8b hazards)
         self.priors.load_state_dict(ckpt['dae_state_dict'])
-        self.vae.load_state_dict(ckpt['vae_state_dict'], strict=False)   # encoders are out of scope
+        self.vae.load_state_dict(ckpt['vae_state_dict'])                 # strict, like the reference (models/lion.py:32-35): all three sub-networks exist
         print(f'INFO finish loading from {model_path}')
 
     def _run_prior(self, prior, num_samples, shape, condition_input, clip_feat):

@@ -60,7 +60,11 @@ def test_state_dict_key_contract():
     assert shp(PVCNN2Prior(cc.sde, 1, cc)) == keys["prior_clip"]
     assert shp(PriorSEDrop(cfg.sde, 128, cfg)) == keys["global"]
     assert shp(PriorSEClip(cc.sde, 128, cc)) == keys["global_clip"]
-    assert shp(Model(cfg)) == keys["vae_decoder"]
+    vae = shp(Model(cfg))                     # the VAE now carries both encoders as well
+    assert {k: v for k, v in vae.items() if k.startswith("decoder.")} == keys["vae_decoder"]
+    ekeys = json.load(open(os.path.join(ROOT, "tests", "golden", "keys_encoder.json")))
+    assert {k[len("style_encoder."):]: v for k, v in vae.items() if k.startswith("style_encoder.")} == ekeys["style_encoder"]
+    assert {k[len("encoder."):]: v for k, v in vae.items() if k.startswith("encoder.")} == ekeys["point_encoder"]
 
 
 def _header_prototypes():
@@ -96,3 +100,22 @@ def test_integration_shim_names_exist():
     assert len(used) >= 7
     for n in used:
         assert hasattr(lib, n), n
+
+
+def test_vae_state_dict_loads_strict():
+    """A reference `vae_state_dict` (style_encoder + encoder + decoder) loads with strict=True: the key contract of
+    keys.json (decoder) and keys_encoder.json (both encoders, dumped from the reference's own modules)."""
+    import json
+    from lion_b200.config import default_prior_cfg
+    from lion_b200.models.vae_adain import Model
+    from tests.synth import synth_state_dict
+    G = os.path.join(ROOT, "tests", "golden")
+    keys = json.load(open(os.path.join(G, "keys.json")))
+    ekeys = json.load(open(os.path.join(G, "keys_encoder.json")))
+    sd = {}
+    for pre, shapes, seed in (("style_encoder.", ekeys["style_encoder"], 21), ("encoder.", ekeys["point_encoder"], 22),
+                              ("decoder.", keys["decoder"], 13)):
+        sd.update({pre + k: v for k, v in synth_state_dict(shapes, seed).items()})
+    vae = Model(default_prior_cfg())
+    vae.load_state_dict(sd, strict=True)
+    assert set(vae.state_dict()) == set(sd)

@@ -269,3 +269,19 @@ def test_generate_samples_ddim_route():
     torch.manual_seed(9)
     img, nfe, _, _, out = generate_samples_vada_2prior(vae.latent_shape(), dae, diff, vae, 2, False, ddim_step=5)
     assert img.shape == (2, 2048, 3) and torch.isfinite(img).all()
+
+
+@pytest.mark.parametrize("B,clip", [(40, False), (33, True), (5, False), (32, True)])
+def test_global_prior_any_batch_vs_oracle(B, clip):
+    """a18 at batch sizes on both sides of the 32-row tile of the persistent kernel: B > 32 is served in chunks (the
+    reference takes any B, models/score_sde/resnet.py:195-218); every row against the CPU oracle, and bit-reproducible."""
+    m = _global(clip=clip, seed=15 if clip else 14)
+    sd = synth_state_dict(KEYS["global_clip" if clip else "global"], 15 if clip else 14)
+    x, t = gen(71, B, 128, 1, 1), torch.randint(1, 1001, (B,), generator=torch.Generator().manual_seed(3)).float()
+    cf = gen(72, B, 512) if clip else None
+    out = m(x=x.cuda(), t=t.cuda(), clip_feat=None if cf is None else cf.cuda())
+    with torch.no_grad():
+        ref = ON.global_prior_forward(sd, x, t, clip_feat=cf)
+    assert_close(out, ref, 2e-3, "global prior, B=%d%s" % (B, " + CLIP" if clip else ""))
+    again = m(x=x.cuda(), t=t.cuda(), clip_feat=None if cf is None else cf.cuda())
+    assert torch.equal(out, again), "global prior is not bit-reproducible"

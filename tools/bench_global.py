@@ -17,4 +17,19 @@ n = int(os.environ.get("ITERS", "50"))
 e0.record()
 for _ in range(n): m(x=x, t=t)
 e1.record(); torch.cuda.synchronize()
-print(json.dumps({"global_prior_forward_us": e0.elapsed_time(e1) * 1000 / n, "B": B}))
+eager_us = e0.elapsed_time(e1) * 1000 / n
+# the sampling loop replays the step from a CUDA graph: time that too (launch gaps are what the graph removes)
+from lion_b200 import _lib as L
+out = m(x=x, t=t)
+with L.capture_graph() as g:
+    out = m(x=x, t=t)
+for _ in range(3): g.replay()
+torch.cuda.synchronize()
+e0.record()
+for _ in range(n): g.replay()
+e1.record(); torch.cuda.synchronize()
+graph_us = e0.elapsed_time(e1) * 1000 / n
+print(json.dumps({"global_prior_forward_us_eager": eager_us, "global_prior_forward_us_graph": graph_us, "B": B,
+                  "launches_per_forward": L.last_launches(), "LION_GP_PERSISTENT": os.environ.get("LION_GP_PERSISTENT", "1"),
+                  "weights_mb": sum(p.numel() for p in m.parameters()) * 4 / 1e6,
+                  "hbm_gbs_graph": sum(p.numel() for p in m.parameters()) * 4 / 1e3 / graph_us}))
