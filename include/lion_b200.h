@@ -65,6 +65,23 @@ int lion_three_nn_interpolate(const float* points, const float* centers, const f
 int lion_voxel_coords(const float* coords, float* norm_coords, int* vox, int B, int N, int r, int normalize, float eps,
                       void* stream);
 
+/* ---- backward passes of the five differentiable operators (training path).  Reference:
+ * src/bindings.cpp:12-13 gather_features_backward, :19-20 grouping_backward, :24-25
+ * three_nearest_neighbors_interpolate_backward, :29-30 trilinear_devoxelize_backward, :33-34 avg_voxelize_backward
+ * (kernels vox.cu:86-110, trilinear_devox.cu:119-162, grouping.cu:58-77, neighbor_interpolate.cu:145-170,
+ * sampling.cu:52-66).  Same layouts as the forward entry points; grad_x is fully written (zeroed inside where the
+ * gradient is a scatter-add). ---- */
+int lion_avg_voxelize_backward(const float* grad_y /*[B,C,r^3]*/, const int* ind /*[B,N]*/, const int* cnt /*[B,r^3]*/,
+                               float* grad_x /*[B,C,N]*/, int B, int C, int N, int r, void* stream);
+int lion_trilinear_devoxelize_backward(const float* grad_y /*[B,C,N]*/, const int* inds /*[B,8,N]*/, const float* wgts /*[B,8,N]*/,
+                                       float* grad_x /*[B,C,r^3]*/, int B, int C, int N, int r, void* stream);
+int lion_grouping_backward(const float* grad_y /*[B,C,M,U]*/, const int* idx /*[B,M,U]*/, float* grad_x /*[B,C,N]*/, int B, int C,
+                           int N, int M, int U, void* stream);
+int lion_three_nn_interpolate_backward(const float* grad_y /*[B,C,N]*/, const int* idx /*[B,3,N]*/, const float* wgt /*[B,3,N]*/,
+                                       float* grad_x /*[B,C,M]*/, int B, int C, int N, int M, void* stream);
+int lion_gather_backward(const float* grad_y /*[B,C,M]*/, const int* idx /*[B,M]*/, float* grad_x /*[B,C,N]*/, int B, int C, int N,
+                         int M, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Networks and blocks.  A model is created from an int descriptor (architecture) and the
  * module's parameters as device pointers in the reference's state_dict order; the pointers

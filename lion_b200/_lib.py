@@ -41,6 +41,11 @@ def _proto(lib):
         "lion_grouping": (P(vp, vp, vp, i, i, i, i, i, vp), i),
         "lion_three_nn_interpolate": (P(vp, vp, vp, vp, vp, vp, i, i, i, i, vp), i),
         "lion_voxel_coords": (P(vp, vp, vp, i, i, i, i, f, vp), i),
+        "lion_avg_voxelize_backward": (P(vp, vp, vp, vp, i, i, i, i, vp), i),
+        "lion_trilinear_devoxelize_backward": (P(vp, vp, vp, vp, i, i, i, i, vp), i),
+        "lion_grouping_backward": (P(vp, vp, vp, i, i, i, i, i, vp), i),
+        "lion_three_nn_interpolate_backward": (P(vp, vp, vp, vp, i, i, i, i, vp), i),
+        "lion_gather_backward": (P(vp, vp, vp, i, i, i, i, vp), i),
         "lion_model_create": (P(vp, i, C.POINTER(i), i, C.POINTER(vp), i, C.POINTER(vp)), i),
         "lion_model_destroy": (P(vp), i),
         "lion_model_refresh": (P(vp), i),

@@ -417,6 +417,9 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   double V = (double)r * r * r;
   LION_TRY(conv_gn(f, p.c1, g_in, Gin, raw1, Gout, geo1, p.g1, V, nullptr, nullptr, a1));
   LION_LAUNCH(f.c, k_unscatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, vp->ppos, g_in, Gin, N, P);
+  // AdaGN-1 + Swish as a stand-alone pass over the grid (HBM-bound, 86 % of the measured peak).  Round 2 tried to fold
+  // it into conv2's operand staging ("transform on load"): parity-green but 3.5x slower convolutions, deleted --
+  // profiles/r02_xf_transform_on_load_experiment.txt.
   float4* act1 = alloc_vg(f, Gout, r);
   LION_LAUNCH(f.c, k_act_grid, dim3(cdiv(P, 256 * ACT_U), Gout, f.B), 256, 0, raw1, act1, a1, Gout, p.cout, rp, P);
   // conv2 -> (stats) -> AdaGN + SE folded into one affine

@@ -198,6 +198,71 @@ k_voxel_coords_soa(const float* __restrict__ coords, float* __restrict__ norm_co
   }
 }
 
+// ------------------------------------------------------------------------------------
+// backward kernels of the five differentiable operators (reference: voxelization/vox.cu:86-110,
+// interpolate/trilinear_devox.cu:119-162, grouping/grouping.cu:58-77, interpolate/neighbor_interpolate.cu:145-170,
+// sampling/sampling.cu:52-66).  The reference launches one CTA per shape and loops over channels inside a thread;
+// here the grid covers (rows, channel, shape) so all 148 SMs take part and every access along rows is coalesced.
+// Scatter-type gradients accumulate with fp32 atomics like the reference (order-dependent in the last bits).
+// ------------------------------------------------------------------------------------
+// avg_voxelize backward is a pure gather: grad_x[b][c][i] = grad_y[b][c][ind[i]] * (1 / cnt[ind[i]])
+__global__ void k_avg_voxelize_bwd(const float* __restrict__ gy, const int* __restrict__ ind, const int* __restrict__ cnt,
+                                   float* __restrict__ gx, int C, int N, int r3) {
+  pdl_prologue();
+  int b = blockIdx.z, c = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int pos = ind[(size_t)b * N + i];
+  int n = cnt[(size_t)b * r3 + pos];
+  float g = 0.0f;
+  if (n > 0) g = gy[((size_t)b * C + c) * r3 + pos] * (float)(1.0 / (double)(float)n);   // vox.cu:101-104
+  gx[((size_t)b * C + c) * N + i] = g;
+}
+// trilinear devoxelize backward: 8 weighted scatter-adds per (point, channel) into the (pre-zeroed) grid gradient
+__global__ void k_trilinear_devox_bwd(const float* __restrict__ gy, const int* __restrict__ inds, const float* __restrict__ wgts,
+                                      float* __restrict__ gx, int C, int N, int r3) {
+  pdl_prologue();
+  int b = blockIdx.z, c = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  float g = gy[((size_t)b * C + c) * N + i];
+  const int* id = inds + (size_t)b * 8 * N + i;
+  const float* w = wgts + (size_t)b * 8 * N + i;
+  float* dst = gx + ((size_t)b * C + c) * r3;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(dst + id[(size_t)k * N], w[(size_t)k * N] * g);
+}
+// grouping backward: grad_x[b][c][idx[b][j][k]] += grad_y[b][c][j][k]
+__global__ void k_grouping_bwd(const float* __restrict__ gy, const int* __restrict__ idx, float* __restrict__ gx, int C, int N, int MU) {
+  pdl_prologue();
+  int b = blockIdx.z, c = blockIdx.y;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MU) return;
+  atomicAdd(gx + ((size_t)b * C + c) * N + idx[(size_t)b * MU + i], gy[((size_t)b * C + c) * MU + i]);
+}
+// 3-NN interpolation backward: grad_cf[b][c][idx_k[j]] += grad_y[b][c][j] * w_k[j], k = 0..2
+__global__ void k_three_interp_bwd(const float* __restrict__ gy, const int* __restrict__ idx, const float* __restrict__ wgt,
+                                   float* __restrict__ gx, int C, int N, int M) {
+  pdl_prologue();
+  int b = blockIdx.z, c = blockIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float g = gy[((size_t)b * C + c) * N + j];
+  size_t o = (size_t)b * 3 * N + j;
+  float* dst = gx + ((size_t)b * C + c) * M;
+  atomicAdd(dst + idx[o], g * wgt[o]);
+  atomicAdd(dst + idx[o + N], g * wgt[o + N]);
+  atomicAdd(dst + idx[o + 2 * (size_t)N], g * wgt[o + 2 * (size_t)N]);
+}
+// gather backward: grad_x[b][c][idx[b][j]] += grad_y[b][c][j]
+__global__ void k_gather_bwd(const float* __restrict__ gy, const int* __restrict__ idx, float* __restrict__ gx, int C, int N, int M) {
+  pdl_prologue();
+  int b = blockIdx.z, c = blockIdx.y;
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  atomicAdd(gx + ((size_t)b * C + c) * N + idx[(size_t)b * M + j], gy[((size_t)b * C + c) * M + j]);
+}
+
 }  // namespace lion
 
 // =====================================================================================
@@ -298,4 +363,45 @@ extern "C" int lion_voxel_coords(const float* coords, float* norm_coords, int* v
   Ctx c = tmp_ctx(stream);
   LION_LAUNCH(&c, k_voxel_coords_soa, B, VOX_THREADS, 0, coords, norm_coords, vox, N, r, normalize, eps);
   return check_launch(&c, "lion_voxel_coords");
+}
+
+// ---- backward entry points (reference: src/bindings.cpp:12-13,19-20,24-25,29-30,33-34) ------------------------------
+extern "C" int lion_avg_voxelize_backward(const float* grad_y, const int* ind, const int* cnt, float* grad_x, int B, int C,
+                                          int N, int r, void* stream) {
+  LION_REQUIRE(grad_y && ind && cnt && grad_x && B > 0 && C > 0 && N > 0 && r > 0, "lion_avg_voxelize_backward: bad arguments");
+  Ctx c = tmp_ctx(stream);
+  LION_LAUNCH(&c, k_avg_voxelize_bwd, dim3(cdiv(N, 256), C, B), 256, 0, grad_y, ind, cnt, grad_x, C, N, r * r * r);
+  return check_launch(&c, "lion_avg_voxelize_backward");
+}
+extern "C" int lion_trilinear_devoxelize_backward(const float* grad_y, const int* inds, const float* wgts, float* grad_x, int B,
+                                                  int C, int N, int r, void* stream) {
+  LION_REQUIRE(grad_y && inds && wgts && grad_x && B > 0 && C > 0 && N > 0 && r > 0, "lion_trilinear_devoxelize_backward: bad arguments");
+  Ctx c = tmp_ctx(stream);
+  const int r3 = r * r * r;
+  LION_TRY(memset_async(&c, grad_x, 0, sizeof(float) * (size_t)B * C * r3));
+  LION_LAUNCH(&c, k_trilinear_devox_bwd, dim3(cdiv(N, 256), C, B), 256, 0, grad_y, inds, wgts, grad_x, C, N, r3);
+  return check_launch(&c, "lion_trilinear_devoxelize_backward");
+}
+extern "C" int lion_grouping_backward(const float* grad_y, const int* idx, float* grad_x, int B, int C, int N, int M, int U,
+                                      void* stream) {
+  LION_REQUIRE(grad_y && idx && grad_x && B > 0 && C > 0 && N > 0 && M > 0 && U > 0, "lion_grouping_backward: bad arguments");
+  Ctx c = tmp_ctx(stream);
+  LION_TRY(memset_async(&c, grad_x, 0, sizeof(float) * (size_t)B * C * N));
+  LION_LAUNCH(&c, k_grouping_bwd, dim3(cdiv(M * U, 256), C, B), 256, 0, grad_y, idx, grad_x, C, N, M * U);
+  return check_launch(&c, "lion_grouping_backward");
+}
+extern "C" int lion_three_nn_interpolate_backward(const float* grad_y, const int* idx, const float* wgt, float* grad_x, int B,
+                                                  int C, int N, int M, void* stream) {
+  LION_REQUIRE(grad_y && idx && wgt && grad_x && B > 0 && C > 0 && N > 0 && M > 0, "lion_three_nn_interpolate_backward: bad arguments");
+  Ctx c = tmp_ctx(stream);
+  LION_TRY(memset_async(&c, grad_x, 0, sizeof(float) * (size_t)B * C * M));
+  LION_LAUNCH(&c, k_three_interp_bwd, dim3(cdiv(N, 256), C, B), 256, 0, grad_y, idx, wgt, grad_x, C, N, M);
+  return check_launch(&c, "lion_three_nn_interpolate_backward");
+}
+extern "C" int lion_gather_backward(const float* grad_y, const int* idx, float* grad_x, int B, int C, int N, int M, void* stream) {
+  LION_REQUIRE(grad_y && idx && grad_x && B > 0 && C > 0 && N > 0 && M > 0, "lion_gather_backward: bad arguments");
+  Ctx c = tmp_ctx(stream);
+  LION_TRY(memset_async(&c, grad_x, 0, sizeof(float) * (size_t)B * C * N));
+  LION_LAUNCH(&c, k_gather_bwd, dim3(cdiv(M, 256), C, B), 256, 0, grad_y, idx, grad_x, C, N, M);
+  return check_launch(&c, "lion_gather_backward");
 }

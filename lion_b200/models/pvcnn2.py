@@ -43,7 +43,7 @@ class SharedMLP(nn.Module):
         return _gn_params(self.layers)
 
     @torch.no_grad()
-    def _apply(self, x):
+    def _fwd(self, x):
         shape = x.shape
         x = _f32c(x).reshape(shape[0], shape[1], -1)
         B, _, R = x.shape
@@ -55,8 +55,8 @@ class SharedMLP(nn.Module):
 
     def forward(self, inputs):
         if isinstance(inputs, (list, tuple)):
-            return (self._apply(inputs[0]), *inputs[1:])
-        return self._apply(inputs)
+            return (self._fwd(inputs[0]), *inputs[1:])
+        return self._fwd(inputs)
 
 
 class PVConv(nn.Module):

@@ -6,6 +6,7 @@ from timeit import default_timer as timer
 
 import torch
 
+from ..utils.diffusion_continuous import DiffusionBase
 from ..utils.diffusion_pvd import DiffusionDiscretized
 
 
@@ -15,11 +16,25 @@ def generate_samples_vada_2prior(shape, dae, diffusion, vae, num_samples, enable
                                  need_denoise=False, ddim_step=0, clip_feat=None, cls_emb=None, ddim_skip_type='uniform',
                                  ddim_kappa=1.0):
     output = {}
+    assert cls_emb is None, 'lion_b200: class-conditional sampling (cls_emb) is not part of the shipped prior configs'
     if ode_sample == 1:
-        raise NotImplementedError("lion_b200: ODE sampling is off in every shipped config (sde.ode_sample=0)")
+        # probability-flow ODE route (train_2prior.py:64-80): both priors through the adaptive host-side RK45 solver
+        assert isinstance(diffusion, DiffusionBase), 'ODE-based sampling requires cont. diffusion!'
+        assert ode_eps is not None and ode_solver_tol is not None
+        start = timer()
+        condition_input, eps_list = None, []
+        nfe, time_ode_solve = 0, 0.0
+        for i in range(len(dae)):
+            eps, nfe, time_ode_solve = diffusion.sample_model_ode(dae[i], num_samples, shape[i], ode_eps, ode_solver_tol,
+                                                                  enable_autocast, temp, noise, condition_input=condition_input,
+                                                                  clip_feat=clip_feat)
+            condition_input = eps
+            eps_list.append(eps)
+            output['sampled_eps'] = eps
+        eps = vae.compose_eps(eps_list)
+        return _finish(output, eps, vae, num_samples, cls_emb, start, nfe, time_ode_solve)
     assert isinstance(diffusion, DiffusionDiscretized), 'Regular sampling requires disc. diffusion!'
     assert noise is None, 'Noise is not used in ancestral sampling.'
-    assert cls_emb is None, 'lion_b200: class-conditional sampling (cls_emb) is not part of the shipped prior configs'
     nfe = diffusion._diffusion_steps
     time_ode_solve = 999.999
     start = timer()
@@ -42,6 +57,11 @@ def generate_samples_vada_2prior(shape, dae, diffusion, vae, num_samples, enable
         output['sampled_eps'] = eps
     eps = vae.compose_eps(all_eps)
     output['eps_list'] = eps_list
+    return _finish(output, eps, vae, num_samples, cls_emb, start, nfe, time_ode_solve)
+
+
+def _finish(output, eps, vae, num_samples, cls_emb, start, nfe, time_ode_solve):
+    """the shared tail of both routes (train_2prior.py:112-127): statistics, decoder, timing tensors"""
     output['print/sample_mean_global'] = eps.view(num_samples, -1).mean(-1).mean()
     output['print/sample_var_global'] = eps.view(num_samples, -1).var(-1).mean()
     decomposed_eps = vae.decompose_eps(eps)
