@@ -141,23 +141,23 @@ def cpu_threads():
     return max(1, min(32, os.cpu_count() or 1))
 
 
-def cpu_reference_sample(local_steps=1, global_steps=1):
+def cpu_reference_sample(local_steps=1, global_steps=1, batch=1):
     """Bounded sample of the reference's CPU path (oracle port, oracle/net.py): `local_steps`
-    PVCNN2Prior denoising steps + `global_steps` global-prior steps at B=1.  The decoder pass
+    PVCNN2Prior denoising steps + `global_steps` global-prior steps at batch `batch`.  The decoder pass
     (58.5 GFLOP, same U-Net minus the time embedding) is costed as one PVCNN2Prior step (59.7 GFLOP).
     Returns (shapes_per_sec extrapolated to 1000 + 1000 + 1 network evaluations, detail)."""
     import torch
     from oracle import net as ON
     from tests.synth import synth_state_dict
     torch.set_num_threads(cpu_threads())
-    st = _CPU_STATE
+    st = _CPU_STATE.setdefault(batch, {})
     if not st:
         keys = json.load(open(os.path.join(ROOT, "tests", "golden", "keys.json")))
         st["sd_l"], st["sd_g"] = synth_state_dict(keys["prior"], 11), synth_state_dict(keys["global"], 14)
         g = torch.Generator().manual_seed(0)
-        st["x"] = torch.randn(1, 8192, 1, 1, generator=g)
-        st["style"] = torch.randn(1, 128, 1, 1, generator=g)
-        st["t"] = torch.full((1,), 500.0)
+        st["x"] = torch.randn(batch, 8192, 1, 1, generator=g)
+        st["style"] = torch.randn(batch, 128, 1, 1, generator=g)
+        st["t"] = torch.full((batch,), 500.0)
         st["spec"] = ON.prior_spec()
     with torch.no_grad():
         t0 = time.perf_counter()
@@ -168,11 +168,11 @@ def cpu_reference_sample(local_steps=1, global_steps=1):
         for _ in range(global_steps):
             ON.global_prior_forward(st["sd_g"], st["style"], st["t"])
         tg = (time.perf_counter() - t0) / global_steps
-    total = T_STEPS * (tl + tg) + tl           # seconds per shape (decoder ~ one more local step)
-    return 1.0 / total, {"s_per_local_step": tl, "s_per_global_step": tg, "threads": cpu_threads()}
+    total = T_STEPS * (tl + tg) + tl           # seconds per batch (decoder ~ one more local step)
+    return batch / total, {"s_per_local_step": tl, "s_per_global_step": tg, "threads": cpu_threads(), "batch": batch}
 
 
-CPU_SAMPLE = ("%d PVCNN2Prior + %d global-prior denoising step(s) at B=1 on the CPU oracle (port of the reference's PyTorch "
+CPU_SAMPLE = ("%d PVCNN2Prior + %d global-prior denoising step(s) at batch %d on the CPU oracle (port of the reference's PyTorch "
               "path), decoder costed as one PVCNN2Prior step, extrapolated to 1000 + 1000 + 1 evaluations")
 
 
@@ -300,16 +300,17 @@ def run_reference_arm(args):
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        v, detail = cpu_reference_sample(1, 1)
+        v, detail = cpu_reference_sample(1, 1, args.batch)      # the arm's own batch (BASELINE configs[1]: 32 shapes)
         if i >= args.warmup:
             vals.append(v)
     v = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": "shapes/sec (1000-step DDPM, 2048 latent pts, B=32)", "value": v, "unit": "shapes/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 32 / v,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "airplane prior, batch 32, 1000 DDPM steps, 2048 latent pts (configs[1])",
-                       "timed_on": "host CPU, oracle port of the reference's PyTorch path; each step = a bounded sample"},
-            "cpu_baseline": {"value": v, "unit": "shapes/s", "cores": cpu_threads(), "kind": "port", "sample": CPU_SAMPLE % (1, 1),
+            "config": {"workload": "airplane prior, batch %d per GPU, 1000 DDPM steps x (global prior + PVCNN2 latent-point prior) + VAE decoder, 2048 latent pts (BASELINE configs[1])" % args.batch,
+                       "global_batch": args.batch,
+                       "timed_on": "host CPU, oracle port of the reference's PyTorch path; each step = a bounded sample (1 + 1 denoising steps of the whole batch), extrapolated x1000"},
+            "cpu_baseline": {"value": v, "unit": "shapes/s", "cores": cpu_threads(), "kind": "port", "sample": CPU_SAMPLE % (1, 1, args.batch),
                              "detail": detail},
             "e2e": {"value": v, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -576,7 +577,7 @@ def main():
                 "achieved": achieved, "peak": bf16_peak / 2.0, "unit": "TFLOP/s", "frac": achieved / (bf16_peak / 2.0),
                 "ms_per_launch": ms_k.value, "flops_per_launch": fl.value, "peak_source": peak_src, "traffic": None}
     try:   # DRAM bytes of the same kernel from the committed ncu --set full capture (B=32 only)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_fp3_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_conv_fp3_traffic.json")))
         if B == 32:
             roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             roofline["traffic_unit"] = "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; algorithmic %d)" % tr["algorithmic_bytes"]
@@ -585,9 +586,9 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:          # reported on rank 0 at N=1 only
-        cpu_reference_sample(1, 1)                       # warm-up (oneDNN primitive creation)
-        v, detail = cpu_reference_sample(2, 2)
-        cpu = {"value": v, "unit": "shapes/s", "cores": cpu_threads(), "kind": "port", "sample": CPU_SAMPLE % (2, 2), "detail": detail}
+        cpu_reference_sample(1, 1, 4)                    # warm-up (oneDNN primitive creation)
+        v, detail = cpu_reference_sample(1, 1, 4)        # 4 shapes: ~20 s of CPU work on the box's cores
+        cpu = {"value": v, "unit": "shapes/s", "cores": cpu_threads(), "kind": "port", "sample": CPU_SAMPLE % (1, 1, 4), "detail": detail}
 
     def child(cmd, timeout):
         """run a helper in a child process (the reference's kernels exit() on a launch error; nothing there may take

@@ -63,3 +63,32 @@ def test_scheduler_tables_match_oracle_scalars():
             assert False, "expected NotImplementedError"
         except NotImplementedError:
             pass
+
+
+def test_vpsde_closed_forms_cpu():
+    """utils/diffusion_continuous.py:571-621 restated: var / g2 / f / e2int_f / inv_var of the linear-beta VPSDE."""
+    import torch
+    from lion_b200.config import default_prior_cfg
+    from lion_b200.utils.diffusion_continuous import make_diffusion
+    d = make_diffusion(default_prior_cfg().sde)
+    t = torch.tensor([0.0, 0.3, 0.7], dtype=torch.float64)
+    assert torch.allclose(d.var(t), 1.0 - torch.exp(-0.1 * t - 0.5 * 19.9 * t * t))
+    assert torch.allclose(d.g2(t), 0.1 + 19.9 * t) and torch.allclose(d.f(t), -0.5 * d.g2(t))
+    assert torch.allclose(d.inv_var(d.var(t[1:])), t[1:], atol=1e-9)
+    assert torch.allclose(d.e2int_f(t) ** 2, 1.0 - d.var(t), atol=1e-12)
+
+
+def test_cuda_order_mean_emulation_is_a_mean():
+    """oracle/point_ops.py::cuda_mean_lastdim reorders a float32 summation (pinned bit-for-bit against torch-CUDA on the
+    GPU box); on the CPU it must at least be a correct mean for every block shape the configuration formula yields."""
+    import numpy as np
+    import torch
+    from oracle import point_ops as P
+    g = torch.Generator().manual_seed(3)
+    for B, N in [(1, 2048), (32, 1024), (2, 64), (3, 700), (2, 33), (7, 128), (5, 4096), (1, 5)]:
+        x = torch.randn(B, 3, N, generator=g)
+        m = P.cuda_mean_lastdim(x.numpy())
+        ref = x.double().mean(2).numpy()
+        assert np.abs(m - ref).max() < 5e-7, (B, N)
+    nc, vox = P.voxel_coords_cuda_order(torch.randn(2, 3, 256, generator=g).numpy(), 8)
+    assert vox.dtype == torch.int32 and int(vox.min()) >= 0 and int(vox.max()) <= 7
