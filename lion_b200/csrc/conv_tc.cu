@@ -37,6 +37,7 @@ constexpr int THREADS = 96 + 32 * EPI_WARPS;   // warp 0 producer, warps 1-2 MMA
 constexpr int MAX_A_STAGES = 16;   // the A ring is as deep as shared memory allows (Params::a_stages)
 constexpr int B_STAGES = 2;
 constexpr int MAX_ACC = 8;
+constexpr int OCC_SMEM = 1024;       // bytes of per-item occupancy flags kept in shared memory (r <= 38)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   uint64_t* bars = (uint64_t*)(s_stat + 8 * 2 * 64);
   uint32_t* s_tmem = (uint32_t*)(bars + 64);
   volatile uint32_t* s_skip = s_tmem + 1;        // [MAX_A_STAGES] stage holds no data (all-zero input slab)
+  uint8_t* s_occ = (uint8_t*)(s_tmem + 32);      // [OCC_SMEM] this item's 64-row occupancy flags (sparse first convolution)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   const uint32_t bar_full_a = smem_u32(bars), bar_empty_a = smem_u32(bars + MAX_A_STAGES);
@@ -299,7 +301,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       ITEM_DECODE(w)
       (void)n0;
       const float* wsrc = P.w + (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);
-      const unsigned char* occ_b = P.occ ? P.occ + (size_t)b * P.occ_stride : nullptr;
+      // sparse input: the shape's occupancy flags (<= 1 KB) are copied to shared memory once per item -- the per-stage
+      // check below then costs a broadcast LDS instead of 3-4 dependent global loads on the producer's critical path
+      // (with 227 KB of shared memory the L1 is ~1 KB, so every __ldg went to L2)
+      const unsigned char* occ_b = (P.occ && P.occ_stride <= OCC_SMEM) ? s_occ : (P.occ ? P.occ + (size_t)b * P.occ_stride : nullptr);
+      if (P.occ && P.occ_stride <= OCC_SMEM) {
+        __syncwarp();
+        for (int k = lane; k < P.occ_stride; k += 32) s_occ[k] = __ldg(P.occ + (size_t)b * P.occ_stride + k);
+        __syncwarp();
+      }
       const long long row_item = (long long)P.p_begin + (long long)tile0 * 128 - P.halo;
       const float4* in_item = P.in + (size_t)b * P.Gin * P.rows;
       for (int cc = 0; cc < P.nchunk; ++cc) {
@@ -325,7 +335,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
               long long lo = row0 < 0 ? 0 : row0, hi = row0 + P.stage_rows - 1;
               if (hi > P.rows - 1) hi = P.rows - 1;
               unsigned any = 0;
-              for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= __ldg(occ_b + k);
+              for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= occ_b[k];
               empty = (any == 0);
             }
             // multi-tile stages (1x1 only): copy just the rows this item still has, and never past
@@ -701,14 +711,16 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
-  const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128;
+  const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128 + tc::OCC_SMEM;
   long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
   int a_stages = (int)(room / P.a_stage_bytes);
+  // (Measured and dropped: capping the footprint at 196 KB so that the side-stream FPS CTAs -- 24 KB each -- can share an SM
+  //  with a persistent convolution CTA changed nothing, 8.41 vs 8.34 s per pass: profiles/r02_smem_cap_fps_coresidency.txt.)
   if (a_stages > tc::MAX_A_STAGES) a_stages = tc::MAX_A_STAGES;
   { static int as = -1; if (as < 0) { const char* e = getenv("LION_TC_ASTAGES"); as = e ? atoi(e) : 0; } if (as > 0 && as < a_stages) a_stages = as; }
   if (a_stages < 2) { set_error("conv_tc: shared memory cannot hold the operand pipeline (N=%d, KG=%d)", NT, KG); return LION_ERR_ARG; }
   P.a_stages = a_stages;
-  size_t smem = (size_t)a_stages * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128;
+  size_t smem = (size_t)a_stages * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + fixed;
   if (smem > 227 * 1024) { set_error("conv_tc: %zu bytes of shared memory needed", smem); return LION_ERR_ARG; }
   long long n_items = (long long)cdiv(ntile, G) * n_tiles_n * B;
   int grid = (int)(n_items < c->num_sms ? n_items : c->num_sms);      // persistent: one CTA per SM
