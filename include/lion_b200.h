@@ -28,6 +28,11 @@ int lion_ctx_last_launches(LionCtx* ctx);
  * captured on this context has the arena addresses baked in; it must not be replayed once the generation changed
  * (lion_b200._lib.capture_graph checks this and raises). */
 unsigned lion_ctx_generation(LionCtx* ctx);
+/* Diagnostic (contexts created with LION_TIMELINE=1 in the environment only): the network-level forward drops
+ * %globaltimer stamps into both of its streams at block boundaries; this returns the stamps of the last forward
+ * (or of the last replay of a graph captured from it): t_ns[i] and a 24-byte name per entry.  Returns the count,
+ * < 0 on error.  Synchronises the device.  Used by tools/timeline_step.py (the image has no nsys). */
+int lion_ctx_timeline(LionCtx* ctx, unsigned long long* t_ns, char* names, int max_entries);
 size_t lion_ctx_arena_bytes(LionCtx* ctx);
 /* device scratch the context currently owns (arena + persistent zero grid).  Entry points size it with a dry
  * pass and grow it on demand -- outside stream capture: run one eager call per shape before capturing. */

@@ -33,6 +33,7 @@ def _proto(lib):
         "lion_ctx_last_launches": (P(vp), i),
         "lion_ctx_arena_bytes": (P(vp), sz),
         "lion_ctx_generation": (P(vp), C.c_uint),
+        "lion_ctx_timeline": (P(vp, vp, vp, i), i),
         "lion_avg_voxelize": (P(vp, vp, vp, vp, vp, i, i, i, i, vp), i),
         "lion_trilinear_devoxelize": (P(vp, vp, vp, vp, vp, i, i, i, i, i, vp), i),
         "lion_furthest_point_sampling": (P(vp, vp, i, i, i, vp), i),

@@ -49,12 +49,14 @@ const char* get_error();
 // A forward is run twice: a dry pass (no launches) that measures the arena high-water mark,
 // then -- after growing the arena if needed, outside any graph capture -- the real pass.
 // ---------------------------------------------------------------------------------------
+constexpr int LION_MAX_STAMPS = 256;
 struct Ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t aux = nullptr;     // side stream for work that is independent of the main chain (FPS)
   cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_temb = nullptr;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* base = nullptr;      // arena
   char* zgrid = nullptr;     // persistent all-zero voxel grid (scatter target; re-zeroed after use)
@@ -67,8 +69,16 @@ struct Ctx {
   bool dry = false;
   bool pdl = false;          // programmatic dependent launch (LION_PDL=1 enables; measured: no gain in graphs)
   int launches = 0;          // kernels launched by the last real pass (gpu_launches evidence)
+  // > 0 while side-stream kernels (FPS, neighbour searches) are expected in flight: persistent convolution CTAs then
+  // leave this much shared memory unclaimed so that both can be resident on one SM (see conv_tc_run)
+  int conv_smem_cap = 0;
+  // LION_TIMELINE=1 (diagnostic, tools/timeline_step.py): %globaltimer stamps dropped into both streams at block
+  // boundaries -- this image has no nsys, and a step's critical path across the two streams is not visible otherwise
+  unsigned long long* d_stamps = nullptr;
+  int n_stamps = 0;
+  char stamp_names[LION_MAX_STAMPS][24];
 
-  void reset() { off = 0; peak = 0; launches = 0; zgrid_need = 0; }
+  void reset() { off = 0; peak = 0; launches = 0; zgrid_need = 0; n_stamps = 0; }
   // 256-byte aligned sub-allocation; in dry mode returns a fake non-null pointer.
   void* alloc(size_t bytes) {
     size_t a = (off + 255) & ~size_t(255);
@@ -107,6 +117,19 @@ inline cudaError_t launch_pdl(cudaStream_t stream, void (*kernel)(KArgs...), dim
       (ctx)->launches++;                                                               \
     }                                                                                  \
   } while (0)
+
+static __global__ void k_stamp(unsigned long long* p) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *p = t;
+}
+inline void stamp(Ctx* c, cudaStream_t s, const char* name, int idx = -1) {
+  if (!c->d_stamps || c->dry || c->n_stamps >= LION_MAX_STAMPS) return;
+  if (idx >= 0) snprintf(c->stamp_names[c->n_stamps], 24, "%s%d", name, idx);
+  else snprintf(c->stamp_names[c->n_stamps], 24, "%s", name);
+  k_stamp<<<1, 1, 0, s>>>(c->d_stamps + c->n_stamps);
+  c->n_stamps++;
+}
 
 inline int memset_async(Ctx* c, void* p, int v, size_t bytes) {
   if (c->dry || bytes == 0) return 0;

@@ -714,8 +714,16 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128 + tc::OCC_SMEM;
   long long room = 227LL * 1024 - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes;
   int a_stages = (int)(room / P.a_stage_bytes);
-  // (Measured and dropped: capping the footprint at 196 KB so that the side-stream FPS CTAs -- 24 KB each -- can share an SM
-  //  with a persistent convolution CTA changed nothing, 8.41 vs 8.34 s per pass: profiles/r02_smem_cap_fps_coresidency.txt.)
+  // Sharing an SM with the side stream.  FPS and the neighbour searches run on the side stream during the first
+  // ~1 ms of a step (32 CTAs x <= 26 KB of shared memory, latency-bound); a persistent convolution CTA that claims all
+  // 227 KB cannot become resident on their SMs, and with the static item split the whole convolution then takes two
+  // waves (tools/timeline_step.py: the first PVConv's second convolution 340 us instead of 178).  While the caller
+  // flags side-stream work (Ctx::conv_smem_cap) the ring gives up a slot or two -- never below 4 -- and the side
+  // kernels opt into the maximum shared-memory carve-out, because an SM only hosts kernels of one carve-out at a time.
+  if (c->conv_smem_cap > 0 && a_stages >= 5) {
+    int capped = (int)(((long long)c->conv_smem_cap - (long long)fixed - (long long)tc::B_STAGES * P.b_stage_bytes) / P.a_stage_bytes);
+    if (capped >= 4 && capped < a_stages) a_stages = capped;
+  }
   if (a_stages > tc::MAX_A_STAGES) a_stages = tc::MAX_A_STAGES;
   { static int as = -1; if (as < 0) { const char* e = getenv("LION_TC_ASTAGES"); as = e ? atoi(e) : 0; } if (as > 0 && as < a_stages) a_stages = as; }
   if (a_stages < 2) { set_error("conv_tc: shared memory cannot hold the operand pipeline (N=%d, KG=%d)", NT, KG); return LION_ERR_ARG; }

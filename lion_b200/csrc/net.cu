@@ -292,16 +292,30 @@ static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* o
 }
 
 // AdaGN (+SE) folded into y = scale*x + shift: k_affine_prep materialises the two [B][C] arrays per layer.
-static int run_affine(Fwd& f, const AdaGNW& g, const double* ssum, const double* ssq, int stat_stride, double count,
-                      const float* se1, const float* se2, AffSrc& a) {
+static PrepJob prep_job(Fwd& f, const AdaGNW& g, const double* ssum, const double* ssq, int stat_stride, double count,
+                        const float* se1, const float* se2, AffSrc& a) {
   a = AffSrc{nullptr, nullptr, ssum, ssq, stat_stride, g.gamma, g.beta, f.aff + g.style_off, f.m->style_total, count};
   float* scale = f.c->alloc_n<float>((size_t)f.B * g.C);
   float* shift = f.c->alloc_n<float>((size_t)f.B * g.C);
-  size_t smem = se1 ? (g.C + g.C / 8) * sizeof(float) : 0;
-  LION_LAUNCH(f.c, k_affine_prep, f.B, g.C, smem, ssum, ssq, stat_stride, g.gamma, g.beta, f.aff + g.style_off,
-              f.m->style_total, se1, se2, scale, shift, g.C, count);
   a.scale = scale; a.shift = shift;
+  return PrepJob{ssum, ssq, stat_stride, g.gamma, g.beta, f.aff + g.style_off, f.m->style_total, se1, se2, scale, shift, g.C, count};
+}
+static int run_prep(Fwd& f, const PrepJob& j0, const PrepJob* j1) {
+  int C = j0.C, njobs = 1;
+  size_t smem = j0.se_w1 ? (j0.C + j0.C / 8) * sizeof(float) : 0;
+  if (j1) {
+    njobs = 2;
+    if (j1->C > C) C = j1->C;
+    size_t s1 = j1->se_w1 ? (j1->C + j1->C / 8) * sizeof(float) : 0;
+    if (s1 > smem) smem = s1;
+  }
+  LION_LAUNCH(f.c, k_affine_prep, dim3(f.B, njobs), C, smem, j0, j1 ? *j1 : j0);
   return check_launch(f.c, "affine_prep");
+}
+static int run_affine(Fwd& f, const AdaGNW& g, const double* ssum, const double* ssq, int stat_stride, double count,
+                      const float* se1, const float* se2, AffSrc& a) {
+  PrepJob j = prep_job(f, g, ssum, ssq, stat_stride, count, se1, se2, a);
+  return run_prep(f, j, nullptr);
 }
 static int stat_pool_begin(Fwd& f, size_t bytes) {
   f.stat_pool = (char*)f.c->alloc(bytes);
@@ -333,6 +347,15 @@ static int conv_gn(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* ou
   LION_TRY(alloc_stats(f, w.cout_pad, &ssum, &ssq));
   LION_TRY(run_conv(f, w, in, Gin, out, Gout_store, ssum, ssq, geo));
   return run_affine(f, g, ssum, ssq, w.cout_pad, count, se1, se2, a);
+}
+// same, but the fold is left to the caller (who merges it with another layer's: run_prep)
+static int conv_gn_deferred(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, const ConvGeom& geo,
+                            const AdaGNW& g, double count, AffSrc& a, PrepJob& job) {
+  double *ssum, *ssq;
+  LION_TRY(alloc_stats(f, w.cout_pad, &ssum, &ssq));
+  LION_TRY(run_conv(f, w, in, Gin, out, Gout_store, ssum, ssq, geo));
+  job = prep_job(f, g, ssum, ssq, w.cout_pad, count, nullptr, nullptr, a);
+  return 0;
 }
 
 // SharedMLP on a PF.  pool: 1, or 32 = max over neighbour rows after the last activation.
@@ -410,27 +433,38 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   float4* g_in = f.c->dry ? (float4*)(uintptr_t)0x1000 : (float4*)f.c->zgrid + ((size_t)rp * rp + rp + 8);
   LION_LAUNCH(f.c, k_scatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, feat.p, vp->order, vp->ppos, vp->len, g_in, Gin, N, P);
   // conv1 (sparse input: empty 64-row blocks are skipped) -> (stats) -> AdaGN + Swish
+  stamp(f.c, f.c->stream, " scatter");
+  // point branch first: conv1x1 -> stats (its fold shares a launch with conv1's below; the activation is applied inside
+  // the devox kernel)
+  const ConvW& pw = p.point.conv[0];
+  PF rawp = alloc_pf(f, Gout, N);
+  AffSrc ap;
+  PrepJob jp, j1;
+  LION_TRY(conv_gn_deferred(f, pw, feat.p, feat.G, rawp.p, Gout, geom_rows(N), p.point.gn[0], (double)N, ap, jp));
+  // conv1 (sparse input: empty 64-row blocks are skipped) -> (stats) -> AdaGN + Swish
   float4* raw1 = alloc_vg(f, Gout, r);
   ConvGeom geo1 = geo;
   geo1.occ = vp->occ; geo1.occ_stride = vp->occ_stride;
   AffSrc a1;
   double V = (double)r * r * r;
-  LION_TRY(conv_gn(f, p.c1, g_in, Gin, raw1, Gout, geo1, p.g1, V, nullptr, nullptr, a1));
-  LION_LAUNCH(f.c, k_unscatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, vp->ppos, g_in, Gin, N, P);
-  // AdaGN-1 + Swish as a stand-alone pass over the grid (HBM-bound, 86 % of the measured peak).  Round 2 tried to fold
-  // it into conv2's operand staging ("transform on load"): parity-green but 3.5x slower convolutions, deleted --
-  // profiles/r02_xf_transform_on_load_experiment.txt.
+  LION_TRY(conv_gn_deferred(f, p.c1, g_in, Gin, raw1, Gout, geo1, p.g1, V, a1, j1));
+  LION_TRY(run_prep(f, j1, &jp));
+  stamp(f.c, f.c->stream, " conv1");
+  // AdaGN-1 + Swish as a stand-alone pass over the grid (HBM-bound).  Round 2 tried to fold it into conv2's operand
+  // staging ("transform on load"): parity-green but 3.5x slower convolutions, deleted --
+  // profiles/r02_xf_transform_on_load_experiment.txt.  Its extra blocks re-zero the scatter grid (was: k_unscatter).
   float4* act1 = alloc_vg(f, Gout, r);
-  LION_LAUNCH(f.c, k_act_grid, dim3(cdiv(P, 256 * ACT_U), Gout, f.B), 256, 0, raw1, act1, a1, Gout, p.cout, rp, P);
+  {
+    const int nb_act = cdiv(P, 256 * ACT_U);
+    LION_LAUNCH(f.c, k_act_grid, dim3(nb_act + cdiv(N, 256), Gout, f.B), 256, 0, raw1, act1, a1, Gout, p.cout, rp, P, nb_act,
+                vp->ppos, g_in, Gin, N);
+  }
+  stamp(f.c, f.c->stream, " act1");
   // conv2 -> (stats) -> AdaGN + SE folded into one affine
   float4* raw2 = alloc_vg(f, Gout, r);
   AffSrc a2;
   LION_TRY(conv_gn(f, p.c2, act1, Gout, raw2, Gout, geo, p.g2, V, p.se1, p.se2, a2));
-  // point branch: conv1x1 -> stats -> affine (activation applied inside the devox kernel)
-  const ConvW& pw = p.point.conv[0];
-  PF rawp = alloc_pf(f, Gout, N);
-  AffSrc ap;
-  LION_TRY(conv_gn(f, pw, feat.p, feat.G, rawp.p, Gout, geom_rows(N), p.point.gn[0], (double)N, nullptr, nullptr, ap));
+  stamp(f.c, f.c->stream, " conv2");
   // voxel -> point gather (+ point branch)
   if (p.has_attn) {
     PF fused = alloc_pf(f, Gout, N);
@@ -456,7 +490,7 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
 // SA module: (features PF, coords) -> (dst PF with Gd groups at g_off, centres C4)
 // pre_fps >= 0: the centres were already sampled on the side stream (event ev[pre_fps])
 static int sa_fwd(Fwd& f, const SABlk& s, PF feat, const float4* c4, float4* centers, float4* dst, int Gd, int g_off,
-                  int pre_fps = -1) {
+                  int pre_fps = -1, const int* pre_nidx = nullptr) {
   int N = feat.R, M = s.m, U = s.k, Gf = s.cfeat / 4;
   if (feat.G != Gf) { set_error("SA: got %d feature channels, expected %d", feat.G * 4, s.cfeat); return LION_ERR_ARG; }
   if (N > FPS_MAX_N) { set_error("SA: N=%d too large for FPS", N); return LION_ERR_ARG; }
@@ -476,9 +510,13 @@ static int sa_fwd(Fwd& f, const SABlk& s, PF feat, const float4* c4, float4* cen
     LION_FPS_DISPATCH(N, VT, LION_FPS_CALL);
 #undef LION_FPS_CALL
   }
-  int* nidx = f.c->alloc_n<int>((size_t)f.B * M * U);
-  float r2 = s.radius * s.radius;
-  LION_LAUNCH(f.c, k_ball_query_c4, dim3(cdiv(M * 32, 256), f.B), 256, 0, centers, c4, nidx, N, M, r2, U);
+  const int* nidx = pre_nidx;                     // ball query already ran on the side stream (behind event ev[pre_fps])
+  if (!nidx) {
+    int* ni = f.c->alloc_n<int>((size_t)f.B * M * U);
+    float r2 = s.radius * s.radius;
+    LION_LAUNCH(f.c, k_ball_query_c4, dim3(cdiv(M * 32, 256), f.B), 256, 0, centers, c4, ni, N, M, r2, U);
+    nidx = ni;
+  }
   PF grp = alloc_pf(f, Gf + 1, M * U);
   LION_LAUNCH(f.c, k_group_gather, dim3(cdiv(M * U, 256), Gf + 1, f.B), 256, 0, feat.p, c4, centers, nidx, grp.p, Gf, N, M, U);
   LION_TRY(check_launch(f.c, "sa grouping"));
@@ -489,14 +527,21 @@ static int sa_fwd(Fwd& f, const SABlk& s, PF feat, const float4* c4, float4* cen
 
 // FP module: interpolate centres' features to the points, concat skip, SharedMLP
 static int fp_fwd(Fwd& f, const FPBlk& b, const float4* pts_c4, int N, const float4* ctr_c4, int M, PF cfeat, PF skip,
-                  float4* dst, int Gd, int g_off) {
+                  float4* dst, int Gd, int g_off, const int* pre_idx = nullptr, const float* pre_wgt = nullptr, int pre_ev = -1) {
   int Gc = b.cc / 4, Gs = roundup(b.cp, 4) / 4;
   if (cfeat.G != Gc || cfeat.R != M) { set_error("FP: centre features mismatch"); return LION_ERR_ARG; }
   if (Gs && (skip.G != Gs || skip.R != N)) { set_error("FP: skip features mismatch (%d groups, expected %d)", skip.G, Gs); return LION_ERR_ARG; }
   size_t mk = f.c->mark();
-  int* idx = f.c->alloc_n<int>((size_t)f.B * N * 3);
-  float* wgt = f.c->alloc_n<float>((size_t)f.B * N * 3);
-  LION_LAUNCH(f.c, k_three_nn_c4, dim3(cdiv(N, 128), f.B), 128, 1024 * sizeof(float4), pts_c4, ctr_c4, idx, wgt, N, M);
+  const int* idx = pre_idx;
+  const float* wgt = pre_wgt;
+  if (idx) {                                      // 3-NN search already ran on the side stream
+    if (!f.c->dry) LION_CHECK_CUDA(cudaStreamWaitEvent(f.c->stream, f.c->ev[pre_ev], 0));
+  } else {
+    int* ii = f.c->alloc_n<int>((size_t)f.B * N * 3);
+    float* ww = f.c->alloc_n<float>((size_t)f.B * N * 3);
+    LION_LAUNCH(f.c, k_three_nn_c4, dim3(cdiv(N, 128), f.B), 128, 1024 * sizeof(float4), pts_c4, ctr_c4, ii, ww, N, M);
+    idx = ii; wgt = ww;
+  }
   PF cat = alloc_pf(f, Gc + Gs, N);
   LION_LAUNCH(f.c, k_interp_rows, dim3(cdiv(N, 128), Gc, f.B), 128, 0, cfeat.p, idx, wgt, cat.p, Gc, M, N, Gc + Gs, 0);
   if (Gs) LION_LAUNCH(f.c, k_copy_groups, dim3(cdiv(N, 256), Gs, f.B), 256, 0, skip.p, cat.p, Gs, Gc + Gs, Gc, N);
@@ -696,14 +741,14 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   Ctx* c = f.c;
   // time embedding: sinusoid -> Linear -> LeakyReLU(0.1) -> Linear  (latent_points_ada.py:53-57, :101-128)
   float* temb = nullptr;
+  float *temb_sinu = nullptr, *temb_h = nullptr;
+  bool temb_pending = false;
   if (E > 0) {
     if (!t) { set_error("unet: this network needs timesteps"); return LION_ERR_ARG; }
     float* sinu = c->alloc_n<float>((size_t)B * E);
     float* h = c->alloc_n<float>((size_t)B * E);
     temb = c->alloc_n<float>((size_t)B * E);
-    LION_LAUNCH(c, k_time_sinusoid, B, 64, 0, t, u.d_freqs, sinu, E / 2, 1.0f);
-    LION_LAUNCH(c, k_small_linear, B, 128, E * sizeof(float), u.e0w, u.e0b, sinu, E, h, E, E, E, 1);
-    LION_LAUNCH(c, k_small_linear, B, 128, E * sizeof(float), u.e2w, u.e2b, h, E, temb, E, E, E, 0);
+    temb_sinu = sinu; temb_h = h;       // launched below, on the side stream: first used at SA level 1
   }
   // AdaGN style Linears (and the CLIP mixing in front of them) depend on the style only, which is constant over the
   // 1000 steps of a sampling run: style == nullptr means "use what lion_unet_cache_style computed"
@@ -734,12 +779,24 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   // furthest-point sampling of all levels depends on coordinates only: a chain of 1360 latency-
   // bound rounds on 32 SMs.  Fork it onto the side stream so it hides under the first PVConvs.
   std::vector<float4*> fps_centers(n_sa, nullptr);
+  // Neighbour searches depend on coordinates only as well: the ball query of level i follows FPS i on the side stream,
+  // the four 3-NN searches of the FP half follow the last FPS (LION_AUX_NN=0: keep them on the main stream).
+  static int aux_nn = -1;
+  if (aux_nn < 0) { const char* e = getenv("LION_AUX_NN"); aux_nn = e ? atoi(e) : 1; }
+  const bool side_nn = aux_nn != 0 && n_sa <= 4;
+  std::vector<int*> sa_nidx(n_sa, nullptr), fp_idx(n_sa, nullptr);
+  std::vector<float*> fp_wgt(n_sa, nullptr);
   {
     const float4* src = c0;
     int ncur = N;
     if (!c->dry) {
       LION_CHECK_CUDA(cudaEventRecord(c->ev_fork, c->stream));
       LION_CHECK_CUDA(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+      static DevOnce carve_once;
+      if (carve_once.need()) {     // side-stream kernels share SMs with the convolutions: same (maximum) carve-out
+        LION_CHECK_CUDA(cudaFuncSetAttribute(k_ball_query_c4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        LION_CHECK_CUDA(cudaFuncSetAttribute(k_three_nn_c4, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      }
     }
     for (int i = 0; i < n_sa && i < 8; ++i) {
       const SABlk& sb = u.sa[i].back().sa;
@@ -752,28 +809,70 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   do {                                                                                                                    \
     if (fps_smem_bytes(ncur) > 48 * 1024)                                                                                 \
       LION_CHECK_CUDA(cudaFuncSetAttribute(k_fps_c4<A_, C_, F_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+    LION_CHECK_CUDA(cudaFuncSetAttribute(k_fps_c4<A_, C_, F_>, cudaFuncAttributePreferredSharedMemoryCarveout,            \
+                                         cudaSharedmemCarveoutMaxShared));                                               \
     k_fps_c4<A_, C_, F_><<<B, FPS_THREADS, fps_smem_bytes(ncur), c->aux>>>(src, fidx, fps_centers[i], ncur, sb.m, VT);    \
   } while (0)
         LION_FPS_DISPATCH(ncur, VT, LION_FPS_CALL);
 #undef LION_FPS_CALL
         c->launches++;
-        LION_CHECK_CUDA(cudaEventRecord(c->ev[i], c->aux));
+        stamp(c, c->aux, "aux:fps", i);
+      }
+      if (side_nn) {
+        sa_nidx[i] = c->alloc_n<int>((size_t)B * sb.m * sb.k);
+        if (!c->dry) {
+          k_ball_query_c4<<<dim3(cdiv(sb.m * 32, 256), B), 256, 0, c->aux>>>(fps_centers[i], src, sa_nidx[i], ncur, sb.m,
+                                                                             sb.radius * sb.radius, sb.k);
+          c->launches++;
+          stamp(c, c->aux, "aux:ballq", i);
+        }
+      }
+      if (!c->dry) LION_CHECK_CUDA(cudaEventRecord(c->ev[i], c->aux));
+      if (i == 0 && temb && !c->dry) {
+        // three tiny dependent launches (~45 us of latency) that nothing needs before level 1
+        k_time_sinusoid<<<B, 64, 0, c->aux>>>(t, u.d_freqs, temb_sinu, E / 2, 1.0f);
+        k_small_linear<<<B, 128, E * sizeof(float), c->aux>>>(u.e0w, u.e0b, temb_sinu, E, temb_h, E, E, E, 1);
+        k_small_linear<<<B, 128, E * sizeof(float), c->aux>>>(u.e2w, u.e2b, temb_h, E, temb, E, E, E, 0);
+        c->launches += 3;
+        stamp(c, c->aux, "aux:temb");
+        LION_CHECK_CUDA(cudaEventRecord(c->ev_temb, c->aux));
+        temb_pending = true;
       }
       src = fps_centers[i];
       ncur = sb.m;
     }
+    if (side_nn && u.fp.size() == (size_t)n_sa) {
+      for (int lvl = n_sa - 1; lvl >= 0; --lvl) {
+        const float4* pts = lvl == 0 ? c0 : fps_centers[lvl - 1];
+        const int npts = lvl == 0 ? N : u.sa[lvl - 1].back().sa.m, nctr = u.sa[lvl].back().sa.m;
+        fp_idx[lvl] = c->alloc_n<int>((size_t)B * npts * 3);
+        fp_wgt[lvl] = c->alloc_n<float>((size_t)B * npts * 3);
+        if (!c->dry) {
+          k_three_nn_c4<<<dim3(cdiv(npts, 128), B), 128, 1024 * sizeof(float4), c->aux>>>(pts, fps_centers[lvl], fp_idx[lvl],
+                                                                                        fp_wgt[lvl], npts, nctr);
+          c->launches++;
+          stamp(c, c->aux, "aux:3nn", lvl);
+          LION_CHECK_CUDA(cudaEventRecord(c->ev[4 + lvl], c->aux));
+        }
+      }
+    }
   }
+  stamp(c, c->stream, "start");
   const float4* coords = c0;
   int Ncur = N;
   bool has_t = temb != nullptr;
   auto with_temb = [&](PF src, PF* dstp) -> int {   // cat(features, temb expanded) (:145)
+    if (temb_pending) { LION_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_temb, 0)); temb_pending = false; }
     PF d = alloc_pf(f, src.G + E / 4, src.R);
     LION_LAUNCH(c, k_copy_groups, dim3(cdiv(src.R, 256), src.G, B), 256, 0, src.p, d.p, src.G, d.G, 0, src.R);
     LION_LAUNCH(c, k_fill_groups, dim3(cdiv(src.R, 256), E / 4, B), 256, 0, temb, E, d.p, d.G, src.G, src.R);
     *dstp = d;
     return check_launch(c, "concat temb");
   };
+  static int share_kb = -1;
+  if (share_kb < 0) { const char* e = getenv("LION_TC_SHARE_KB"); share_kb = e ? atoi(e) : 196; }
   for (int i = 0; i < n_sa; ++i) {
+    c->conv_smem_cap = (i == 0 && share_kb > 0) ? share_kb * 1024 : 0;      // the side stream is busy during level 0
     feats_list[i] = feat; coords_list[i] = coords; n_list[i] = Ncur;
     if (i > 0 && has_t) LION_TRY(with_temb(feat, &feat));
     for (auto& blk : u.sa[i]) {
@@ -781,14 +880,17 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
         PF o = alloc_pf(f, blk.pv.cout / 4, Ncur);
         LION_TRY(pvconv_fwd(f, blk.pv, feat, coords, o.p, o.G, 0));
         feat = o;
+        stamp(c, c->stream, "sa.pvconv", i);
       } else {
         PF o = alloc_pf(f, blk.sa.mlp.cout() / 4, blk.sa.m);
         float4* ctr = fps_centers[i];
-        LION_TRY(sa_fwd(f, blk.sa, feat, coords, ctr, o.p, o.G, 0, i));
+        LION_TRY(sa_fwd(f, blk.sa, feat, coords, ctr, o.p, o.G, 0, i, sa_nidx[i]));
         feat = o; coords = ctr; Ncur = blk.sa.m;
+        stamp(c, c->stream, "sa.module", i);
       }
     }
   }
+  c->conv_smem_cap = 0;
   // skip features of level 0 are the extra channels only (inputs[:, 3:], :153): packed as
   // one group [f, 0, 0, 0]
   if (u.extra == 1) {
@@ -802,6 +904,7 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
     PF o = alloc_pf(f, feat.G, Ncur);
     LION_TRY(attn_fwd(f, u.gatt, feat, o.p, o.G, 0));
     feat = o;
+    stamp(c, c->stream, "global_att");
   }
   for (size_t i = 0; i < u.fp.size(); ++i) {
     int lvl = n_sa - 1 - (int)i;
@@ -810,12 +913,15 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
         PF cf = feat;
         if (has_t) LION_TRY(with_temb(feat, &cf));          // torch.cat([features, temb]) (:160)
         PF o = alloc_pf(f, blk.fp.mlp.cout() / 4, n_list[lvl]);
-        LION_TRY(fp_fwd(f, blk.fp, coords_list[lvl], n_list[lvl], coords, Ncur, cf, feats_list[lvl], o.p, o.G, 0));
+        LION_TRY(fp_fwd(f, blk.fp, coords_list[lvl], n_list[lvl], coords, Ncur, cf, feats_list[lvl], o.p, o.G, 0,
+                        fp_idx[lvl], fp_wgt[lvl], 4 + lvl));
         feat = o; coords = coords_list[lvl]; Ncur = n_list[lvl];
+        stamp(c, c->stream, "fp.module", (int)i);
       } else {
         PF o = alloc_pf(f, blk.pv.cout / 4, Ncur);
         LION_TRY(pvconv_fwd(f, blk.pv, feat, coords, o.p, o.G, 0));
         feat = o;
+        stamp(c, c->stream, "fp.pvconv", (int)i);
       }
     }
   }
@@ -828,6 +934,8 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
     LION_TRY(run_conv(f, u.cls2, h.p, h.G, o4.p, o4.G, nullptr, nullptr, geom_rows(Ncur)));
     LION_LAUNCH(c, k_pf_to_pm, dim3(cdiv(Ncur, 256), o4.G, B), 256, 0, o4.p, out, o4.G, u.num_classes, Ncur);
   }
+  if (temb_pending) LION_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_temb, 0));   // never consumed: still join the side stream
+  stamp(c, c->stream, "end");
   return check_launch(c, "unet epilogue");
 }
 
@@ -877,7 +985,10 @@ extern "C" int lion_ctx_create(int device, LionCtx** out) {
   h->c.num_sms = prop.multiProcessorCount;
   { const char* e = getenv("LION_PDL"); h->c.pdl = (e && atoi(e) != 0); }   // measured: no gain inside CUDA graphs; off by default
   LION_CHECK_CUDA(cudaStreamCreateWithFlags(&h->c.aux, cudaStreamNonBlocking));
+  { const char* e = getenv("LION_TIMELINE");
+    if (e && atoi(e) != 0) LION_CHECK_CUDA(cudaMalloc(&h->c.d_stamps, LION_MAX_STAMPS * sizeof(unsigned long long))); }
   LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev_fork, cudaEventDisableTiming));
+  LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev_temb, cudaEventDisableTiming));
   for (int i = 0; i < 8; ++i) LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev[i], cudaEventDisableTiming));
   if (prop.major != 10) {
     set_error("lion_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
@@ -892,13 +1003,25 @@ extern "C" int lion_ctx_destroy(LionCtx* h) {
   if (h->c.base) cudaFree(h->c.base);
   if (h->c.zgrid) cudaFree(h->c.zgrid);
   if (h->c.aux) cudaStreamDestroy(h->c.aux);
+  if (h->c.d_stamps) cudaFree(h->c.d_stamps);
   if (h->c.ev_fork) cudaEventDestroy(h->c.ev_fork);
+  if (h->c.ev_temb) cudaEventDestroy(h->c.ev_temb);
   for (int i = 0; i < 8; ++i) if (h->c.ev[i]) cudaEventDestroy(h->c.ev[i]);
   delete h;
   return 0;
 }
 extern "C" int lion_ctx_last_launches(LionCtx* h) { return h ? h->c.launches : 0; }
 extern "C" unsigned lion_ctx_generation(LionCtx* h) { return h ? h->c.generation : 0; }
+extern "C" int lion_ctx_timeline(LionCtx* h, unsigned long long* t_ns, char* names, int max_entries) {
+  LION_REQUIRE(h && t_ns && names && max_entries >= 0, "lion_ctx_timeline: null argument");
+  if (!h->c.d_stamps) { set_error("lion_ctx_timeline: the context was created without LION_TIMELINE=1"); return LION_ERR_STATE; }
+  int n = h->c.n_stamps < max_entries ? h->c.n_stamps : max_entries;
+  LION_CHECK_CUDA(cudaSetDevice(h->c.device));
+  LION_CHECK_CUDA(cudaDeviceSynchronize());
+  LION_CHECK_CUDA(cudaMemcpy(t_ns, h->c.d_stamps, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) memcpy(names + (size_t)i * 24, h->c.stamp_names[i], 24);
+  return n;
+}
 extern "C" size_t lion_ctx_arena_bytes(LionCtx* h) { return h ? h->c.cap : 0; }
 extern "C" size_t lion_workspace_bytes(LionCtx* h) { return h ? h->c.cap + h->c.zgrid_cap : 0; }
 

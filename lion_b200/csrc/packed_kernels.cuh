@@ -147,17 +147,6 @@ __global__ void k_scatter(const float4* __restrict__ feat, const int* __restrict
   grid[((size_t)b * G + g) * P + pp] = acc;
 }
 
-// restore the all-zero invariant of the persistent scatter grid: zero exactly the voxels that
-// k_scatter wrote (N*G stores instead of a full-grid memset per PVConv)
-__global__ void k_unscatter(const int* __restrict__ s_ppos, float4* __restrict__ grid, int G, int N, int P) {
-  pdl_prologue();
-  int b = blockIdx.z, g = blockIdx.y;
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= N) return;
-  int pp = s_ppos[(size_t)b * N + s];
-  if (pp >= 0) grid[((size_t)b * G + g) * P + pp] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
 // ------------------------------------------------------------------------------------
 // SIMT reference convolution (3x3x3 over a VG, or 1x1 over a PF with ntaps == 1).
 // Correctness scaffold and small-shape fallback; the tensor-core kernel (conv_tc.cu) has the
@@ -241,50 +230,69 @@ k_conv_simt(const float4* __restrict__ in, const float* __restrict__ Wt, const f
 // y, which is affine in the per-channel mean of x, so its gate folds in as well.
 //   grid = B, block = C (<= 512; C multiple of 8)
 // ------------------------------------------------------------------------------------
-__global__ void k_affine_prep(const double* __restrict__ ssum, const double* __restrict__ ssq, int stat_stride,
-                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                              const float* __restrict__ style_fb /*[B][2C] for this layer*/, int fb_stride,
-                              const float* __restrict__ se_w1 /*[C/8][C] or null*/, const float* __restrict__ se_w2 /*[C][C/8]*/,
-                              float* __restrict__ scale, float* __restrict__ shift, int C, double count) {
+struct PrepJob {
+  const double* ssum; const double* ssq; int stat_stride;
+  const float* gamma; const float* beta;
+  const float* style_fb /*[B][2C] for this layer*/; int fb_stride;
+  const float* se_w1 /*[C/8][C] or null*/; const float* se_w2 /*[C][C/8]*/;
+  float* scale; float* shift; int C; double count;
+};
+// grid = (B, number of jobs <= 2), block = the larger C; dynamic smem = (C + C/8) floats of the largest SE job.
+// Two layers whose statistics are complete at the same point of the stream (a PVConv's first convolution and its
+// point branch) are folded by ONE launch: each tiny launch costs 4-5 us on the step's critical path.
+__global__ void k_affine_prep(PrepJob j0, PrepJob j1) {
   pdl_prologue();
   extern __shared__ float s_f[];   // [C] se input, [C/8] hidden
   __shared__ double s_gs[8], s_gq[8];
+  const PrepJob& J = blockIdx.y == 0 ? j0 : j1;
+  const int C = J.C;
   int b = blockIdx.x, c = threadIdx.x;
+  const bool on = c < C;
   int cpg = C / 8;
   if (c < 8) { s_gs[c] = 0; s_gq[c] = 0; }
   __syncthreads();
-  double s = ssum[(size_t)b * stat_stride + c], q = ssq[(size_t)b * stat_stride + c];
-  atomicAdd(&s_gs[c / cpg], s);
-  atomicAdd(&s_gq[c / cpg], q);
+  double s = 0.0, q = 0.0;
+  if (on) {
+    s = J.ssum[(size_t)b * J.stat_stride + c]; q = J.ssq[(size_t)b * J.stat_stride + c];
+    atomicAdd(&s_gs[c / cpg], s);
+    atomicAdd(&s_gq[c / cpg], q);
+  }
   __syncthreads();
-  double n = count * cpg;
-  double mean = s_gs[c / cpg] / n;
-  double var = s_gq[c / cpg] / n - mean * mean;
-  if (var < 0) var = 0;
-  float rstd = (float)(1.0 / sqrt(var + 1e-5));
-  float f = style_fb[(size_t)b * fb_stride + c], bb = style_fb[(size_t)b * fb_stride + C + c];
-  float ga = gamma[c], be = beta[c];
-  float sc = rstd * ga * f;
-  float sh = (be - (float)mean * rstd * ga) * f + bb;
-  if (se_w1) {
+  float sc = 0.f, sh = 0.f;
+  if (on) {
+    double n = J.count * cpg;
+    double mean = s_gs[c / cpg] / n;
+    double var = s_gq[c / cpg] / n - mean * mean;
+    if (var < 0) var = 0;
+    float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    float f = J.style_fb[(size_t)b * J.fb_stride + c], bb = J.style_fb[(size_t)b * J.fb_stride + C + c];
+    float ga = J.gamma[c], be = J.beta[c];
+    sc = rstd * ga * f;
+    sh = (be - (float)mean * rstd * ga) * f + bb;
+  }
+  if (J.se_w1) {                                   // block-uniform
     int H = C / 8;
     float* s_h = s_f + C;
-    s_f[c] = sc * (float)(s / count) + sh;     // mean over voxels of the AdaGN output
+    if (on) s_f[c] = sc * (float)(s / J.count) + sh;     // mean over voxels of the AdaGN output
     __syncthreads();
     if (c < H) {
       float a = 0.0f;
-      for (int k = 0; k < C; ++k) a = fmaf(se_w1[c * C + k], s_f[k], a);
+      for (int k = 0; k < C; ++k) a = fmaf(J.se_w1[c * C + k], s_f[k], a);
       s_h[c] = fmaxf(a, 0.0f);
     }
     __syncthreads();
-    float a = 0.0f;
-    for (int k = 0; k < H; ++k) a = fmaf(se_w2[c * H + k], s_h[k], a);
-    float gate = 1.0f / (1.0f + expf(-a));
-    sc *= gate;
-    sh *= gate;
+    if (on) {
+      float a = 0.0f;
+      for (int k = 0; k < H; ++k) a = fmaf(J.se_w2[c * H + k], s_h[k], a);
+      float gate = 1.0f / (1.0f + expf(-a));
+      sc *= gate;
+      sh *= gate;
+    }
   }
-  scale[(size_t)b * C + c] = sc;
-  shift[(size_t)b * C + c] = sh;
+  if (on) {
+    J.scale[(size_t)b * C + c] = sc;
+    J.shift[(size_t)b * C + c] = sh;
+  }
 }
 
 // all AdaGN style Linears of a network in one launch: out[b][off_l + o] = W_l[o] . style[b] + bias_l[o]
@@ -426,9 +434,21 @@ __device__ __forceinline__ void aff_block_load(const AffSrc& a, int b, int g, in
 // ACT_U positions per thread, loads issued before any use: a 16-byte access per thread leaves too
 // few bytes in flight per SM to cover HBM latency (4.3 TB/s measured with one access per thread).
 constexpr int ACT_U = 4;
-__global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ out, AffSrc aff, int G, int C, int rp, int P) {
+// Blocks with blockIdx.x >= nb_act do k_unscatter's job instead (us_ppos != null): they restore the all-zero
+// invariant of the persistent scatter grid that the first convolution has finished reading by now (one launch less
+// per PVConv on the critical path); block (x, y, z) zeroes its 256 points in groups y, y + gridDim.y, ... < us_G.
+__global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ out, AffSrc aff, int G, int C, int rp, int P,
+                           int nb_act, const int* __restrict__ us_ppos, float4* __restrict__ us_grid, int us_G, int us_N) {
   pdl_prologue();
   int b = blockIdx.z, g = blockIdx.y;
+  if ((int)blockIdx.x >= nb_act) {
+    int sidx = ((int)blockIdx.x - nb_act) * blockDim.x + threadIdx.x;
+    if (sidx >= us_N) return;
+    int pp = us_ppos[(size_t)b * us_N + sidx];
+    if (pp >= 0)
+      for (int gg = g; gg < us_G; gg += gridDim.y) us_grid[((size_t)b * us_G + gg) * P + pp] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   float4 s, t;
   aff_block_load(aff, b, g, C, s, t);
   const float4* src = in + ((size_t)b * G + g) * P;
