@@ -202,6 +202,11 @@ struct Params {
   int a_stages;          // depth of the A ring
   const unsigned char* occ;   // 64-row occupancy flags of the input (sparse first conv of a PVConv) or null
   int occ_stride;
+  // pooled 1x1 (last layer of a set-abstraction MLP): instead of the [rows][C] result, write per 32 consecutive rows (the
+  // neighbours of one centre = the 32 TMEM lanes of one epilogue warp) the per-channel minimum and maximum,
+  // pool_mm[b][C/4][rows/32][2][4].  AdaGN's affine is monotonic and Swish is quasi-convex (one minimum), so
+  // max_i swish(s*x_i + t) = max(swish(s*min + t), swish(s*max + t)): the consumer needs 2 of the 32 values.
+  float* pool_mm;
 };
 
 // per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
@@ -237,7 +242,37 @@ __device__ __forceinline__ float warp_transpose_sum16(float* v, int lane) {
   }
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
+// same butterfly with min / max: v is destroyed; returns in lane l the extreme over the warp's 32 rows of channel ch16(l)
+template <bool MAX>
+__device__ __forceinline__ float warp_transpose_ext16(float* v, int lane) {
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {
+    const int bit = half * 2;
+    bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      float keep = upper ? v[i + half] : v[i];
+      float send = upper ? v[i] : v[i + half];
+      float got = __shfl_xor_sync(0xffffffffu, send, bit);
+      v[i] = MAX ? fmaxf(keep, got) : fminf(keep, got);
+    }
+  }
+  float o = __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return MAX ? fmaxf(v[0], o) : fminf(v[0], o);
+}
 __device__ __forceinline__ int ch16_of_lane(int lane) { return (lane >> 1) & 15; }
+// pooled epilogue: v[16] = this lane's row, columns col..col+15 of the item's n-tile (bias added); centre = row / 32
+__device__ __forceinline__ void pool_store16(const Params& P, int b, int n0, int col, long long centre, const float* v, int lane) {
+  float lo[16], hi[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { lo[i] = v[i]; hi[i] = v[i]; }
+  const float mn = warp_transpose_ext16<false>(lo, lane);
+  const float mx = warp_transpose_ext16<true>(hi, lane);
+  const int c = n0 + col + ch16_of_lane(lane);
+  const long long ncent = (long long)P.rows / 32;
+  float* dst = P.pool_mm + ((((size_t)b * (P.cout_pad / 4) + (c >> 2)) * ncent + centre) * 2) * 4 + (c & 3);
+  if ((lane & 1) == 0) { dst[0] = mn; dst[4] = mx; }
+}
 
 template <int KG, int TPG>
 __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
@@ -476,7 +511,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
               float v[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = valid ? __uint_as_float(rr[cc][i]) + s_bias[col + i] : 0.0f;
-              if (inrange) {
+              if (P.pool_mm) pool_store16(P, b, n0, col, (long long)(p >> 5), v, lane);     // all rows valid (rows % 128 == 0)
+              else if (inrange) {
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
                   int g = (n0 + col) / 4 + g4;
@@ -516,7 +552,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * P.NT + col), v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = valid ? v[i] + s_bias[col + i] : 0.0f;
-          if (inrange) {
+          if (TPG == 1 && P.pool_mm) pool_store16(P, b, n0, col, (long long)(p >> 5), v, lane);
+          else if (inrange) {
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
               int g = (n0 + col) / 4 + g4;
@@ -656,8 +693,12 @@ bool conv_tc_usable(const ConvW& w, const ConvGeom& geo) {
 }
 
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum, double* ssq,
-                const ConvGeom& geo, int B) {
+                const ConvGeom& geo, int B, float* pool_mm) {
   tc::Params P{};
+  if (pool_mm && (w.ntaps != 1 || geo.p_begin != 0 || geo.p_end != geo.rows || geo.rows % 128)) {
+    set_error("conv_tc: the pooled epilogue needs a 1x1 convolution over a multiple of 128 rows"); return LION_ERR_ARG;
+  }
+  P.pool_mm = pool_mm;
   int NT, KG, nchunk, ntg, tpg;
   tc_shape(w, NT, KG, nchunk, ntg, tpg);
   P.in = in; P.w = w.tc.w; P.bias = w.bias; P.out = out; P.ssum = ssum; P.ssq = ssq;

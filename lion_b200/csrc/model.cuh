@@ -157,6 +157,6 @@ int conv_tc_prepare(Model* m, ConvW& w);
 int conv_tc_pack_job(const PackJob& j);
 bool conv_tc_usable(const ConvW& w, const ConvGeom& geo);
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum,
-                double* ssq, const ConvGeom& geo, int B);
+                double* ssq, const ConvGeom& geo, int B, float* pool_mm = nullptr);
 
 }  // namespace lion

@@ -276,10 +276,11 @@ static ConvGeom geom_grid(int r) {
 
 // out rows in [p_begin,p_end) of every (b, group < Gout_store); statistics optional
 static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store,
-                    double* ssum, double* ssq, const ConvGeom& geo) {
+                    double* ssum, double* ssq, const ConvGeom& geo, float* pool_mm = nullptr) {
   if (Gin * 4 != w.cin_pad) { set_error("conv: input has %d channels, weights expect %d", Gin * 4, w.cin_pad); return LION_ERR_ARG; }
   if (conv_tc_usable(w, geo))
-    return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B);
+    return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B, pool_mm);
+  if (pool_mm) { set_error("conv: the pooled epilogue exists on the tensor-core path only"); return LION_ERR_STATE; }
   int span = geo.p_end - geo.p_begin;
   if (w.cout_pad == 4) {
     LION_LAUNCH(f.c, k_conv_simt<4>, dim3(cdiv(span, 128), 1, f.B), 128, geo.ntaps * 16 * sizeof(float),
@@ -366,10 +367,24 @@ static int shared_mlp_fwd(Fwd& f, const SharedMLPBlk& m, PF in, int pool, float4
   for (int i = 0; i < n; ++i) {
     const ConvW& w = m.conv[i];
     int Gout = w.cout / 4;
-    PF raw = alloc_pf(f, Gout, cur.R);
-    AffSrc a;
-    LION_TRY(conv_gn(f, w, cur.p, cur.G, raw.p, Gout, geom_rows(cur.R), m.gn[i], (double)cur.R, nullptr, nullptr, a));
     bool last = (i == n - 1);
+    AffSrc a;
+    if (last && pool == 32 && cur.R % 128 == 0 && w.cout == w.cout_pad && conv_tc_usable(w, geom_rows(cur.R))) {
+      // pooled last layer: the convolution's epilogue keeps, per centre and channel, the minimum and the maximum over the
+      // 32 neighbours (enough to evaluate max_i swish(affine(x_i)) exactly, see conv_tc.cu: Params::pool_mm); the
+      // [B, C, M, 32] tensor is never written
+      int Ro = cur.R / 32;
+      float* mm = f.c->alloc_n<float>((size_t)f.B * Gout * Ro * 8);
+      double *ssum, *ssq;
+      LION_TRY(alloc_stats(f, w.cout_pad, &ssum, &ssq));
+      LION_TRY(run_conv(f, w, cur.p, cur.G, nullptr, Gout, ssum, ssq, geom_rows(cur.R), mm));
+      LION_TRY(run_affine(f, m.gn[i], ssum, ssq, w.cout_pad, (double)cur.R, nullptr, nullptr, a));
+      LION_LAUNCH(f.c, k_act_pool_minmax, dim3(cdiv(Ro, 256), Gout, f.B), 256, 0, (const float4*)mm, dst, a, Gout, w.cout, Ro, Gd, g_off);
+      LION_TRY(check_launch(f.c, "shared_mlp pooled"));
+      continue;
+    }
+    PF raw = alloc_pf(f, Gout, cur.R);
+    LION_TRY(conv_gn(f, w, cur.p, cur.G, raw.p, Gout, geom_rows(cur.R), m.gn[i], (double)cur.R, nullptr, nullptr, a));
     if (last && pool > 1) {
       if (pool != 32 || cur.R % 32) { set_error("shared_mlp: unsupported pooling %d", pool); return LION_ERR_ARG; }
       int Ro = cur.R / 32;
@@ -391,10 +406,12 @@ static int attn_fwd(Fwd& f, const AttnBlk& a, PF x, float4* dst, int Gd, int g_o
   int hid = a.heads * 32, N = x.R;
   PF qkv = alloc_pf(f, 3 * hid / 4, N);
   LION_TRY(run_conv(f, a.qkv, x.p, x.G, qkv.p, qkv.G, nullptr, nullptr, geom_rows(N)));
-  float* ctx = f.c->alloc_n<float>((size_t)f.B * a.heads * 1024);
-  LION_LAUNCH(f.c, k_attn_ctx, dim3(a.heads, f.B), 256, 0, qkv.p, ctx, a.heads, N);
+  const int S = cdiv(N, ATTN_CHUNK);
+  if (S > 32) { set_error("attention: N=%d too large (max %d points)", N, 32 * ATTN_CHUNK); return LION_ERR_ARG; }
+  float* part = f.c->alloc_n<float>((size_t)f.B * a.heads * S * ATTN_PART);
+  LION_LAUNCH(f.c, k_attn_ctx, dim3(a.heads, f.B, S), 256, 0, qkv.p, part, a.heads, N);
   PF o = alloc_pf(f, hid / 4, N);
-  LION_LAUNCH(f.c, k_attn_apply, dim3(cdiv(N, 128), a.heads, f.B), 128, 0, qkv.p, ctx, o.p, a.heads, N);
+  LION_LAUNCH(f.c, k_attn_apply, dim3(cdiv(N, 128), a.heads, f.B), 128, 0, qkv.p, part, o.p, a.heads, N, S);
   LION_TRY(check_launch(f.c, "attention"));
   if (Gd != a.C / 4 || g_off != 0) { set_error("attention: destination must be a plain PF"); return LION_ERR_ARG; }
   return run_conv(f, a.out, o.p, o.G, dst, a.C / 4, nullptr, nullptr, geom_rows(N));

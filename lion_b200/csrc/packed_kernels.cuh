@@ -531,6 +531,22 @@ __global__ void k_act_rows_pool32(const float4* __restrict__ in, float4* __restr
   }
 }
 
+// pooled SharedMLP tail: mm[b][g][centre] = (min4, max4) over the centre's 32 neighbours of the raw convolution output
+// (written by the convolution's epilogue).  y = swish(scale*x + shift) is monotonic-then-quasi-convex in x, so its
+// maximum over the neighbours is attained at one of the two extremes: the same set maximum as k_act_rows_pool32.
+__global__ void k_act_pool_minmax(const float4* __restrict__ mm, float4* __restrict__ out, AffSrc aff, int G, int C, int R_out,
+                                  int Gd, int g_off) {
+  pdl_prologue();
+  int b = blockIdx.z, g = blockIdx.y;
+  float4 s, t;
+  aff_block_load(aff, b, g, C, s, t);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R_out) return;
+  const float4* src = mm + (((size_t)b * G + g) * R_out + i) * 2;
+  float4 lo = f4_swish(f4_affine(src[0], s, t)), hi = f4_swish(f4_affine(src[1], s, t));
+  out[((size_t)b * Gd + g_off + g) * R_out + i] = make_float4(fmaxf(lo.x, hi.x), fmaxf(lo.y, hi.y), fmaxf(lo.z, hi.z), fmaxf(lo.w, hi.w));
+}
+
 // per-channel sum / sum of squares over the rows of a PF (stand-alone AdaGN / SE3d entry points;
 // on the fused path these statistics come out of the convolution epilogue instead)
 __global__ void k_row_stats(const float4* __restrict__ in, double* __restrict__ ssum, double* __restrict__ ssq, int G, int R,
@@ -732,73 +748,83 @@ __global__ void k_interp_rows(const float4* __restrict__ cf, const int* __restri
 // linear attention (models/pvcnn2_ada.py:54-71).  qkv PF has 3*H*32 channels ordered
 // (qkv, head, c).  ctx[b][h][d][e] = sum_n softmax_n(k[d])[n] * v[e][n];  out[e][n] = sum_d ctx[d][e] q[d][n]
 // ------------------------------------------------------------------------------------
+// Split over N (online softmax): block (h, b, c) handles the 128 points of chunk c and leaves an UNNORMALISED partial
+// context plus its per-channel running max / sum; k_attn_apply merges the S = ceil(N/128) partials in its prologue.
+// (Round 1 used one block per (b, head) looping over all N: 128 blocks, 57 us at N = 1024 -- latency-bound.)
+//   part[b][h][c] = { ctx_c[32][32], max_c[32], sum_c[32] }   (ATTN_PART floats)
+constexpr int ATTN_CHUNK = 128;
+constexpr int ATTN_PART = 1024 + 64;
 __global__ void __launch_bounds__(256)
-k_attn_ctx(const float4* __restrict__ qkv, float* __restrict__ ctx, int H, int N) {
+k_attn_ctx(const float4* __restrict__ qkv, float* __restrict__ part, int H, int N) {
   pdl_prologue();
-  int h = blockIdx.x, b = blockIdx.y;
-  int Gq = 3 * H * 8;                       // groups in qkv
-  const float4* kb = qkv + ((size_t)b * Gq + (H + h) * 8) * N;       // k: 8 groups x N
-  const float4* vb = qkv + ((size_t)b * Gq + (2 * H + h) * 8) * N;   // v
-  __shared__ float s_max[32], s_sum[32];
-  __shared__ float s_k[32][65], s_v[32][65];
-  int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // pass 1: per-channel max and sum(exp) over N; warp w handles channels 4w..4w+3 (one group)
-  {
-    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    for (int n = lane; n < N; n += 32) {
-      float4 v = kb[(size_t)wid * N + n];
-      m[0] = fmaxf(m[0], v.x); m[1] = fmaxf(m[1], v.y); m[2] = fmaxf(m[2], v.z); m[3] = fmaxf(m[3], v.w);
-    }
-    float s[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) m[j] = warp_max(m[j]);
-    for (int n = lane; n < N; n += 32) {
-      float4 v = kb[(size_t)wid * N + n];
-      s[0] += expf(v.x - m[0]); s[1] += expf(v.y - m[1]); s[2] += expf(v.z - m[2]); s[3] += expf(v.w - m[3]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s[j] = warp_sum(s[j]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { s_max[wid * 4 + j] = m[j]; s_sum[wid * 4 + j] = s[j]; }
-    }
+  const int h = blockIdx.x, b = blockIdx.y, c = blockIdx.z, S = gridDim.z;
+  const int Gq = 3 * H * 8;                       // groups in qkv
+  const int n0 = c * ATTN_CHUNK, nn = min(ATTN_CHUNK, N - n0);
+  const float4* kb = qkv + ((size_t)b * Gq + (H + h) * 8) * N + n0;       // k: 8 groups x N
+  const float4* vb = qkv + ((size_t)b * Gq + (2 * H + h) * 8) * N + n0;   // v
+  __shared__ float s_k[32][ATTN_CHUNK + 1], s_v[32][ATTN_CHUNK + 1];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 8 * ATTN_CHUNK; i += 256) {
+    const int g = i / ATTN_CHUNK, n = i % ATTN_CHUNK;
+    float4 kv = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), vv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < nn) { kv = kb[(size_t)g * N + n]; vv = vb[(size_t)g * N + n]; }
+    s_k[g * 4 + 0][n] = kv.x; s_k[g * 4 + 1][n] = kv.y; s_k[g * 4 + 2][n] = kv.z; s_k[g * 4 + 3][n] = kv.w;
+    s_v[g * 4 + 0][n] = vv.x; s_v[g * 4 + 1][n] = vv.y; s_v[g * 4 + 2][n] = vv.z; s_v[g * 4 + 3][n] = vv.w;
   }
   __syncthreads();
-  // pass 2: thread (d = tid/8, e in 4*(tid%8)..+3) accumulates over tiles of 64 points
-  int d = tid >> 3, e0 = (tid & 7) * 4;
-  float acc[4] = {0, 0, 0, 0};
-  for (int n0 = 0; n0 < N; n0 += 64) {
-    __syncthreads();
-    for (int i = tid; i < 8 * 64; i += 256) {
-      int g = i / 64, n = i % 64;
-      float4 kv = make_float4(0, 0, 0, 0), vv = kv;
-      bool ok = n0 + n < N;
-      if (ok) { kv = kb[(size_t)g * N + n0 + n]; vv = vb[(size_t)g * N + n0 + n]; }
-      s_k[g * 4 + 0][n] = ok ? expf(kv.x - s_max[g * 4 + 0]) : 0.f;
-      s_k[g * 4 + 1][n] = ok ? expf(kv.y - s_max[g * 4 + 1]) : 0.f;
-      s_k[g * 4 + 2][n] = ok ? expf(kv.z - s_max[g * 4 + 2]) : 0.f;
-      s_k[g * 4 + 3][n] = ok ? expf(kv.w - s_max[g * 4 + 3]) : 0.f;
-      s_v[g * 4 + 0][n] = vv.x; s_v[g * 4 + 1][n] = vv.y; s_v[g * 4 + 2][n] = vv.z; s_v[g * 4 + 3][n] = vv.w;
-    }
-    __syncthreads();
-    for (int n = 0; n < 64; ++n) {
-      float kk = s_k[d][n];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(kk, s_v[e0 + j][n], acc[j]);
-    }
+  // channel d = tid / 8: eight threads share its 128 entries
+  const int d = tid >> 3, sub = tid & 7;
+  float m = -INFINITY;
+  for (int n = sub; n < ATTN_CHUNK; n += 8) m = fmaxf(m, s_k[d][n]);
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+  float sum = 0.0f;
+  for (int n = sub; n < ATTN_CHUNK; n += 8) {
+    const float e = (n < nn) ? expf(s_k[d][n] - m) : 0.0f;
+    s_k[d][n] = e;
+    sum += e;
   }
-  float inv = 1.0f / s_sum[d];
-  float* o = ctx + (((size_t)b * H + h) * 32 + d) * 32 + e0;
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+  __syncthreads();
+  const int e0 = sub * 4;
+  float acc[4] = {0, 0, 0, 0};
+  for (int n = 0; n < ATTN_CHUNK; ++n) {
+    const float kk = s_k[d][n];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) o[j] = acc[j] * inv;
+    for (int j = 0; j < 4; ++j) acc[j] = fmaf(kk, s_v[e0 + j][n], acc[j]);
+  }
+  float* o = part + (((size_t)b * H + h) * S + c) * ATTN_PART;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[d * 32 + e0 + j] = acc[j];
+  if (sub == 0) { o[1024 + d] = m; o[1024 + 32 + d] = sum; }
 }
 
 __global__ void __launch_bounds__(128)
-k_attn_apply(const float4* __restrict__ qkv, const float* __restrict__ ctx, float4* __restrict__ out, int H, int N) {
+k_attn_apply(const float4* __restrict__ qkv, const float* __restrict__ part, float4* __restrict__ out, int H, int N, int S) {
   pdl_prologue();
   int h = blockIdx.y, b = blockIdx.z;
   __shared__ float s_ctx[32 * 32];
-  for (int i = threadIdx.x; i < 1024; i += 128) s_ctx[i] = ctx[((size_t)b * H + h) * 1024 + i];
+  __shared__ float s_w[32][33];          // [chunk (<= 32)][d]: exp(max_c - max) / denominator
+  const float* pb = part + ((size_t)b * H + h) * S * ATTN_PART;
+  if (threadIdx.x < 32) {
+    const int d = threadIdx.x;
+    float M = -INFINITY;
+    for (int c = 0; c < S; ++c) M = fmaxf(M, pb[(size_t)c * ATTN_PART + 1024 + d]);
+    float den = 0.0f;
+    for (int c = 0; c < S; ++c) den += expf(pb[(size_t)c * ATTN_PART + 1024 + d] - M) * pb[(size_t)c * ATTN_PART + 1024 + 32 + d];
+    const float inv = 1.0f / den;
+    for (int c = 0; c < S; ++c) s_w[c][d] = expf(pb[(size_t)c * ATTN_PART + 1024 + d] - M) * inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += 128) {
+    const int d = i >> 5;
+    float a = 0.0f;
+    for (int c = 0; c < S; ++c) a = fmaf(s_w[c][d], pb[(size_t)c * ATTN_PART + i], a);
+    s_ctx[i] = a;
+  }
   __syncthreads();
   int n = blockIdx.x * 128 + threadIdx.x;
   if (n >= N) return;
