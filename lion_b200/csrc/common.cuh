@@ -194,6 +194,21 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float swishf(float x) { return x / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float4 f4_affine(float4 v, float4 s, float4 t) {
+  return make_float4(fmaf(v.x, s.x, t.x), fmaf(v.y, s.y, t.y), fmaf(v.z, s.z, t.z), fmaf(v.w, s.w, t.w));
+}
+__device__ __forceinline__ float4 f4_swish(float4 v) {
+  return make_float4(swishf(v.x), swishf(v.y), swishf(v.z), swishf(v.w));
+}
+// round-to-nearest(-away) to TF32, the unbiased conversion cuDNN applies to tensor-core operands;
+// used where the ONLY consumer of a tensor is a tcgen05 kind::tf32 convolution (which would
+// otherwise truncate the low 13 mantissa bits, a one-sided error that accumulates over layers)
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 f4_tf32(float4 v) { return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)); }
 // squared distance with the FMA contraction nvcc applies to the reference's
 // dx*dx + dy*dy + dz*dz (t = dy*dy; t = fma(dx,dx,t); t = fma(dz,dz,t)); see oracle/point_ops.py.
 __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {

@@ -156,6 +156,11 @@ struct ConvGeom {
 int conv_tc_prepare(Model* m, ConvW& w);
 int conv_tc_pack_job(const PackJob& j);
 bool conv_tc_usable(const ConvW& w, const ConvGeom& geo);
+// fused set-abstraction MLP (sa_fused.cu)
+bool sa_fused_usable(const SABlk& s);
+int sa_fused_run(Ctx* c, const SABlk& s, const float4* feat, const float4* points, const float4* centers, const int* nidx,
+                 const float* scale1, const float* shift1, double* ssum, double* ssq, int stat_stride, float* pool_mm,
+                 int B, int N);
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum,
                 double* ssq, const ConvGeom& geo, int B, float* pool_mm = nullptr);
 

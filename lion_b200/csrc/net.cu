@@ -534,6 +534,24 @@ static int sa_fwd(Fwd& f, const SABlk& s, PF feat, const float4* c4, float4* cen
     LION_LAUNCH(f.c, k_ball_query_c4, dim3(cdiv(M * 32, 256), f.B), 256, 0, centers, c4, ni, N, M, r2, U);
     nidx = ni;
   }
+  if (sa_fused_usable(s)) {
+    // gather -> conv -> AdaGN/Swish -> conv -> max-pool in two fused passes (sa_fused.cu): no [B, C, M, 32] round trips
+    const ConvW &c1 = s.mlp.conv[0], &c2 = s.mlp.conv[1];
+    double *s1, *q1, *s2, *q2;
+    AffSrc a1, a2;
+    LION_TRY(alloc_stats(f, c1.cout_pad, &s1, &q1));
+    LION_TRY(sa_fused_run(f.c, s, feat.p, c4, centers, nidx, nullptr, nullptr, s1, q1, c1.cout_pad, nullptr, f.B, N));
+    LION_TRY(run_affine(f, s.mlp.gn[0], s1, q1, c1.cout_pad, (double)M * U, nullptr, nullptr, a1));
+    LION_TRY(alloc_stats(f, c2.cout_pad, &s2, &q2));
+    float* mm = f.c->alloc_n<float>((size_t)f.B * (c2.cout / 4) * M * 8);
+    LION_TRY(sa_fused_run(f.c, s, feat.p, c4, centers, nidx, a1.scale, a1.shift, s2, q2, c2.cout_pad, mm, f.B, N));
+    LION_TRY(run_affine(f, s.mlp.gn[1], s2, q2, c2.cout_pad, (double)M * U, nullptr, nullptr, a2));
+    LION_LAUNCH(f.c, k_act_pool_minmax, dim3(cdiv(M, 256), c2.cout / 4, f.B), 256, 0, (const float4*)mm, dst, a2, c2.cout / 4, c2.cout, M,
+                Gd, g_off);
+    LION_TRY(check_launch(f.c, "sa fused"));
+    f.c->release(mk);
+    return 0;
+  }
   PF grp = alloc_pf(f, Gf + 1, M * U);
   LION_LAUNCH(f.c, k_group_gather, dim3(cdiv(M * U, 256), Gf + 1, f.B), 256, 0, feat.p, c4, centers, nidx, grp.p, Gf, N, M, U);
   LION_TRY(check_launch(f.c, "sa grouping"));

@@ -13,7 +13,7 @@
 // DRAM traffic of SA level 0 at B = 32: ~1.36 GB per step with the unfused kernels, indices + 2 x 17 MB with this one.
 #include "common.cuh"
 #include "model.cuh"
-#include "packed_kernels.cuh"
+#include <cstdlib>
 
 namespace lion {
 namespace saf {
@@ -109,8 +109,8 @@ __global__ void __launch_bounds__(128, 4) k_sa_fused(Params P) {
   float* s_b2 = s_b1 + N1;                                   // [N2]
   float* s_sc = s_b2 + N2;                                   // [N1]
   float* s_sh = s_sc + N1;                                   // [N1]
-  float* s_stat = s_sh + N1;                                 // [2][NS] CTA-level sums
-  uint64_t* bars = (uint64_t*)(s_stat + 2 * (N1 > N2 ? N1 : N2));
+  float* s_stat = s_sh + N1;                                 // [4 warps][2][NS] partial sums
+  uint64_t* bars = (uint64_t*)(s_stat + 8 * (N1 > N2 ? N1 : N2));
   uint32_t* s_tmem = (uint32_t*)(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_per_shape = P.M / 4;
@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(128, 4) k_sa_fused(Params P) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
+    __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(s_tmem)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -137,7 +138,6 @@ __global__ void __launch_bounds__(128, 4) k_sa_fused(Params P) {
     if (PASS == 2) { s_sc[tid] = P.scale1[(size_t)b * N1 + tid]; s_sh[tid] = P.shift1[(size_t)b * N1 + tid]; }
   }
   if (PASS == 2 && tid < N2) s_b2[tid] = P.b2 ? P.b2[tid] : 0.0f;
-  if (tid < 2 * NS) s_stat[tid] = 0.0f;
   for (int g = GF + 1; g < G1; ++g) sA1[g * 128 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -248,21 +248,25 @@ __global__ void __launch_bounds__(128, 4) k_sa_fused(Params P) {
     // tcgen05.ld before the next MMAs across the barrier inside the next iteration
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
-  // ---- statistics: warp partials -> CTA -> one fp64 atomic per channel
+  // ---- statistics: warp partials -> CTA (fixed order: bit-reproducible) -> one fp64 atomic per channel
   if ((lane & 1) == 0) {
 #pragma unroll
     for (int k = 0; k < NS / 16; ++k) {
-      atomicAdd(&s_stat[k * 16 + ((lane >> 1) & 15)], run_s[k]);
-      atomicAdd(&s_stat[NS + k * 16 + ((lane >> 1) & 15)], run_q[k]);
+      s_stat[(warp * 2 + 0) * NS + k * 16 + ((lane >> 1) & 15)] = run_s[k];
+      s_stat[(warp * 2 + 1) * NS + k * 16 + ((lane >> 1) & 15)] = run_q[k];
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < NS) {
-    atomicAdd(P.ssum + (size_t)b * P.stat_stride + tid, (double)s_stat[tid]);
-    atomicAdd(P.ssq + (size_t)b * P.stat_stride + tid, (double)s_stat[NS + tid]);
+    float a = 0.0f, q = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) { a += s_stat[(w * 2 + 0) * NS + tid]; q += s_stat[(w * 2 + 1) * NS + tid]; }
+    atomicAdd(P.ssum + (size_t)b * P.stat_stride + tid, (double)a);
+    atomicAdd(P.ssq + (size_t)b * P.stat_stride + tid, (double)q);
   }
   if (warp == 0) {
+    __syncwarp();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
   }
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(128, 4) k_sa_fused(Params P) {
 template <int GF, int N1, int N2>
 constexpr size_t smem_bytes() {
   constexpr int G1 = (GF + 2) & ~1, G2 = N1 / 4;
-  return (size_t)(G1 * 128 + G2 * 128 + G1 * N1 + G2 * N2) * 16 + (size_t)(N1 + N2 + 2 * N1 + 2 * (N1 > N2 ? N1 : N2)) * 4 + 64;
+  return (size_t)(G1 * 128 + G2 * 128 + G1 * N1 + G2 * N2) * 16 + (size_t)(N1 + N2 + 2 * N1 + 8 * (N1 > N2 ? N1 : N2)) * 4 + 64;
 }
 
 }  // namespace saf

@@ -66,6 +66,20 @@ def test_sa_module(cfeat, m, radius, outs, N):
     assert_close(out, o_feat, TOL, "SA module")
 
 
+def test_sa_module_is_bit_reproducible():
+    """The fused level-0 SA kernel (csrc/sa_fused.cu) and the pooled convolution epilogue reduce their GroupNorm
+    statistics in a fixed order: the same input gives the same bits, eagerly and run after run (the sampling loop relies
+    on it: graph replay == eager loop)."""
+    from lion_b200.models.pvcnn2_ada import PointNetSAModule
+    for cfeat, m, radius, outs, N in [(32, 1024, 0.1, [32, 64], 2048), (64, 256, 0.2, [64, 128], 1024)]:
+        mod, sd = _load(PointNetSAModule(m, radius, 32, cfeat, outs, cfg=_cfg()), 24)
+        B = 4
+        feats, coords, style = gen(7, B, cfeat, N).cuda(), gen(8, B, 3, N, scale=0.3).cuda(), gen(9, B, 128).cuda()
+        ref = mod((feats, coords, None, style))[0].clone()
+        for _ in range(4):
+            assert torch.equal(mod((feats, coords, None, style))[0], ref)
+
+
 @pytest.mark.parametrize("cc,cp,outs,N,M", [(192, 128, [128, 128], 64, 16), (192, 1, [128, 128, 64], 2048, 1024), (128, 0, [64], 256, 64)])
 def test_fp_module(cc, cp, outs, N, M):
     from lion_b200.models.pvcnn2_ada import PointNetFPModule
