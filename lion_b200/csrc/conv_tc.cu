@@ -207,6 +207,8 @@ struct Params {
   // pool_mm[b][C/4][rows/32][2][4].  AdaGN's affine is monotonic and Swish is quasi-convex (one minimum), so
   // max_i swish(s*x_i + t) = max(swish(s*min + t), swish(s*max + t)): the consumer needs 2 of the 32 values.
   float* pool_mm;
+  // row-major output (the y = x W GEMM of the sparse first convolution): out_rm[(b*rows + p) * ld_rm + n], no PF store
+  float* out_rm; int ld_rm;
 };
 
 // per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
@@ -553,7 +555,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = valid ? v[i] + s_bias[col + i] : 0.0f;
           if (TPG == 1 && P.pool_mm) pool_store16(P, b, n0, col, (long long)(p >> 5), v, lane);
-          else if (inrange) {
+          else if (TPG == 1 && P.out_rm) {
+            if (inrange && n0 + col < P.ld_rm) {
+              float4* d = reinterpret_cast<float4*>(P.out_rm + ((size_t)b * P.rows + p) * P.ld_rm + n0 + col);
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) d[g4] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+            }
+          } else if (inrange) {
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
               int g = (n0 + col) / 4 + g4;
@@ -693,8 +701,12 @@ bool conv_tc_usable(const ConvW& w, const ConvGeom& geo) {
 }
 
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum, double* ssq,
-                const ConvGeom& geo, int B, float* pool_mm) {
+                const ConvGeom& geo, int B, float* pool_mm, float* out_rm, int ld_rm) {
   tc::Params P{};
+  if (out_rm && (w.ntaps != 1 || w.cout_pad < 128 || ld_rm % 16)) {
+    set_error("conv_tc: the row-major epilogue needs a 1x1 convolution with >= 128 output channels"); return LION_ERR_ARG;
+  }
+  P.out_rm = out_rm; P.ld_rm = ld_rm;
   if (pool_mm && (w.ntaps != 1 || geo.p_begin != 0 || geo.p_end != geo.rows || geo.rows % 128)) {
     set_error("conv_tc: the pooled epilogue needs a 1x1 convolution over a multiple of 128 rows"); return LION_ERR_ARG;
   }

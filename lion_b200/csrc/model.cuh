@@ -56,6 +56,7 @@ struct AttnBlk {
 struct PVConvBlk {
   int cin = 0, cout = 0, r = 0;
   ConvW c1, c2;
+  ConvW c1y;            // sparse first convolution: 1x1 "convolution" x[v] -> y[v][tap][cout] (c1y.tc.w set when available)
   AdaGNW g1, g2;
   const float* se1 = nullptr; const float* se2 = nullptr;
   SharedMLPBlk point;
@@ -156,12 +157,15 @@ struct ConvGeom {
 int conv_tc_prepare(Model* m, ConvW& w);
 int conv_tc_pack_job(const PackJob& j);
 bool conv_tc_usable(const ConvW& w, const ConvGeom& geo);
+// sparse first convolution, GEMM half (sparse_conv.cu)
+bool ygemm_usable(const ConvW& y);
+int ygemm_run(Ctx* c, const ConvW& y, const float4* xc, float* out, int ld, const int* nocc, int B, int N);
 // fused set-abstraction MLP (sa_fused.cu)
 bool sa_fused_usable(const SABlk& s);
 int sa_fused_run(Ctx* c, const SABlk& s, const float4* feat, const float4* points, const float4* centers, const int* nidx,
                  const float* scale1, const float* shift1, double* ssum, double* ssq, int stat_stride, float* pool_mm,
                  int B, int N);
 int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store, double* ssum,
-                double* ssq, const ConvGeom& geo, int B, float* pool_mm = nullptr);
+                double* ssq, const ConvGeom& geo, int B, float* pool_mm = nullptr, float* out_rm = nullptr, int ld_rm = 0);
 
 }  // namespace lion

@@ -97,6 +97,15 @@ __global__ void k_pack_conv_w(const float* __restrict__ w_ref, const int* __rest
   if (src >= 0 && co < cout) v = w_ref[((size_t)co * cin_ref + src) * ntaps + t];
   wt[i] = v;
 }
+// sparse first convolution: the 27 taps side by side, wy[ci][t * cout_pad + co] = wt[t][ci][co] (zero beyond 27 * cout_pad)
+__global__ void k_pack_taps_wide(const float* __restrict__ wt, float* __restrict__ wy, int cin_pad, int cout_pad, int ny_pad) {
+  pdl_prologue();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)cin_pad * ny_pad) return;
+  int n = i % ny_pad, ci = i / ny_pad;
+  int t = n / cout_pad, co = n % cout_pad;
+  wy[i] = t < 27 ? wt[((size_t)t * cin_pad + ci) * cout_pad + co] : 0.0f;
+}
 __global__ void k_pad_vec(const float* __restrict__ src, float* __restrict__ dst, int n, int n_pad) {
   pdl_prologue();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,6 +146,8 @@ int run_jobs(Model* m) {
       k_pack_conv_w<<<(unsigned)cdivz(total, 256), 256>>>(j.src, j.kmap, j.dst, j.a, j.b, j.c, j.d, j.e);
     } else if (j.type == 1) {
       k_pad_vec<<<cdiv(j.b, 128), 128>>>(j.src, j.dst, j.a, j.b);
+    } else if (j.type == 3) {
+      k_pack_taps_wide<<<(unsigned)cdivz((size_t)j.a * j.c, 256), 256>>>(j.src, j.dst, j.a, j.b, j.c);
     } else {
       LION_TRY(conv_tc_pack_job(j));
     }
@@ -191,6 +202,15 @@ int make_pvconv(Model* m, PVConvBlk& p, Cursor& cur, int cin, int cout, int r, b
   const float* w1 = cur.next(); const float* b1 = cur.next();
   if (cur.bad) { set_error("model parameters exhausted in PVConv"); return LION_ERR_ARG; }
   LION_TRY(make_conv(m, p.c1, w1, b1, 27, cin, cout, ident_map(cin)));
+  if ((p.c1.cout_pad == 32 || p.c1.cout_pad == 64) && p.c1.cout == p.c1.cout_pad && p.c1.cin_pad >= 16) {
+    // weights of the sparse form of this convolution (pvconv_fwd): one GEMM x[v] -> y[v][27 taps][cout]
+    ConvW& y = p.c1y;
+    y.ntaps = 1; y.cin_ref = p.c1.cin_pad; y.cin_pad = p.c1.cin_pad;
+    y.cout = y.cout_pad = roundup(27 * p.c1.cout_pad, 128);
+    LION_TRY(m->dmalloc(&y.wt, (size_t)y.cin_pad * y.cout_pad));
+    m->jobs.push_back({3, p.c1.wt, nullptr, y.wt, y.cin_pad, p.c1.cout_pad, y.cout_pad, 0, 0});
+    LION_TRY(conv_tc_prepare(m, y));
+  }
   LION_TRY(make_adagn(m, p.g1, cur, cout, plain));
   const float* w2 = cur.next(); const float* b2 = cur.next();
   if (cur.bad) { set_error("model parameters exhausted in PVConv"); return LION_ERR_ARG; }
@@ -226,7 +246,8 @@ int make_fp(Model* m, FPBlk& f, Cursor& cur, int cc, int cp, const std::vector<i
 // forward-time helpers
 // =====================================================================================
 struct PF { float4* p = nullptr; int G = 0; int R = 0; };
-struct VoxPrep { const float4* c4; int N, r; float4* nc; int* order; int* ppos; int* len; unsigned char* occ; int occ_stride; };
+struct VoxPrep { const float4* c4; int N, r; float4* nc; int* order; int* ppos; int* len; unsigned char* occ; int occ_stride;
+                 int* cidx; int* nocc; int* vgrid; };   // compact ids of the occupied voxels (sparse first convolution) or null
 struct Fwd {
   Ctx* c; Model* m; int B;
   char* stat_pool = nullptr;     // all GroupNorm statistics of a forward: zeroed by ONE memset
@@ -276,11 +297,11 @@ static ConvGeom geom_grid(int r) {
 
 // out rows in [p_begin,p_end) of every (b, group < Gout_store); statistics optional
 static int run_conv(Fwd& f, const ConvW& w, const float4* in, int Gin, float4* out, int Gout_store,
-                    double* ssum, double* ssq, const ConvGeom& geo, float* pool_mm = nullptr) {
+                    double* ssum, double* ssq, const ConvGeom& geo, float* pool_mm = nullptr, float* out_rm = nullptr, int ld_rm = 0) {
   if (Gin * 4 != w.cin_pad) { set_error("conv: input has %d channels, weights expect %d", Gin * 4, w.cin_pad); return LION_ERR_ARG; }
   if (conv_tc_usable(w, geo))
-    return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B, pool_mm);
-  if (pool_mm) { set_error("conv: the pooled epilogue exists on the tensor-core path only"); return LION_ERR_STATE; }
+    return conv_tc_run(f.c, w, in, Gin, out, Gout_store, ssum, ssq, geo, f.B, pool_mm, out_rm, ld_rm);
+  if (pool_mm || out_rm) { set_error("conv: the pooled epilogue exists on the tensor-core path only"); return LION_ERR_STATE; }
   int span = geo.p_end - geo.p_begin;
   if (w.cout_pad == 4) {
     LION_LAUNCH(f.c, k_conv_simt<4>, dim3(cdiv(span, 128), 1, f.B), 128, geo.ntaps * 16 * sizeof(float),
@@ -417,9 +438,18 @@ static int attn_fwd(Fwd& f, const AttnBlk& a, PF x, float4* dst, int Gd, int g_o
   return run_conv(f, a.out, o.p, o.G, dst, a.C / 4, nullptr, nullptr, geom_rows(N));
 }
 
+// The first convolution of a PVConv reads a grid with at most N occupied voxels.  When that is a small fraction of r^3
+// it is cheaper to multiply only the occupied voxels by all 27 taps (one GEMM, 27 * N rows of output instead of r^3 * 27
+// taps of dense work) and let every output voxel gather its neighbours' rows (k_sparse_conv_gather): at r = 32, N = 2048
+// that is 16x fewer FLOPs and the convolution becomes a ~0.7 GB streaming problem.  LION_SPARSE_CONV1=0 disables it.
+static bool sparse_conv1_wanted(int N, int r) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("LION_SPARSE_CONV1"); on = e ? atoi(e) : 1; }
+  return on && (long long)N * 8 <= (long long)r * r * r;
+}
 static int get_vox(Fwd& f, const float4* c4, int N, int r, VoxPrep** out) {
   for (auto& v : f.vox) if (v.c4 == c4 && v.N == N && v.r == r) { *out = &v; return 0; }
-  VoxPrep v{c4, N, r, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  VoxPrep v{c4, N, r, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr};
   if (N > VOXP_MAXN || r > 32) { set_error("voxelisation: N=%d (max %d) or r=%d (max 32) unsupported", N, VOXP_MAXN, r); return LION_ERR_ARG; }
   v.nc = f.c->alloc_n<float4>((size_t)f.B * N);
   v.order = f.c->alloc_n<int>((size_t)f.B * N);
@@ -429,7 +459,13 @@ static int get_vox(Fwd& f, const float4* c4, int N, int r, VoxPrep** out) {
   v.occ_stride = (P + 63) / 64 + 4;
   v.occ = f.c->alloc_n<unsigned char>((size_t)f.B * v.occ_stride);
   LION_TRY(memset_async(f.c, v.occ, 0, (size_t)f.B * v.occ_stride));
-  LION_LAUNCH(f.c, k_vox_prep, f.B, VOXP_THREADS, 0, c4, v.nc, v.order, v.ppos, v.len, v.occ, v.occ_stride, N, r);
+  if (sparse_conv1_wanted(N, r)) {
+    v.cidx = f.c->alloc_n<int>((size_t)f.B * N);
+    v.nocc = f.c->alloc_n<int>((size_t)f.B);
+    v.vgrid = f.c->alloc_n<int>((size_t)f.B * P);
+    LION_TRY(memset_async(f.c, v.vgrid, 0xff, (size_t)f.B * P * sizeof(int)));     // -1 = empty voxel
+  }
+  LION_LAUNCH(f.c, k_vox_prep, f.B, VOXP_THREADS, 0, c4, v.nc, v.order, v.ppos, v.len, v.occ, v.occ_stride, N, r, v.cidx, v.nocc, v.vgrid);
   LION_TRY(check_launch(f.c, "vox_prep"));
   f.vox.push_back(v);
   *out = &f.vox.back();
@@ -444,12 +480,20 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   LION_TRY(get_vox(f, c4, N, r, &vp));
   size_t mk = f.c->mark();
   ConvGeom geo = geom_grid(r);
-  // point -> voxel scatter-mean into the context's persistent all-zero grid (no per-call memset)
-  size_t zbytes = sizeof(float4) * ((size_t)f.B * Gin * P + 2 * ((size_t)rp * rp + rp + 8));
-  if (zbytes > f.c->zgrid_need) f.c->zgrid_need = zbytes;
-  float4* g_in = f.c->dry ? (float4*)(uintptr_t)0x1000 : (float4*)f.c->zgrid + ((size_t)rp * rp + rp + 8);
-  LION_LAUNCH(f.c, k_scatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, feat.p, vp->order, vp->ppos, vp->len, g_in, Gin, N, P);
-  // conv1 (sparse input: empty 64-row blocks are skipped) -> (stats) -> AdaGN + Swish
+  const bool sparse1 = vp->cidx && ygemm_usable(p.c1y) && feat.G == p.c1y.cin_pad / 4;
+  float4* g_in = nullptr;
+  PF xc;
+  if (sparse1) {
+    // compact list of the occupied voxels' mean features (same values k_scatter would store into the grid)
+    xc = alloc_pf(f, Gin, N);
+    LION_LAUNCH(f.c, k_scatter_compact, dim3(cdiv(N, 128), Gin, f.B), 128, 0, feat.p, vp->order, vp->cidx, vp->len, vp->nocc, xc.p, Gin, N);
+  } else {
+    // point -> voxel scatter-mean into the context's persistent all-zero grid (no per-call memset)
+    size_t zbytes = sizeof(float4) * ((size_t)f.B * Gin * P + 2 * ((size_t)rp * rp + rp + 8));
+    if (zbytes > f.c->zgrid_need) f.c->zgrid_need = zbytes;
+    g_in = f.c->dry ? (float4*)(uintptr_t)0x1000 : (float4*)f.c->zgrid + ((size_t)rp * rp + rp + 8);
+    LION_LAUNCH(f.c, k_scatter, dim3(cdiv(N, 128), Gin, f.B), 128, 0, feat.p, vp->order, vp->ppos, vp->len, g_in, Gin, N, P);
+  }
   stamp(f.c, f.c->stream, " scatter");
   // point branch first: conv1x1 -> stats (its fold shares a launch with conv1's below; the activation is applied inside
   // the devox kernel)
@@ -458,13 +502,36 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   AffSrc ap;
   PrepJob jp, j1;
   LION_TRY(conv_gn_deferred(f, pw, feat.p, feat.G, rawp.p, Gout, geom_rows(N), p.point.gn[0], (double)N, ap, jp));
-  // conv1 (sparse input: empty 64-row blocks are skipped) -> (stats) -> AdaGN + Swish
+  // conv1 -> (stats) -> AdaGN + Swish
   float4* raw1 = alloc_vg(f, Gout, r);
-  ConvGeom geo1 = geo;
-  geo1.occ = vp->occ; geo1.occ_stride = vp->occ_stride;
   AffSrc a1;
   double V = (double)r * r * r;
-  LION_TRY(conv_gn_deferred(f, p.c1, g_in, Gin, raw1, Gout, geo1, p.g1, V, a1, j1));
+  if (sparse1) {
+    const int ld = 27 * p.c1.cout_pad;
+    float* y = f.c->alloc_n<float>((size_t)f.B * N * ld);
+    LION_TRY(ygemm_run(f.c, p.c1y, xc.p, y, ld, vp->nocc, f.B, N));
+    double *s1, *q1;
+    LION_TRY(alloc_stats(f, p.c1.cout_pad, &s1, &q1));
+    const int nwarp = 8;
+    const size_t smem = (size_t)nwarp * (32 * (p.c1.cout_pad + 2) * sizeof(float) + SPG_LIST * sizeof(int2));
+    static DevOnce attr_once;
+    if (attr_once.need()) {
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_sparse_conv_gather<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_sparse_conv_gather<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    }
+    const dim3 grid(cdiv(r * r * r, 32 * nwarp), f.B);
+    if (p.c1.cout_pad == 32)
+      LION_LAUNCH(f.c, k_sparse_conv_gather<32>, grid, 32 * nwarp, smem, y, ld, vp->vgrid, p.c1.bias, raw1, s1, q1, p.c1.cout_pad, r, N);
+    else
+      LION_LAUNCH(f.c, k_sparse_conv_gather<64>, grid, 32 * nwarp, smem, y, ld, vp->vgrid, p.c1.bias, raw1, s1, q1, p.c1.cout_pad, r, N);
+    LION_TRY(check_launch(f.c, "sparse conv1"));
+    j1 = prep_job(f, p.g1, s1, q1, p.c1.cout_pad, V, nullptr, nullptr, a1);
+  } else {
+    // (the tensor-core kernel still skips operand slabs whose 64-row occupancy flags are all clear)
+    ConvGeom geo1 = geo;
+    geo1.occ = vp->occ; geo1.occ_stride = vp->occ_stride;
+    LION_TRY(conv_gn_deferred(f, p.c1, g_in, Gin, raw1, Gout, geo1, p.g1, V, a1, j1));
+  }
   LION_TRY(run_prep(f, j1, &jp));
   stamp(f.c, f.c->stream, " conv1");
   // AdaGN-1 + Swish as a stand-alone pass over the grid (HBM-bound).  Round 2 tried to fold it into conv2's operand
@@ -473,7 +540,7 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   float4* act1 = alloc_vg(f, Gout, r);
   {
     const int nb_act = cdiv(P, 256 * ACT_U);
-    LION_LAUNCH(f.c, k_act_grid, dim3(nb_act + cdiv(N, 256), Gout, f.B), 256, 0, raw1, act1, a1, Gout, p.cout, rp, P, nb_act,
+    LION_LAUNCH(f.c, k_act_grid, dim3(nb_act + (sparse1 ? 0 : cdiv(N, 256)), Gout, f.B), 256, 0, raw1, act1, a1, Gout, p.cout, rp, P, nb_act,
                 vp->ppos, g_in, Gin, N);
   }
   stamp(f.c, f.c->stream, " act1");

@@ -52,7 +52,8 @@ constexpr int VOXP_MAXN = 4096;
 
 __global__ void __launch_bounds__(VOXP_THREADS)
 k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restrict__ s_order, int* __restrict__ s_ppos,
-           int* __restrict__ s_len, unsigned char* __restrict__ occ, int occ_stride, int N, int r) {
+           int* __restrict__ s_len, unsigned char* __restrict__ occ, int occ_stride, int N, int r,
+           int* __restrict__ s_cidx /*[B][N] or null*/, int* __restrict__ nocc /*[B]*/, int* __restrict__ vgrid /*[B][(r+2)^3], pre-set to -1*/) {
   pdl_prologue();
   int b = blockIdx.x;
   const float4* c = c4 + (size_t)b * N;
@@ -94,21 +95,178 @@ k_vox_prep(const float4* __restrict__ c4, float4* __restrict__ nc, int* __restri
   }
   int rp = r + 2;
   unsigned mask = (1u << bits) - 1u;
-  for (int s = threadIdx.x; s < N; s += blockDim.x) {
-    unsigned key = s_key[s];
-    int vox = (int)(key >> bits);
-    bool lead = (s == 0) || ((int)(s_key[s - 1] >> bits) != vox);
-    int len = 0, pp = -1;
-    if (lead) {
-      len = 1;
-      while (s + len < N && (int)(s_key[s + len] >> bits) == vox) ++len;
-      int xi = vox / (r * r), yi = (vox / r) % r, zi = vox % r;
-      pp = ((xi + 1) * rp + (yi + 1)) * rp + (zi + 1);
-      occ[(size_t)b * occ_stride + (pp >> 6)] = 1;       // 64-row occupancy flags (pre-zeroed) for the sparse-input conv
+  // occupied voxels in ascending voxel order get compact ids 0..n_occ-1 (the rank of their leading slot): the sparse
+  // first convolution (k_sparse_conv_gather) works on the compact list instead of the 94 %-empty grid
+  __shared__ int s_wsum[VOXP_THREADS / 32];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < N; s0 += blockDim.x) {           // uniform trip count: barriers inside
+    const int s = s0 + threadIdx.x;
+    unsigned key = 0;
+    int vox = -1;
+    bool lead = false;
+    if (s < N) {
+      key = s_key[s];
+      vox = (int)(key >> bits);
+      lead = (s == 0) || ((int)(s_key[s - 1] >> bits) != vox);
     }
-    s_order[(size_t)b * N + s] = (int)(key & mask);
-    s_ppos[(size_t)b * N + s] = pp;
-    s_len[(size_t)b * N + s] = len;
+    const unsigned bal = __ballot_sync(0xffffffffu, lead);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_wsum[wid] = __popc(bal);
+    __syncthreads();
+    int before = s_base + __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < wid; ++w) before += s_wsum[w];
+    int total = 0;
+    for (int w = 0; w < VOXP_THREADS / 32; ++w) total += s_wsum[w];
+    __syncthreads();
+    if (threadIdx.x == 0) s_base += total;
+    if (s < N) {
+      int len = 0, pp = -1;
+      if (lead) {
+        len = 1;
+        while (s + len < N && (int)(s_key[s + len] >> bits) == vox) ++len;
+        int xi = vox / (r * r), yi = (vox / r) % r, zi = vox % r;
+        pp = ((xi + 1) * rp + (yi + 1)) * rp + (zi + 1);
+        occ[(size_t)b * occ_stride + (pp >> 6)] = 1;       // 64-row occupancy flags (pre-zeroed) for the sparse-input conv
+        if (vgrid) vgrid[(size_t)b * rp * rp * rp + pp] = before;
+      }
+      s_order[(size_t)b * N + s] = (int)(key & mask);
+      s_ppos[(size_t)b * N + s] = pp;
+      s_len[(size_t)b * N + s] = len;
+      if (s_cidx) s_cidx[(size_t)b * N + s] = lead ? before : -1;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && nocc) nocc[b] = s_base;
+}
+
+// scatter-mean into the COMPACT voxel list: row cidx of xc[B][G][N] = mean feature of occupied voxel cidx (same
+// summation order as k_scatter); rows n_occ..N-1 are zeroed.
+__global__ void k_scatter_compact(const float4* __restrict__ feat, const int* __restrict__ s_order, const int* __restrict__ s_cidx,
+                                  const int* __restrict__ s_len, const int* __restrict__ nocc, float4* __restrict__ xc, int G, int N) {
+  pdl_prologue();
+  int b = blockIdx.z, g = blockIdx.y;
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  float4* dst = xc + ((size_t)b * G + g) * N;
+  if (s >= nocc[b]) dst[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int ci = s_cidx[(size_t)b * N + s];
+  if (ci < 0) return;
+  int len = s_len[(size_t)b * N + s];
+  float inv = 1.0f / (float)len;
+  const float4* f = feat + ((size_t)b * G + g) * N;
+  const int* ord = s_order + (size_t)b * N + s;
+  float4 acc = f4_scale(f[ord[0]], inv);
+  for (int k = 1; k < len; ++k) acc = f4_add(acc, f4_scale(f[ord[k]], inv));
+  dst[ci] = acc;
+}
+
+// Sparse first convolution of a PVConv, second half.  y[b][v][t][c] = W[t]^T x[v] for every occupied voxel v and tap t
+// (one dense GEMM over the compact list, conv_tc.cu with a row-major epilogue); here every interior output voxel p sums,
+// in ascending tap order, the rows y[vgrid[p + off(t)]][t] of its occupied neighbours -- each y row is read exactly
+// once -- adds the bias, stores the raw convolution output and accumulates the GroupNorm statistics.  Deterministic.
+//   one warp = 32 consecutive interior voxels; accumulators [32][C] in shared memory; C <= 64 (2 channels per lane)
+//   grid = (ceil(r^3 / (32 * warps)), B), block = 32 * warps, dynamic smem = warps * (32 * (C + 2) floats + SPG_LIST int2)
+constexpr int SPG_LIST = 256;      // contribution-list entries per warp
+constexpr int SPG_BATCH = 16;      // y rows in flight per warp
+template <int C>
+__global__ void __launch_bounds__(256)
+k_sparse_conv_gather(const float* __restrict__ y, int ldy, const int* __restrict__ vgrid, const float* __restrict__ bias,
+                     float4* __restrict__ out, double* __restrict__ ssum, double* __restrict__ ssq, int stat_stride,
+                     int r, int Nrows) {
+  pdl_prologue();
+  static_assert(C == 32 || C == 64, "two (or one) channels per lane");
+  constexpr int CPL = C / 32;                     // channels per lane
+  constexpr int PITCH = C + 2;
+  extern __shared__ float s_acc[];
+  __shared__ float s_red[2][8][C];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int rp = r + 2, P = rp * rp * rp, V = r * r * r;
+  const int q = (blockIdx.x * nw + wid) * 32 + lane;          // interior voxel (x, y, z) flattened
+  const bool live = q < V;
+  int p = 0;
+  if (live) { int z = q % r, yy = (q / r) % r, x = q / (r * r); p = ((x + 1) * rp + (yy + 1)) * rp + (z + 1); }
+  float* acc = s_acc + (size_t)wid * 32 * PITCH;
+  // bias
+  for (int j = 0; j < 32; ++j)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[j * PITCH + lane * CPL + k] = bias ? bias[lane * CPL + k] : 0.0f;
+  const int* vg = vgrid + (size_t)b * P;
+  const float* yb = y + (size_t)b * Nrows * ldy;
+  // the 27 neighbour ids of this lane's voxel: independent loads, all in flight together (the tap loop below must not
+  // serialise 27 L2 round trips per warp -- that alone cost 280 us in the first version of this kernel)
+  int nb[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const int off = ((t / 9) - 1) * rp * rp + (((t / 3) % 3) - 1) * rp + ((t % 3) - 1);
+    nb[t] = live ? __ldg(vg + p + off) : -1;
+  }
+  // contributions (occupied neighbour v of lane j's voxel, tap t) are listed in shared memory in (t, j) order, then
+  // consumed SPG_BATCH at a time: that many independent 4*C-byte row reads in flight per warp; the accumulation order per
+  // output voxel is ascending t whatever the batching
+  int2* list = reinterpret_cast<int2*>(s_acc + (size_t)nw * 32 * PITCH) + wid * SPG_LIST;
+  int n = 0;
+  auto flush = [&]() {
+    __syncwarp();
+    for (int i0 = 0; i0 < n; i0 += SPG_BATCH) {
+      float2 val[SPG_BATCH];
+      int jj[SPG_BATCH];
+#pragma unroll
+      for (int k = 0; k < SPG_BATCH; ++k) {
+        jj[k] = -1;
+        if (i0 + k < n) {
+          const int2 e = list[i0 + k];
+          const float* src = yb + (size_t)e.x * ldy + (e.y >> 5) * C + lane * CPL;
+          if (CPL == 2) val[k] = __ldg(reinterpret_cast<const float2*>(src));
+          else val[k] = make_float2(__ldg(src), 0.0f);
+          jj[k] = e.y & 31;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < SPG_BATCH; ++k) {
+        if (jj[k] >= 0) {
+          float* a = acc + jj[k] * PITCH + lane * CPL;
+          a[0] += val[k].x;
+          if (CPL == 2) a[1] += val[k].y;
+        }
+      }
+    }
+    __syncwarp();
+    n = 0;
+  };
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const int v = nb[t];
+    const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+    if (n + 32 > SPG_LIST) flush();
+    if (v >= 0) list[n + __popc(m & ((1u << lane) - 1u))] = make_int2(v, (t << 5) | lane);
+    n += __popc(m);
+  }
+  flush();
+  // store (PF/VG layout: consecutive lanes = consecutive z) and statistics
+  if (live) {
+#pragma unroll
+    for (int g = 0; g < C / 4; ++g) {
+      const float* a = acc + lane * PITCH + g * 4;
+      out[((size_t)b * (C / 4) + g) * P + p] = make_float4(a[0], a[1], a[2], a[3]);
+    }
+  }
+  float cs[CPL], cq[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) { cs[k] = 0.0f; cq[k] = 0.0f; }
+  const int nlive = min(32, V - (blockIdx.x * nw + wid) * 32);
+  for (int j = 0; j < nlive; ++j)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) { const float a = acc[j * PITCH + lane * CPL + k]; cs[k] += a; cq[k] = fmaf(a, a, cq[k]); }
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) { s_red[0][wid][lane * CPL + k] = cs[k]; s_red[1][wid][lane * CPL + k] = cq[k]; }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float a = 0.0f, qq = 0.0f;
+    for (int w = 0; w < nw; ++w) { a += s_red[0][w][threadIdx.x]; qq += s_red[1][w][threadIdx.x]; }
+    atomicAdd(ssum + (size_t)b * stat_stride + threadIdx.x, (double)a);
+    atomicAdd(ssq + (size_t)b * stat_stride + threadIdx.x, (double)qq);
   }
 }
 

@@ -41,7 +41,8 @@ def test_linear_attention(C, heads, N):
 
 
 @pytest.mark.parametrize("cin,cout,r,N,attn", [(4, 32, 32, 2048, False), (128, 64, 16, 1024, True), (192, 128, 8, 256, False),
-                                               (128, 128, 8, 64, False), (64, 64, 32, 2048, False)])
+                                               (128, 128, 8, 64, False), (64, 64, 32, 2048, False), (32, 32, 32, 2048, False),
+                                               (64, 64, 32, 700, False)])
 def test_pvconv(cin, cout, r, N, attn):
     from lion_b200.models.pvcnn2_ada import PVConv
     m, sd = _load(PVConv(cin, cout, 3, r, with_se=True, attention=attn, cfg=_cfg()), 23)

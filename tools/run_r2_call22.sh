@@ -1,0 +1,15 @@
+#!/bin/bash
+# round 2, call 22-23: sparse first convolution (compact GEMM + neighbour gather) -- parity, A/B
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_blocks_gpu.py -m gpu -q -x -k "pvconv" 2>&1 | tail -15 | tee gpurun_out/pytest_call22a.log
+timeout 1200 python -m pytest tests/test_blocks_gpu.py tests/test_net_gpu.py tests/test_encoder_gpu.py tests/test_fullsize_gpu.py tests/test_trainer_gpu.py -m gpu -q 2>&1 | tail -15 | tee gpurun_out/pytest_call22.log
+for sp in 0 1; do
+  LION_SPARSE_CONV1=$sp timeout 300 python tools/timeline_step.py > gpurun_out/timeline_sparse$sp.txt 2> gpurun_out/timeline.err
+done
+for sp in 0 1; do
+  LION_SPARSE_CONV1=$sp timeout 600 python bench.py --allow-knobs --steps 2 --warmup 3 --no-cpu-baseline --no-gpu-baseline --no-parity --no-extra-configs --no-e2e > gpurun_out/bench_r2k_sparse$sp.json 2> gpurun_out/bench_r2k.err
+done
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum
+timeout 600 ncu --metrics $M --clock-control none --profile-from-start off -k "regex:k_sparse_conv_gather|k_scatter_compact|k_ygemm" --csv --log-file gpurun_out/r02_sparse_conv_metrics.csv python tools/profile_step.py > gpurun_out/r02_sparse_conv_metrics.log 2>&1
+nvidia-smi --query-gpu=name,temperature.gpu,clocks.sm --format=csv
