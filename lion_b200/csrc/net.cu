@@ -480,7 +480,9 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
   LION_TRY(get_vox(f, c4, N, r, &vp));
   size_t mk = f.c->mark();
   ConvGeom geo = geom_grid(r);
-  const bool sparse1 = vp->cidx && ygemm_usable(p.c1y) && feat.G == p.c1y.cin_pad / 4;
+  static int sparse_minc = -1;
+  if (sparse_minc < 0) { const char* e = getenv("LION_SPARSE_MINC"); sparse_minc = e ? atoi(e) : 32; }
+  const bool sparse1 = vp->cidx && ygemm_usable(p.c1y) && feat.G == p.c1y.cin_pad / 4 && p.c1.cout_pad >= sparse_minc;
   float4* g_in = nullptr;
   PF xc;
   if (sparse1) {
@@ -512,8 +514,8 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
     LION_TRY(ygemm_run(f.c, p.c1y, xc.p, y, ld, vp->nocc, f.B, N));
     double *s1, *q1;
     LION_TRY(alloc_stats(f, p.c1.cout_pad, &s1, &q1));
-    const int nwarp = 8;
-    const size_t smem = (size_t)nwarp * (32 * (p.c1.cout_pad + 2) * sizeof(float) + SPG_LIST * sizeof(int2));
+    const int nwarp = 4;
+    const size_t smem = (size_t)nwarp * (32 * (p.c1.cout_pad + 2) * sizeof(float) + SPG_LIST * sizeof(unsigned));
     static DevOnce attr_once;
     if (attr_once.need()) {
       LION_CHECK_CUDA(cudaFuncSetAttribute(k_sparse_conv_gather<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

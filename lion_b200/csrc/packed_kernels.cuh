@@ -168,10 +168,44 @@ __global__ void k_scatter_compact(const float4* __restrict__ feat, const int* __
 // once -- adds the bias, stores the raw convolution output and accumulates the GroupNorm statistics.  Deterministic.
 //   one warp = 32 consecutive interior voxels; accumulators [32][C] in shared memory; C <= 64 (2 channels per lane)
 //   grid = (ceil(r^3 / (32 * warps)), B), block = 32 * warps, dynamic smem = warps * (32 * (C + 2) floats + SPG_LIST int2)
-constexpr int SPG_LIST = 256;      // contribution-list entries per warp
+constexpr int SPG_LIST = 256;      // contribution-list entries per warp (packed: v << 10 | tap << 5 | voxel-in-warp)
 constexpr int SPG_BATCH = 16;      // y rows in flight per warp
+// consume a warp's contribution list: SPG_BATCH independent 4*C-byte row reads in flight, then the adds in list order.
+// NOT inlined: the tap loop below is fully unrolled and an inlined copy per tap made a 12 600-instruction kernel whose
+// fetch stalls dominated (ncu: 25 % of the samples on no-instruction / EXIT).
 template <int C>
-__global__ void __launch_bounds__(256)
+__device__ __noinline__ void spg_flush(float* __restrict__ acc, const unsigned* __restrict__ list, int n,
+                                       const float* __restrict__ yb, int ldy, int lane) {
+  constexpr int CPL = C / 32, PITCH = C + 2;
+  __syncwarp();
+  for (int i0 = 0; i0 < n; i0 += SPG_BATCH) {
+    float2 val[SPG_BATCH];
+    int jj[SPG_BATCH];
+#pragma unroll
+    for (int k = 0; k < SPG_BATCH; ++k) {
+      jj[k] = -1;
+      if (i0 + k < n) {
+        const unsigned e = list[i0 + k];
+        const float* src = yb + (size_t)(e >> 10) * ldy + ((e >> 5) & 31) * C + lane * CPL;
+        if (CPL == 2) val[k] = __ldg(reinterpret_cast<const float2*>(src));
+        else val[k] = make_float2(__ldg(src), 0.0f);
+        jj[k] = (int)(e & 31);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < SPG_BATCH; ++k) {
+      if (jj[k] >= 0) {
+        float* a = acc + jj[k] * PITCH + lane * CPL;
+        a[0] += val[k].x;
+        if (CPL == 2) a[1] += val[k].y;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int C>
+__global__ void __launch_bounds__(128)
 k_sparse_conv_gather(const float* __restrict__ y, int ldy, const int* __restrict__ vgrid, const float* __restrict__ bias,
                      float4* __restrict__ out, double* __restrict__ ssum, double* __restrict__ ssq, int stat_stride,
                      int r, int Nrows) {
@@ -180,7 +214,7 @@ k_sparse_conv_gather(const float* __restrict__ y, int ldy, const int* __restrict
   constexpr int CPL = C / 32;                     // channels per lane
   constexpr int PITCH = C + 2;
   extern __shared__ float s_acc[];
-  __shared__ float s_red[2][8][C];
+  __shared__ float s_red[2][4][C];
   const int b = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int rp = r + 2, P = rp * rp * rp, V = r * r * r;
   const int q = (blockIdx.x * nw + wid) * 32 + lane;          // interior voxel (x, y, z) flattened
@@ -188,62 +222,38 @@ k_sparse_conv_gather(const float* __restrict__ y, int ldy, const int* __restrict
   int p = 0;
   if (live) { int z = q % r, yy = (q / r) % r, x = q / (r * r); p = ((x + 1) * rp + (yy + 1)) * rp + (z + 1); }
   float* acc = s_acc + (size_t)wid * 32 * PITCH;
-  // bias
-  for (int j = 0; j < 32; ++j)
-#pragma unroll
-    for (int k = 0; k < CPL; ++k) acc[j * PITCH + lane * CPL + k] = bias ? bias[lane * CPL + k] : 0.0f;
+  // the 27 neighbour ids of this lane's voxel: independent loads, all in flight together (a rolled tap loop serialised
+  // 27 L2 round trips per warp)
   const int* vg = vgrid + (size_t)b * P;
-  const float* yb = y + (size_t)b * Nrows * ldy;
-  // the 27 neighbour ids of this lane's voxel: independent loads, all in flight together (the tap loop below must not
-  // serialise 27 L2 round trips per warp -- that alone cost 280 us in the first version of this kernel)
   int nb[27];
 #pragma unroll
   for (int t = 0; t < 27; ++t) {
     const int off = ((t / 9) - 1) * rp * rp + (((t / 3) % 3) - 1) * rp + ((t % 3) - 1);
     nb[t] = live ? __ldg(vg + p + off) : -1;
   }
-  // contributions (occupied neighbour v of lane j's voxel, tap t) are listed in shared memory in (t, j) order, then
-  // consumed SPG_BATCH at a time: that many independent 4*C-byte row reads in flight per warp; the accumulation order per
-  // output voxel is ascending t whatever the batching
-  int2* list = reinterpret_cast<int2*>(s_acc + (size_t)nw * 32 * PITCH) + wid * SPG_LIST;
+  // accumulators start at the bias
+  {
+    float bv[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) bv[k] = bias ? bias[lane * CPL + k] : 0.0f;
+    for (int j = 0; j < 32; ++j)
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) acc[j * PITCH + lane * CPL + k] = bv[k];
+  }
+  const float* yb = y + (size_t)b * Nrows * ldy;
+  // contributions (occupied neighbour v of lane j's voxel, tap t) are listed in shared memory in (t, j) order and then
+  // consumed in that order: the accumulation order per output voxel is ascending t whatever the batching
+  unsigned* list = reinterpret_cast<unsigned*>(s_acc + (size_t)nw * 32 * PITCH) + wid * SPG_LIST;
   int n = 0;
-  auto flush = [&]() {
-    __syncwarp();
-    for (int i0 = 0; i0 < n; i0 += SPG_BATCH) {
-      float2 val[SPG_BATCH];
-      int jj[SPG_BATCH];
-#pragma unroll
-      for (int k = 0; k < SPG_BATCH; ++k) {
-        jj[k] = -1;
-        if (i0 + k < n) {
-          const int2 e = list[i0 + k];
-          const float* src = yb + (size_t)e.x * ldy + (e.y >> 5) * C + lane * CPL;
-          if (CPL == 2) val[k] = __ldg(reinterpret_cast<const float2*>(src));
-          else val[k] = make_float2(__ldg(src), 0.0f);
-          jj[k] = e.y & 31;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < SPG_BATCH; ++k) {
-        if (jj[k] >= 0) {
-          float* a = acc + jj[k] * PITCH + lane * CPL;
-          a[0] += val[k].x;
-          if (CPL == 2) a[1] += val[k].y;
-        }
-      }
-    }
-    __syncwarp();
-    n = 0;
-  };
 #pragma unroll
   for (int t = 0; t < 27; ++t) {
     const int v = nb[t];
     const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
-    if (n + 32 > SPG_LIST) flush();
-    if (v >= 0) list[n + __popc(m & ((1u << lane) - 1u))] = make_int2(v, (t << 5) | lane);
+    if (n + 32 > SPG_LIST) { spg_flush<C>(acc, list, n, yb, ldy, lane); n = 0; }
+    if (v >= 0) list[n + __popc(m & ((1u << lane) - 1u))] = ((unsigned)v << 10) | ((unsigned)t << 5) | (unsigned)lane;
     n += __popc(m);
   }
-  flush();
+  spg_flush<C>(acc, list, n, yb, ldy, lane);
   // store (PF/VG layout: consecutive lanes = consecutive z) and statistics
   if (live) {
 #pragma unroll
@@ -252,15 +262,21 @@ k_sparse_conv_gather(const float* __restrict__ y, int ldy, const int* __restrict
       out[((size_t)b * (C / 4) + g) * P + p] = make_float4(a[0], a[1], a[2], a[3]);
     }
   }
-  float cs[CPL], cq[CPL];
+  float cs[2][CPL], cq[2][CPL];
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) { cs[k] = 0.0f; cq[k] = 0.0f; }
-  const int nlive = min(32, V - (blockIdx.x * nw + wid) * 32);
-  for (int j = 0; j < nlive; ++j)
+  for (int k = 0; k < CPL; ++k) { cs[0][k] = cs[1][k] = 0.0f; cq[0][k] = cq[1][k] = 0.0f; }
+  const int nlive = max(0, min(32, V - (blockIdx.x * nw + wid) * 32));
+  for (int j = 0; j < nlive; j += 2) {
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) { const float a = acc[j * PITCH + lane * CPL + k]; cs[k] += a; cq[k] = fmaf(a, a, cq[k]); }
+    for (int h = 0; h < 2; ++h) {
+      if (j + h < nlive) {
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) { s_red[0][wid][lane * CPL + k] = cs[k]; s_red[1][wid][lane * CPL + k] = cq[k]; }
+        for (int k = 0; k < CPL; ++k) { const float a = acc[(j + h) * PITCH + lane * CPL + k]; cs[h][k] += a; cq[h][k] = fmaf(a, a, cq[h][k]); }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) { s_red[0][wid][lane * CPL + k] = cs[0][k] + cs[1][k]; s_red[1][wid][lane * CPL + k] = cq[0][k] + cq[1][k]; }
   __syncthreads();
   if (threadIdx.x < C) {
     float a = 0.0f, qq = 0.0f;

@@ -12,7 +12,7 @@
 // tap-channels and TMEM columns voxels, so a tcgen05.ld register holds one voxel for 32 consecutive n across the warp:
 // every store instruction writes 128 contiguous bytes of a y row.  (The convolution kernel's own epilogue, lanes = rows,
 // wrote 16-byte pieces 6.9 KB apart: 220 us for the same 453 MB.)
-// One CTA = 128 threads, one n-tile, a strided range of 256-row blocks; operands by cp.async.bulk; the next block's
+// One CTA = 256 threads, one n-tile, a strided range of 256-row blocks; operands by cp.async.bulk; the next block's
 // voxels are requested as soon as the MMAs of the current one retire, i.e. under the epilogue; 2 CTAs per SM.
 #include "common.cuh"
 #include "model.cuh"
@@ -79,7 +79,7 @@ struct Params {
   int G, N, B, ld, blocks_per_shape, nblocks;
 };
 
-__global__ void __launch_bounds__(128, 2) k_ygemm(Params P) {
+__global__ void __launch_bounds__(256, 2) k_ygemm(Params P) {
   extern __shared__ __align__(128) uint8_t smem[];
   float4* sW = (float4*)smem;                              // [G][128]
   float4* sX = sW + (size_t)P.G * 128;                     // [G][ROWS]
@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(128, 2) k_ygemm(Params P) {
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ROWS >> 3) << 17) | ((128u >> 4) << 24);
   if (tid == 0) mbar_wait(bar_w, 0);      // only the issuing thread consumes the operand buffers
   uint32_t phase = 0;
-  const int n = nt * 128 + warp * 32 + lane;                    // this lane's tap-channel
+  const int half = warp >> 2, wq = warp & 3;
+  const int n = nt * 128 + wq * 32 + lane;                      // this lane's tap-channel
+  const bool n_ok = nt * 128 + wq * 32 < P.ld;                  // warp-uniform (ld is a multiple of 32)
+  const uint32_t tl = tmem + ((uint32_t)(wq * 32) << 16);
   while (rb < P.nblocks) {
     if (tid == 0) {
       mbar_wait(bar_x, phase);
@@ -149,28 +152,23 @@ __global__ void __launch_bounds__(128, 2) k_ygemm(Params P) {
     while (nb < P.nblocks && (n2 = block_rows(nb, b2, r2)) == 0) nb += gridDim.y;
     if (tid == 0 && nb < P.nblocks) load_x(b2, r2, n2);
     rb = nb; b = b2; r0 = r2; nrows = n2;
-    // ---- epilogue: lane = tap-channel n, register i of chunk c = voxel row cr0 + 16 c + i
-    float* yrow = P.y + ((size_t)cb * P.N + cr0) * P.ld + n;
-    const bool n_ok = n < P.ld;
-    uint32_t ra[16], rbuf[16];
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    // ---- epilogue: lane = tap-channel n, register i of chunk c = voxel row cr0 + 16 c + i.  Warps w and w + 4 share a
+    // TMEM lane quarter and take alternate 16-voxel chunks.  ~3 instructions per 128-byte store (pointer bump + STG):
+    // the first version spent 12 (64-bit index arithmetic and a row predicate per store) and was issue-bound at 98 us.
+    const size_t ldb = (size_t)P.ld;
     const int nchunk = (cn + 15) >> 4;
-    tmem_ld16_issue(tl, ra);
-    for (int c = 0; c < nchunk; c += 2) {
-      tmem_ld16_wait(ra);
-      if (c + 1 < nchunk) tmem_ld16_issue(tl + (uint32_t)((c + 1) * 16), rbuf);
-      if (n_ok) {
+    if (n_ok) {
+      for (int c = half; c < nchunk; c += 2) {
+        uint32_t ra[16];
+        tmem_ld16_issue(tl + (uint32_t)(c * 16), ra);
+        tmem_ld16_wait(ra);
+        float* yp = P.y + ((size_t)cb * P.N + cr0 + c * 16) * ldb + n;
+        if (c * 16 + 16 <= cn) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c * 16 + i < cn) yrow[(size_t)(c * 16 + i) * P.ld] = __uint_as_float(ra[i]);
-      }
-      if (c + 1 < nchunk) {
-        tmem_ld16_wait(rbuf);
-        if (c + 2 < nchunk) tmem_ld16_issue(tl + (uint32_t)((c + 2) * 16), ra);
-        if (n_ok) {
+          for (int i = 0; i < 16; ++i) { *yp = __uint_as_float(ra[i]); yp += ldb; }
+        } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if ((c + 1) * 16 + i < cn) yrow[(size_t)((c + 1) * 16 + i) * P.ld] = __uint_as_float(rbuf[i]);
+          for (int i = 0; i < 16; ++i) { if (c * 16 + i < cn) *yp = __uint_as_float(ra[i]); yp += ldb; }
         }
       }
     }
@@ -198,6 +196,7 @@ bool ygemm_usable(const ConvW& y) {
 // y[b][v][0..ld) = x[b][v][:] * Wy for the first nocc[b] rows of every shape
 int ygemm_run(Ctx* c, const ConvW& y, const float4* xc, float* out, int ld, const int* nocc, int B, int N) {
   if (c->dry) return 0;
+  if (ld % 32) { set_error("ygemm: row pitch %d is not a multiple of 32", ld); return LION_ERR_ARG; }
   spc::Params P{};
   P.x = xc; P.w = y.tc.w; P.y = out; P.nocc = nocc;
   P.G = y.tc.nchunk * (y.tc.ck / 4);        // group slots of the packing (>= cin_pad / 4; extra slots hold zero weights)
@@ -214,7 +213,7 @@ int ygemm_run(Ctx* c, const ConvW& y, const float4* xc, float* out, int ld, cons
   if (attr_once.need())
     LION_CHECK_CUDA(cudaFuncSetAttribute(spc::k_ygemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
   if (smem > 113 * 1024) { set_error("ygemm: %d input channels do not fit two CTAs per SM", y.cin_pad); return LION_ERR_ARG; }
-  spc::k_ygemm<<<dim3(n_tiles, slices), 128, smem, c->stream>>>(P);
+  spc::k_ygemm<<<dim3(n_tiles, slices), 256, smem, c->stream>>>(P);
   c->launches++;
   return check_launch(c, "ygemm");
 }
