@@ -23,8 +23,6 @@
 //     issuers (even / odd row tiles), warps 3-10 = epilogue (tcgen05.ld -> +bias -> halo mask ->
 //     coalesced float4 stores, GroupNorm sum / sum-of-squares reduced in registers / shared memory,
 //     one fp64 atomic per channel per work item).
-//   * 1x1 convolutions may stage several consecutive row tiles per pipeline stage (Params::MT):
-//     their stages carry only KG/2 MMAs per tile, so the barrier round trip per stage dominates.
 #include "common.cuh"
 #include "model.cuh"
 #include <cstdlib>
@@ -196,7 +194,6 @@ struct Params {
   int KG, nchunk;        // channel groups per chunk, chunks
   int NT;                // output channels per CTA (UMMA N)
   int G;                 // row tiles (accumulators) per work item
-  int MT;                // row tiles per A stage (1 for 3x3x3; 1x1: consecutive tiles share one bulk copy)
   int B;                 // shapes
   int a_stage_bytes, b_stage_bytes, stage_rows;
   int a_stages;          // depth of the A ring
@@ -320,42 +317,54 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   // tail; from here on global memory written by that kernel is consumed
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
+  // Work distribution.  The (n-tile, shape, row-tile) space is flattened (row tile fastest) and cut into gridDim.x
+  // contiguous ranges of equal length (+-1 tile); inside its range a CTA forms work items = up to G consecutive row
+  // tiles sharing the weight slabs (they may belong to two shapes), sized evenly (9 tiles -> 3+3+3, not 4+4+1).  Round 1 dealt fixed
+  // G-tile items round-robin: with 41 tiles per shape (r = 16) that left some CTAs 12 tiles and others 8 -- the kernel
+  // ran at the pace of the 12 (profiles/r02_conv_balanced_ranges.txt).
   const int ntile_total = (P.p_end - P.p_begin + 127) / 128;
-  const int ngrp = (ntile_total + P.G - 1) / P.G;
   const int n_nt = P.cout_pad / P.NT;
-  const int n_items = ngrp * n_nt * P.B;
-  // work item w -> (b, n-tile, row-tile group); consecutive items share weights (L2 locality)
-#define ITEM_DECODE(w)                                                  \
-  const int grp = (w) % ngrp; const int nt = ((w) / ngrp) % n_nt; const int b = (w) / (ngrp * n_nt); \
-  const int tile0 = grp * P.G; const int ntile = min(P.G, ntile_total - tile0); const int n0 = nt * P.NT;
+  const long long U = (long long)n_nt * P.B * ntile_total;
+  const long long u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
+  struct Items {
+    long long u, u_end; int ntile_total, B, G;
+    // next item: n-tile nt, first tile v0 in the n-tile's flat (shape, row tile) space, ntile tiles.  An item may run
+    // across a shape boundary -- its tiles share the weight slabs whatever shape they belong to -- but not across n-tiles.
+    __device__ __forceinline__ bool next(int& nt, long long& v0, int& ntile) {
+      if (u >= u_end) return false;
+      const long long per_nt = (long long)B * ntile_total;
+      nt = (int)(u / per_nt);
+      v0 = u - (long long)nt * per_nt;
+      long long run = per_nt - v0;
+      if (u_end - u < run) run = u_end - u;
+      const long long k = (run + G - 1) / G;
+      ntile = (int)((run + k - 1) / k);
+      u += ntile;
+      return true;
+    }
+  };
 
   if (warp == 0) {
     // ===================== producer (whole warp; lane kg issues the copy of channel group kg) ====
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;          // ring positions and phase bits
     const uint32_t bytes = (uint32_t)P.stage_rows * 16u;
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-      ITEM_DECODE(w)
-      (void)n0;
+    Items items{u_begin, u_end, ntile_total, P.B, P.G};
+    int nt, ntile;
+    long long v0;
+    int occ_shape = -1;                                // shape whose occupancy flags s_occ holds
+    while (items.next(nt, v0, ntile)) {
       const float* wsrc = P.w + (size_t)nt * P.nchunk * P.ntg * (P.b_stage_bytes / 4);
-      // sparse input: the shape's occupancy flags (<= 1 KB) are copied to shared memory once per item -- the per-stage
-      // check below then costs a broadcast LDS instead of 3-4 dependent global loads on the producer's critical path
-      // (with 227 KB of shared memory the L1 is ~1 KB, so every __ldg went to L2)
-      const unsigned char* occ_b = (P.occ && P.occ_stride <= OCC_SMEM) ? s_occ : (P.occ ? P.occ + (size_t)b * P.occ_stride : nullptr);
-      if (P.occ && P.occ_stride <= OCC_SMEM) {
-        __syncwarp();
-        for (int k = lane; k < P.occ_stride; k += 32) s_occ[k] = __ldg(P.occ + (size_t)b * P.occ_stride + k);
-        __syncwarp();
-      }
-      const long long row_item = (long long)P.p_begin + (long long)tile0 * 128 - P.halo;
-      const float4* in_item = P.in + (size_t)b * P.Gin * P.rows;
+      // lane l keeps (shape, row tile) of the item's tile l: one division per item, a shuffle per stage
+      int my_b = 0, my_t = 0;
+      if (lane < ntile) { const int vl = (int)v0 + lane; my_b = vl / ntile_total; my_t = vl - my_b * ntile_total; }
       for (int cc = 0; cc < P.nchunk; ++cc) {
         const int kg_real = min(KG, P.Gin - cc * KG);
-        const float4* in_lane = in_item + (size_t)(cc * KG + (lane < kg_real ? lane : 0)) * P.rows;
+        const size_t grp_lane = (size_t)(cc * KG + (lane < kg_real ? lane : 0));
         for (int tg = 0; tg < P.ntg; ++tg) {
           // the last sweep of an item is never skipped: every accumulator then receives at
           // least one (zero-initialising) MMA per item and needs no "was it touched" bookkeeping
-          const bool may_skip = occ_b && !(cc == P.nchunk - 1 && tg == P.ntg - 1);
+          const bool may_skip = P.occ && !(cc == P.nchunk - 1 && tg == P.ntg - 1);
           mbar_wait(bar_empty_b + 8 * sb, pb ^ 1);
           if (lane == 0) {
             mbar_expect_tx(bar_full_b + 8 * sb, P.b_stage_bytes);
@@ -363,35 +372,40 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
                      P.b_stage_bytes, bar_full_b + 8 * sb);
           }
           if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
-          long long row0 = row_item + P.tg_off[tg];
-          const int MT = (TPG == 1) ? P.MT : 1;      // compile-time 1 in the 3x3x3 instantiations
-          for (int j = 0; j < ntile; j += MT, row0 += 128 * MT) {
+          for (int j = 0; j < ntile; ++j) {
+            const int bj = __shfl_sync(0xffffffffu, my_b, j), tj = __shfl_sync(0xffffffffu, my_t, j);
+            const long long row0 = (long long)P.p_begin + (long long)tj * 128 - P.halo + P.tg_off[tg];
+            const float4* in_lane = P.in + ((size_t)bj * P.Gin + grp_lane) * P.rows;
             mbar_wait(bar_empty_a + 8 * sa, pa ^ 1);
             bool empty = false;
             if (may_skip) {
+              // sparse input: the shape's occupancy flags (<= 1 KB) live in shared memory -- a broadcast LDS per
+              // check instead of dependent global loads on the producer's critical path
+              const unsigned char* occ_b = P.occ + (size_t)bj * P.occ_stride;
+              if (P.occ_stride <= OCC_SMEM) {
+                if (occ_shape != bj) {
+                  __syncwarp();
+                  for (int k = lane; k < P.occ_stride; k += 32) s_occ[k] = __ldg(occ_b + k);
+                  __syncwarp();
+                  occ_shape = bj;
+                }
+                occ_b = s_occ;
+              }
               long long lo = row0 < 0 ? 0 : row0, hi = row0 + P.stage_rows - 1;
               if (hi > P.rows - 1) hi = P.rows - 1;
               unsigned any = 0;
               for (int k = (int)(lo >> 6); k <= (int)(hi >> 6); ++k) any |= occ_b[k];
               empty = (any == 0);
             }
-            // multi-tile stages (1x1 only): copy just the rows this item still has, and never past
-            // the end of the (b, group) slab
-            uint32_t nbytes = bytes;
-            if (MT > 1) {
-              long long nr = (long long)min(MT, ntile - j) * 128;
-              if (nr > P.rows - row0) nr = P.rows - row0;
-              nbytes = (uint32_t)nr * 16u;
-            }
             const uint32_t full = bar_full_a + 8 * sa;
             if (lane == 0) {
               s_skip[sa] = empty ? 1u : 0u;
               if (empty) asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(full) : "memory");
-              else mbar_expect_tx(full, nbytes * kg_real);
+              else mbar_expect_tx(full, bytes * kg_real);
             }
             __syncwarp();
             if (!empty && lane < kg_real)
-              bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, nbytes, full);
+              bulk_g2s(sA_addr + sa * (uint32_t)P.a_stage_bytes + lane * bytes, in_lane + row0, bytes, full);
             if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
           }
         }
@@ -412,9 +426,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
     const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4;
     const uint32_t a_ring16 = (smem_u32(sA) >> 4) + (uint32_t)P.halo;
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      ITEM_DECODE(w)
-      (void)b; (void)n0; (void)tile0;
+    Items items{u_begin, u_end, ntile_total, P.B, P.G};
+    int nt, ntile;
+    long long v0;
+    for (; items.next(nt, v0, ntile); ++it) {
       uint32_t started = 0;
       // accumulators this item does not use still take part in the per-item phase bookkeeping:
       // wait until the epilogue released them (previous item) before re-arming them below
@@ -426,8 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
           const uint32_t b_base16 = smem_u32(sB + (size_t)sb * P.b_stage_bytes) >> 4;
           const bool first = (cc | tg) == 0;
           const bool last = (cc == P.nchunk - 1) && (tg == P.ntg - 1);
-          const int MT = (TPG == 1) ? P.MT : 1;      // compile-time 1 in the 3x3x3 instantiations (their issue loop is the critical path)
-          for (int j = 0; j < ntile; j += MT) {
+          for (int jt = 0; jt < ntile; ++jt) {
             const uint32_t my_sa = sa, my_pa = pa;
             if (++sa == (uint32_t)A_STAGES) { sa = 0; pa ^= 1; }
             // BOTH issuers wait on every stage and both release it (empty count 2).  A parity wait is
@@ -436,21 +450,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             // phase behind and mistake "not yet loaded" for "loaded" (seen with odd ring depths).
             mbar_wait(bar_full_a + 8 * my_sa, my_pa);
             bool issued = false;
-            for (int jj = 0; jj < MT; ++jj) {
-              const int jt = j + jj;
-              if (jt >= ntile) break;
-              if ((jt & 1) != me) continue;                              // the other issuer's tile
+            if ((jt & 1) == me) {                                         // else: the other issuer's tile
               if (first) mbar_wait(bar_tfree + 8 * jt, (it & 1) ^ 1);    // accumulator jt drained (previous item)
-              if (s_skip[my_sa]) continue;                               // all-zero input slab: nothing to accumulate
-              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-              const uint32_t a_base16 = a_ring16 + my_sa * a_stage16 + (uint32_t)jj * 128u;
-              const uint32_t d = tmem_base + (uint32_t)(jt * P.NT);
-              const bool fresh = ((started >> jt) & 1u) == 0;
-              started |= 1u << jt;
-              issue_stage<KG, TPG>(d, a_lo_c | (a_base16 & 0x3fff), b_lo_c | (b_base16 & 0x3fff), idesc, fresh ? 0u : 1u, d_hi,
-                                   2u * a_pitch16, 2u * b_pitch16, b_tap16, P.tap_off);
-              if (last) umma_commit_w(bar_accf + 8 * jt);   // accumulator jt complete -> epilogue may drain it
-              issued = true;
+              if (!s_skip[my_sa]) {                                      // (all-zero input slab: nothing to accumulate)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_base16 = a_ring16 + my_sa * a_stage16;
+                const uint32_t d = tmem_base + (uint32_t)(jt * P.NT);
+                const bool fresh = ((started >> jt) & 1u) == 0;
+                started |= 1u << jt;
+                issue_stage<KG, TPG>(d, a_lo_c | (a_base16 & 0x3fff), b_lo_c | (b_base16 & 0x3fff), idesc, fresh ? 0u : 1u, d_hi,
+                                     2u * a_pitch16, 2u * b_pitch16, b_tap16, P.tap_off);
+                if (last) umma_commit_w(bar_accf + 8 * jt);   // accumulator jt complete -> epilogue may drain it
+                issued = true;
+              }
             }
             // hand the stage back: when this warp's MMAs retire, or at once if it issued none
             if (issued) umma_commit_w(bar_empty_a + 8 * my_sa);
@@ -470,12 +482,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
     const int hcol = (ew >> 2) * (P.NT / 2);       // first accumulator column of this warp's half
     const int CH = P.NT / 2;
     uint32_t it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-      ITEM_DECODE(w)
+    Items items{u_begin, u_end, ntile_total, P.B, P.G};
+    int nt, ntile;
+    long long v0;
+    for (; items.next(nt, v0, ntile); ++it) {
+      const int n0 = nt * P.NT;
       asm volatile("bar.sync 1, 256;" ::: "memory");            // previous item's s_bias / s_stat readers are done
       if (et < P.NT) s_bias[et] = P.bias ? P.bias[n0 + et] : 0.0f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       float run_s[4] = {0, 0, 0, 0}, run_q[4] = {0, 0, 0, 0};    // per 16-column chunk of this warp's half
+      // GroupNorm statistics are per shape: flushed whenever the item moves on to the next shape, and at its end
+      // (warp partials -> shared memory -> one fp64 atomic per channel; block-uniform control flow: bar.sync inside)
+      auto flush_stats = [&](int bb) {
+        if ((lane & 1) == 0) {
+          for (int k = 0; k < CH / 16; ++k) {
+            s_stat[(ew * 2 + 0) * 64 + k * 16 + ch16_of_lane(lane)] = run_s[k];
+            s_stat[(ew * 2 + 1) * 64 + k * 16 + ch16_of_lane(lane)] = run_q[k];
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et < P.NT) {
+          const int half = et / CH, ch = et % CH;
+          float s = 0.f, qq = 0.f;
+#pragma unroll
+          for (int ww = 0; ww < 4; ++ww) { s += s_stat[((half * 4 + ww) * 2 + 0) * 64 + ch]; qq += s_stat[((half * 4 + ww) * 2 + 1) * 64 + ch]; }
+          atomicAdd(P.ssum + (size_t)bb * P.cout_pad + n0 + et, (double)s);
+          atomicAdd(P.ssq + (size_t)bb * P.cout_pad + n0 + et, (double)qq);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // s_stat is free again
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { run_s[k] = 0.0f; run_q[k] = 0.0f; }
+      };
+      int b = (int)(v0 / ntile_total);
       if (TPG == 1 && CH <= 32) {
         // 1x1 convolutions, N <= 64 (compiled out of the 3x3x3 instantiations, whose epilogue is off the
         // critical path and whose issue loop suffered from the extra register pressure): per-lane (= per-row) running sums over the item's tiles, ONE cross-lane reduction
@@ -486,8 +524,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
         for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
           for (int i = 0; i < 16; ++i) { acc_s[cc][i] = 0.0f; acc_q[cc][i] = 0.0f; }
+        auto fold_acc = [&]() {
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            if (cc * 16 < CH) {
+              run_s[cc] = warp_transpose_sum16(acc_s[cc], lane);
+              run_q[cc] = warp_transpose_sum16(acc_q[cc], lane);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { acc_s[cc][i] = 0.0f; acc_q[cc][i] = 0.0f; }
+          }
+        };
         for (int j = 0; j < ntile; ++j) {
-          int p = P.p_begin + (tile0 + j) * 128 + q * 32 + lane;
+          const long long vj = v0 + j;
+          const int bj = (int)(vj / ntile_total), tj = (int)(vj - (long long)bj * ntile_total);
+          if (bj != b) { if (P.ssum) { fold_acc(); flush_stats(b); } b = bj; }
+          int p = P.p_begin + tj * 128 + q * 32 + lane;
           bool inrange = p < P.p_end;
           bool valid = inrange;
           if (P.rp > 0 && inrange) {
@@ -527,18 +579,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
             }
           }
         }
-        if (P.ssum) {
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            if (cc * 16 < CH) {
-              run_s[cc] = warp_transpose_sum16(acc_s[cc], lane);
-              run_q[cc] = warp_transpose_sum16(acc_q[cc], lane);
-            }
-          }
-        }
+        if (P.ssum) fold_acc();
       } else
       for (int j = 0; j < ntile; ++j) {
-        int p = P.p_begin + (tile0 + j) * 128 + q * 32 + lane;
+        const long long vj = v0 + j;
+        const int bj = (int)(vj / ntile_total), tj = (int)(vj - (long long)bj * ntile_total);
+        if (bj != b) { if (P.ssum) flush_stats(b); b = bj; }
+        int p = P.p_begin + tj * 128 + q * 32 + lane;
         bool inrange = p < P.p_end;
         bool valid = inrange;
         if (P.rp > 0 && inrange) {
@@ -582,23 +629,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_tfree + 8 * j) : "memory");
       }
-      if (P.ssum) {
-        if ((lane & 1) == 0) {
-          for (int k = 0; k < CH / 16; ++k) {
-            s_stat[(ew * 2 + 0) * 64 + k * 16 + ch16_of_lane(lane)] = run_s[k];
-            s_stat[(ew * 2 + 1) * 64 + k * 16 + ch16_of_lane(lane)] = run_q[k];
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et < P.NT) {
-          const int half = et / CH, ch = et % CH;
-          float s = 0.f, qq = 0.f;
-#pragma unroll
-          for (int ww = 0; ww < 4; ++ww) { s += s_stat[((half * 4 + ww) * 2 + 0) * 64 + ch]; qq += s_stat[((half * 4 + ww) * 2 + 1) * 64 + ch]; }
-          atomicAdd(P.ssum + (size_t)b * P.cout_pad + n0 + et, (double)s);
-          atomicAdd(P.ssq + (size_t)b * P.cout_pad + n0 + et, (double)qq);
-        }
-      }
+      if (P.ssum) flush_stats(b);
       // accumulators this item did not use: release them too so that the phase bookkeeping of
       // bar_tfree stays in step with the item counter
       for (int j = ntile; j < MAX_ACC; ++j) {
@@ -607,7 +638,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       }
     }
   }
-#undef ITEM_DECODE
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
@@ -725,43 +755,19 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   } else {
     P.tg_off[0] = 0; P.tap_off[0] = 0; P.halo = 0;
   }
-  P.MT = 1;
   P.stage_rows = 128 + 2 * P.halo;
-  P.a_stage_bytes = KG * P.stage_rows * 16;     // per row tile; multi-tile stages are sized below, once G is known
+  P.a_stage_bytes = KG * P.stage_rows * 16;
   P.b_stage_bytes = tpg * KG * NT * 16;
   int ntile = cdiv(geo.p_end - geo.p_begin, 128);
   int n_tiles_n = w.cout_pad / NT;
   int gmax = 512 / NT;
   if (gmax > tc::MAX_ACC) gmax = tc::MAX_ACC;
-  // row tiles per work item: more tiles amortise the weight slab (B stage) over more MMAs but
-  // leave fewer, longer items to balance over the SMs.  Pick G by a small cost model:
-  //   rounds(G) * G * max(1, L2 bytes per stage / (MMA cycles per stage * ~38 B/clk/SM))
-  int G = 1;
-  {
-    const double mma_cycles = (double)tpg * (KG / 2) * (NT / 2.0);          // UMMA M128 x N x K8 = N/2 cycles
-    double best = 1e30;
-    for (int g = 1; g <= gmax; g <<= 1) {
-      long long items = (long long)cdiv(ntile, g) * n_tiles_n * B;
-      double rounds = (double)((items + c->num_sms - 1) / c->num_sms);
-      double bw = ((double)P.b_stage_bytes / g + P.a_stage_bytes) / (mma_cycles * 38.0);
-      double cost = rounds * g * (bw > 1.0 ? bw : 1.0);
-      if (cost < best * 0.999) { best = cost; G = g; }
-    }
-  }
+  // row tiles per work item: as many as TMEM holds (the weight slab of a stage is then shared by that many MMA groups);
+  // parallelism does not depend on G any more -- the kernel cuts the flat tile space into equal ranges per CTA
+  int G = gmax;
+  { static int ge = -1; if (ge < 0) { const char* e = getenv("LION_TC_G"); ge = e ? atoi(e) : 0; } if (ge > 0 && ge < G) G = ge; }
   P.G = G;
   P.B = B;
-  if (w.ntaps == 1) {
-    // 1x1: a stage carries only KG/2 MMAs per row tile, so the per-stage barrier round trips of
-    // producer and issuers dominate; stage MT consecutive row tiles with one bulk copy per group
-    static int mt_env = -1;
-    if (mt_env < 0) { const char* e = getenv("LION_TC_MT"); mt_env = e ? atoi(e) : 1; }
-    int mt = mt_env < 1 ? 1 : mt_env;
-    while (mt > 1 && (mt > G || (mt & (mt - 1)))) --mt;
-    while (mt > 1 && 3LL * KG * 128 * mt * 16 + (long long)tc::B_STAGES * P.b_stage_bytes + 8192 > 227LL * 1024) mt >>= 1;   // ring >= 3
-    P.MT = mt;
-    P.stage_rows = 128 * mt;
-    P.a_stage_bytes = KG * P.stage_rows * 16;
-  }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
   const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128 + tc::OCC_SMEM;
@@ -783,8 +789,12 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   P.a_stages = a_stages;
   size_t smem = (size_t)a_stages * P.a_stage_bytes + (size_t)tc::B_STAGES * P.b_stage_bytes + fixed;
   if (smem > 227 * 1024) { set_error("conv_tc: %zu bytes of shared memory needed", smem); return LION_ERR_ARG; }
-  long long n_items = (long long)cdiv(ntile, G) * n_tiles_n * B;
-  int grid = (int)(n_items < c->num_sms ? n_items : c->num_sms);      // persistent: one CTA per SM
+  // persistent, at most one CTA per SM: the fewest CTAs that still reach the minimal maximum of tiles per CTA
+  // (224 tiles on 148 SMs: 112 CTAs x 2 tiles, not 148 CTAs x 1-2 -- every CTA streams the whole weight tensor from L2,
+  // and the r = 8 layers are bound by exactly that)
+  long long n_units = (long long)ntile * n_tiles_n * B;
+  long long per_cta = (n_units + c->num_sms - 1) / c->num_sms;
+  int grid = (int)((n_units + per_cta - 1) / per_cta);
 #define LION_TC_CASE(kg, tpg_)                                                                            \
   if (KG == kg && tpg == tpg_) {                                                                          \
     static DevOnce attr_once;                                                                         \

@@ -439,13 +439,13 @@ static int attn_fwd(Fwd& f, const AttnBlk& a, PF x, float4* dst, int Gd, int g_o
 }
 
 // The first convolution of a PVConv reads a grid with at most N occupied voxels.  When that is a small fraction of r^3
-// it is cheaper to multiply only the occupied voxels by all 27 taps (one GEMM, 27 * N rows of output instead of r^3 * 27
+// (<= 25 %) it is cheaper to multiply only the occupied voxels by all 27 taps (one GEMM, 27 * N rows of output instead of r^3 * 27
 // taps of dense work) and let every output voxel gather its neighbours' rows (k_sparse_conv_gather): at r = 32, N = 2048
 // that is 16x fewer FLOPs and the convolution becomes a ~0.7 GB streaming problem.  LION_SPARSE_CONV1=0 disables it.
 static bool sparse_conv1_wanted(int N, int r) {
   static int on = -1;
   if (on < 0) { const char* e = getenv("LION_SPARSE_CONV1"); on = e ? atoi(e) : 1; }
-  return on && (long long)N * 8 <= (long long)r * r * r;
+  return on && (long long)N * 4 <= (long long)r * r * r;
 }
 static int get_vox(Fwd& f, const float4* c4, int N, int r, VoxPrep** out) {
   for (auto& v : f.vox) if (v.c4 == c4 && v.N == N && v.r == r) { *out = &v; return 0; }
@@ -520,6 +520,12 @@ static int pvconv_fwd(Fwd& f, const PVConvBlk& p, PF feat, const float4* c4, flo
     if (attr_once.need()) {
       LION_CHECK_CUDA(cudaFuncSetAttribute(k_sparse_conv_gather<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       LION_CHECK_CUDA(cudaFuncSetAttribute(k_sparse_conv_gather<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      // level 0 runs next to the side stream: same (maximum) shared-memory carve-out as its kernels, or these blocks
+      // cannot become resident on the SMs FPS occupies (see unet_forward)
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_sparse_conv_gather<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_sparse_conv_gather<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_act_grid, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      LION_CHECK_CUDA(cudaFuncSetAttribute(k_scatter_compact, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     const dim3 grid(cdiv(r * r * r, 32 * nwarp), f.B);
     if (p.c1.cout_pad == 32)

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256, 2) k_ygemm(Params P) {
 }  // namespace spc
 
 bool ygemm_usable(const ConvW& y) {
-  return y.tc.w && y.ntaps == 1 && y.tc.n == 128 && y.cin_pad % 8 == 0 && y.cin_pad <= 64 &&
+  return y.tc.w && y.ntaps == 1 && y.tc.n == 128 && y.cin_pad % 8 == 0 && y.cin_pad <= 128 &&
          y.tc.nchunk * (y.tc.ck / 4) == y.cin_pad / 4;
 }
 
@@ -210,9 +210,11 @@ int ygemm_run(Ctx* c, const ConvW& y, const float4* xc, float* out, int ld, cons
   if (slices < 1) slices = 1;
   const size_t smem = (size_t)P.G * (128 + spc::ROWS) * 16 + 64;
   static DevOnce attr_once;
-  if (attr_once.need())
-    LION_CHECK_CUDA(cudaFuncSetAttribute(spc::k_ygemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-  if (smem > 113 * 1024) { set_error("ygemm: %d input channels do not fit two CTAs per SM", y.cin_pad); return LION_ERR_ARG; }
+  if (attr_once.need()) {
+    LION_CHECK_CUDA(cudaFuncSetAttribute(spc::k_ygemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LION_CHECK_CUDA(cudaFuncSetAttribute(spc::k_ygemm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
+  if (smem > 200 * 1024) { set_error("ygemm: %d input channels do not fit shared memory", y.cin_pad); return LION_ERR_ARG; }   // > 113 KB: one CTA per SM
   spc::k_ygemm<<<dim3(n_tiles, slices), 256, smem, c->stream>>>(P);
   c->launches++;
   return check_launch(c, "ygemm");
