@@ -573,7 +573,8 @@ def main():
     ms_k, fl = C.c_float(), C.c_double()
     L.check(L.lib().lion_bench_conv(L.ctx(dev), 27, 64, 64, 32, B, 20, 3, C.byref(ms_k), C.byref(fl), L.stream()), "bench_conv")
     achieved = fl.value / (ms_k.value * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "lion::tc::k_conv_tc (3x3x3 conv 64->64 @ 32^3, B=%d; 4 launches / denoising step, 49%% of FLOPs)" % B,
+    roofline = {"bound": "tensor", "kernel": "lion::tc::k_conv_tc (3x3x3 conv 64->64 @ 32^3, B=%d; the largest dense convolution: 2 launches / denoising step "
+                          "since the first convolution of each r=32 PVConv runs in sparse form)" % B,
                 "achieved": achieved, "peak": bf16_peak / 2.0, "unit": "TFLOP/s", "frac": achieved / (bf16_peak / 2.0),
                 "ms_per_launch": ms_k.value, "flops_per_launch": fl.value, "peak_source": peak_src, "traffic": None}
     try:   # DRAM bytes of the same kernel from the committed ncu --set full capture (B=32 only)

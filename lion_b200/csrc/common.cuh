@@ -57,6 +57,7 @@ struct Ctx {
   cudaStream_t aux = nullptr;     // side stream for work that is independent of the main chain (FPS)
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_temb = nullptr;
+  cudaEvent_t ev_vox[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   char* base = nullptr;      // arena
   char* zgrid = nullptr;     // persistent all-zero voxel grid (scatter target; re-zeroed after use)

@@ -895,6 +895,7 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   if (aux_nn < 0) { const char* e = getenv("LION_AUX_NN"); aux_nn = e ? atoi(e) : 1; }
   const bool side_nn = aux_nn != 0 && n_sa <= 4;
   std::vector<int*> sa_nidx(n_sa, nullptr), fp_idx(n_sa, nullptr);
+  std::vector<char> vox_pending(n_sa + 1, 0);
   std::vector<float*> fp_wgt(n_sa, nullptr);
   {
     const float4* src = c0;
@@ -948,6 +949,30 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
         LION_CHECK_CUDA(cudaEventRecord(c->ev_temb, c->aux));
         temb_pending = true;
       }
+      // voxelisation prep of the PVConvs that work on these centres (the next SA level and, mirrored, an FP level):
+      // it depends on coordinates only -- one CTA per shape, 13-25 us each on the critical path otherwise
+      if (side_nn) {
+        int rs[2] = {0, 0};
+        if (i + 1 < n_sa) for (auto& blk : u.sa[i + 1]) if (blk.kind == LION_KIND_PVCONV) rs[0] = blk.pv.r;
+        const int fi = n_sa - 2 - i;                  // FP stage whose PVConvs run on level i + 1's points
+        if (fi >= 0 && fi < (int)u.fp.size()) for (auto& blk : u.fp[fi]) if (blk.kind == LION_KIND_PVCONV) rs[1] = blk.pv.r;
+        bool any = false;
+        for (int k = 0; k < 2; ++k) {
+          if (rs[k] <= 0 || (k == 1 && rs[1] == rs[0])) continue;
+          cudaStream_t main_stream = c->stream;
+          c->stream = c->aux;
+          VoxPrep* vp = nullptr;
+          int rc = get_vox(f, fps_centers[i], sb.m, rs[k], &vp);
+          c->stream = main_stream;
+          if (rc) return rc;
+          any = true;
+        }
+        if (any && !c->dry) {
+          stamp(c, c->aux, "aux:voxprep", i + 1);
+          LION_CHECK_CUDA(cudaEventRecord(c->ev_vox[i], c->aux));
+          vox_pending[i + 1] = true;
+        }
+      }
       src = fps_centers[i];
       ncur = sb.m;
     }
@@ -984,6 +1009,7 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
   for (int i = 0; i < n_sa; ++i) {
     c->conv_smem_cap = (i == 0 && share_kb > 0) ? share_kb * 1024 : 0;      // the side stream is busy during level 0
     feats_list[i] = feat; coords_list[i] = coords; n_list[i] = Ncur;
+    if (vox_pending[i]) { LION_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_vox[i - 1], 0)); vox_pending[i] = 0; }
     if (i > 0 && has_t) LION_TRY(with_temb(feat, &feat));
     for (auto& blk : u.sa[i]) {
       if (blk.kind == LION_KIND_PVCONV) {
@@ -1045,6 +1071,7 @@ static int unet_forward(Fwd& f, const float* x, const float* t, const float* sty
     LION_LAUNCH(c, k_pf_to_pm, dim3(cdiv(Ncur, 256), o4.G, B), 256, 0, o4.p, out, o4.G, u.num_classes, Ncur);
   }
   if (temb_pending) LION_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_temb, 0));   // never consumed: still join the side stream
+  for (int i = 1; i <= n_sa; ++i) if (vox_pending[i]) LION_CHECK_CUDA(cudaStreamWaitEvent(c->stream, c->ev_vox[i - 1], 0));
   stamp(c, c->stream, "end");
   return check_launch(c, "unet epilogue");
 }
@@ -1099,6 +1126,7 @@ extern "C" int lion_ctx_create(int device, LionCtx** out) {
     if (e && atoi(e) != 0) LION_CHECK_CUDA(cudaMalloc(&h->c.d_stamps, LION_MAX_STAMPS * sizeof(unsigned long long))); }
   LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev_fork, cudaEventDisableTiming));
   LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev_temb, cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i) LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev_vox[i], cudaEventDisableTiming));
   for (int i = 0; i < 8; ++i) LION_CHECK_CUDA(cudaEventCreateWithFlags(&h->c.ev[i], cudaEventDisableTiming));
   if (prop.major != 10) {
     set_error("lion_b200 is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
@@ -1116,6 +1144,7 @@ extern "C" int lion_ctx_destroy(LionCtx* h) {
   if (h->c.d_stamps) cudaFree(h->c.d_stamps);
   if (h->c.ev_fork) cudaEventDestroy(h->c.ev_fork);
   if (h->c.ev_temb) cudaEventDestroy(h->c.ev_temb);
+  for (int i = 0; i < 4; ++i) if (h->c.ev_vox[i]) cudaEventDestroy(h->c.ev_vox[i]);
   for (int i = 0; i < 8; ++i) if (h->c.ev[i]) cudaEventDestroy(h->c.ev[i]);
   delete h;
   return 0;
