@@ -206,6 +206,7 @@ struct Params {
   float* pool_mm;
   // row-major output (the y = x W GEMM of the sparse first convolution): out_rm[(b*rows + p) * ld_rm + n], no PF store
   float* out_rm; int ld_rm;
+  int sched;             // work distribution: 0 contiguous range per CTA, 1 interleaved items (see k_conv_tc)
 };
 
 // per 32 channels: butterfly that leaves in lane l the sum over the warp's 32 rows of channel l.
@@ -317,22 +318,45 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   // tail; from here on global memory written by that kernel is consumed
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // Work distribution.  The (n-tile, shape, row-tile) space is flattened (row tile fastest) and cut into gridDim.x
-  // contiguous ranges of equal length (+-1 tile); inside its range a CTA forms work items = up to G consecutive row
-  // tiles sharing the weight slabs (they may belong to two shapes), sized evenly (9 tiles -> 3+3+3, not 4+4+1).  Round 1 dealt fixed
-  // G-tile items round-robin: with 41 tiles per shape (r = 16) that left some CTAs 12 tiles and others 8 -- the kernel
-  // ran at the pace of the 12 (profiles/r02_conv_balanced_ranges.txt).
+  // Work distribution.  The (n-tile, shape, row-tile) space is flattened (row tile fastest) and cut into work items = up to G
+  // consecutive row tiles sharing the weight slabs (they may belong to two shapes, never to two n-tiles).  Every CTA gets
+  // the same number of tiles (+-1).  Round 1 dealt fixed G-tile items round-robin: with 41 tiles per shape (r = 16) that
+  // left some CTAs 12 tiles and others 8 -- the kernel ran at the pace of the 12 (profiles/r02_conv_balanced_ranges.txt).
+  //   sched 0: one contiguous range per CTA, cut into evenly sized items (9 tiles -> 3+3+3, not 4+4+1).  Balanced, but at
+  //            r = 32 the 147 CTAs then stream 147 distant windows of a 268 MB input at once: the 3 x-plane sweeps of a tile
+  //            (9 tiles apart) miss the L2 and the launch reads 975 MB from DRAM instead of 268 (ncu, profiles/).
+  //   sched 1: the same number of items per CTA, m = ceil(ceil(U / grid) / G), but the m * grid items are cut evenly from
+  //            the whole space and dealt round-robin (item j -> CTA j mod grid): at any moment the CTAs work on ~grid
+  //            ADJACENT items (a few shapes), so a tile's x-plane neighbours are in flight in a neighbouring CTA and hit L2.
   const int ntile_total = (P.p_end - P.p_begin + 127) / 128;
   const int n_nt = P.cout_pad / P.NT;
   const long long U = (long long)n_nt * P.B * ntile_total;
   const long long u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
+  const long long per_cta = (U + gridDim.x - 1) / gridDim.x;
+  const int n_items = (int)((per_cta + P.G - 1) / P.G) * (int)gridDim.x;      // sched 1: all items of the launch
   struct Items {
     long long u, u_end; int ntile_total, B, G;
+    int mode, U, I, j, stride;       // sched 1: [u, u_end) is the rest of the current item (an item is cut at an n-tile boundary)
     // next item: n-tile nt, first tile v0 in the n-tile's flat (shape, row tile) space, ntile tiles.  An item may run
     // across a shape boundary -- its tiles share the weight slabs whatever shape they belong to -- but not across n-tiles.
     __device__ __forceinline__ bool next(int& nt, long long& v0, int& ntile) {
-      if (u >= u_end) return false;
       const long long per_nt = (long long)B * ntile_total;
+      if (mode) {
+        while (u >= u_end) {
+          if (j >= I) return false;
+          u = (long long)U * j / I;
+          u_end = (long long)U * (j + 1) / I;
+          j += stride;
+        }
+        nt = (int)(u / per_nt);
+        v0 = u - (long long)nt * per_nt;
+        const long long lim = (long long)(nt + 1) * per_nt;
+        const long long e = u_end < lim ? u_end : lim;
+        ntile = (int)(e - u);          // <= ceil(U / I) <= G
+        u = e;
+        return true;
+      }
+      if (u >= u_end) return false;
       nt = (int)(u / per_nt);
       v0 = u - (long long)nt * per_nt;
       long long run = per_nt - v0;
@@ -343,13 +367,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       return true;
     }
   };
+  const Items items0 = P.sched ? Items{0, 0, ntile_total, P.B, P.G, 1, (int)U, n_items, (int)blockIdx.x, (int)gridDim.x}
+                               : Items{u_begin, u_end, ntile_total, P.B, P.G, 0, 0, 0, 0, 0};
 
   if (warp == 0) {
     // ===================== producer (whole warp; lane kg issues the copy of channel group kg) ====
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0;          // ring positions and phase bits
     const uint32_t bytes = (uint32_t)P.stage_rows * 16u;
     const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-    Items items{u_begin, u_end, ntile_total, P.B, P.G};
+    Items items = items0;
     int nt, ntile;
     long long v0;
     int occ_shape = -1;                                // shape whose occupancy flags s_occ holds
@@ -426,7 +452,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
     const uint32_t a_stage16 = (uint32_t)P.a_stage_bytes >> 4;
     const uint32_t a_ring16 = (smem_u32(sA) >> 4) + (uint32_t)P.halo;
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-    Items items{u_begin, u_end, ntile_total, P.B, P.G};
+    Items items = items0;
     int nt, ntile;
     long long v0;
     for (; items.next(nt, v0, ntile); ++it) {
@@ -482,7 +508,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
     const int hcol = (ew >> 2) * (P.NT / 2);       // first accumulator column of this warp's half
     const int CH = P.NT / 2;
     uint32_t it = 0;
-    Items items{u_begin, u_end, ntile_total, P.B, P.G};
+    Items items = items0;
     int nt, ntile;
     long long v0;
     for (; items.next(nt, v0, ntile); ++it) {
@@ -768,6 +794,7 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   { static int ge = -1; if (ge < 0) { const char* e = getenv("LION_TC_G"); ge = e ? atoi(e) : 0; } if (ge > 0 && ge < G) G = ge; }
   P.G = G;
   P.B = B;
+  { static int sc = -1; if (sc < 0) { const char* e = getenv("LION_CONV_SCHED"); sc = e ? atoi(e) : 1; } P.sched = sc; }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
   const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128 + tc::OCC_SMEM;

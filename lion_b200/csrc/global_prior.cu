@@ -171,18 +171,221 @@ __global__ void k_gp_reduce(const float* __restrict__ part, int nsplit, const fl
   out[(size_t)b * out_stride + o] = v;
 }
 
-// Round-2 experiment (deleted; numbers in profiles/r02_global_prior_persistent_ab.txt): the whole network as ONE
-// cooperative persistent kernel -- 128 CTAs, 16 output rows each over the full K (no split-K, so no cross-CTA
-// reduction), 4-deep cp.async ring, next-phase weight prefetch across a sense-reversing grid barrier.  Correct and
-// bit-reproducible, but 395 us per step against 359 us for the two-kernels-per-layer form below: without split-K every
-// CTA re-reads the whole activation matrix (256 KB per layer, 2x its 128 KB of weights), and the SMs' aggregate ingest
-// (~6.4 TB/s measured here) is then spent three times over -- 307 us even with the 34 grid barriers removed.  Beating
-// the launch-bound form needs split-K with an in-cluster (DSMEM) reduction inside the persistent kernel; not done.
+// ---------------------------------------------------------------------------------------------------------------
+// The whole network as ONE persistent kernel (round 2, second design; the first -- no split-K, every CTA re-reading
+// the full activation matrix -- lost to the two-kernels-per-Linear form: profiles/r02_global_prior_persistent_ab.txt).
+//   * grid = 16 thread-block clusters x 8 CTAs, one CTA per SM.  Cluster c owns output rows [128c, 128c+128) of every
+//     Linear; its 8 CTAs split K eight ways (the SAME 256-wide slices and the same summation order as k_gp_partial /
+//     k_gp_reduce for K = 2048), so each CTA reads only its [32 shapes x K/8] slice of the activations.
+//   * split-K reduction through distributed shared memory: every CTA leaves its [32 x 128] partial tile in its own
+//     shared memory, one barrier.cluster, then CTA r sums columns [16r, 16r+16) over the 8 peers with ld.shared::cluster
+//     (fixed order -> bit-reproducible), applies bias / ReLU / sigmoid / SE gate / residual and stores the final values.
+//   * weights never wait for activations: warp w streams its own 16 rows of the CTA's weight tile with cp.async.bulk
+//     into two private ring slots ([16 rows x <= 128 columns] each) and refills a slot with the NEXT layer's rows the
+//     moment it has consumed it, so the HBM stream (309 MB per evaluation) runs ahead across the grid barriers.
+//   * one grid barrier per Linear (monotonic counter, zeroed by k_gp_posemb): 36 instead of 73 kernel boundaries.
+// All 128 CTAs must be co-resident (checked once with cudaOccupancyMaxActiveClusters; otherwise the two-kernel form
+// runs).  LION_GP_PERSIST=0 selects the two-kernel form (A/B).
+namespace gpp {
+constexpr int CL = 8;                 // CTAs per cluster = K splits
+constexpr int NCL = 16;               // clusters = 128-row output tiles
+constexpr int TO = 128;               // output rows per cluster
+constexpr int CW = 128;               // columns per weight stage
+constexpr int WP = CW + 4;            // stage row pitch in floats (bank = 4 * row + column: conflict-free fragments)
+constexpr int STAGE_FLOATS = 16 * WP; // one stage = one warp's 16 rows
+constexpr int NSLOT = 16;             // two per warp
+constexpr int KC_MAX = 512;           // K / 8 <= 512 (K <= 4096)
+constexpr int XP = KC_MAX + 4;
+constexpr int PP = TO + 4;
+constexpr int THREADS = 256;
+constexpr int MAXL = 38;
+constexpr size_t SMEM = (size_t)(NSLOT * STAGE_FLOATS + 32 * XP + 32 * PP) * sizeof(float) + NSLOT * 8;
+
+struct Layer {
+  const float* w; const float* bias; const float* x; const float* add; float* out; float* out2; const float* mul; const float* res;
+  int K, O, xs, as, os, os2, ms, rs, act, pad;
+};
+struct Prog { int nl, B; unsigned* counter; Layer l[MAXL]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded waits: a protocol bug traps (CUDA error) instead of hanging the GPU
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > 2000000000LL) __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// every CTA of the grid has finished the previous layer (its global stores included)
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    long long t0 = clock64();
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      if (clock64() - t0 > 2000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+}
+
+struct Cur { int l, cs; };     // (layer, column stage) of a cluster's weight stream
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) k_gp_persist(const __grid_constant__ Prog P) {
+  extern __shared__ __align__(128) float gsm[];
+  float* s_ring = gsm;                                   // [NSLOT][16][WP]
+  float* s_x = s_ring + NSLOT * STAGE_FLOATS;            // [32][XP]  activations slice, TF32-rounded
+  float* s_part = s_x + 32 * XP;                         // [32][PP]  this CTA's partial sums [shape][output]
+  uint64_t* s_bar = (uint64_t*)(s_part + 32 * PP);       // [NSLOT]   "stage landed"
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int cr = blockIdx.x % CL, cid = blockIdx.x / CL;
+  const int B = P.B;
+  const uint32_t bar0 = smem_u32(s_bar), ring0 = smem_u32(s_ring);
+  if (tid == 0) {
+    for (int i = 0; i < NSLOT; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * i));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto active = [&](int l) { return cid * TO < P.l[l].O; };
+  auto ncs_of = [&](int l) { return (P.l[l].K / CL + CW - 1) / CW; };
+  // warp-collective: start the copy of stage `c` (this warp's 16 rows) as fetch number fi of this warp
+  auto fetch = [&](Cur c, int fi) {
+    const Layer& L = P.l[c.l];
+    const int kc = L.K / CL, cw = min(CW, kc - c.cs * CW);
+    const int slot = (fi & 1) * 8 + w;
+    const uint32_t bar = bar0 + 8 * slot;
+    const uint32_t bytes = (uint32_t)cw * 4u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // this slot was read through the generic proxy
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 16u) : "memory");
+    __syncwarp();
+    if (lane < 16) {
+      const float* src = L.w + (size_t)(cid * TO + w * 16 + lane) * L.K + cr * kc + c.cs * CW;
+      const uint32_t dst = ring0 + (uint32_t)(slot * STAGE_FLOATS + lane * WP) * 4u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    }
+  };
+  auto advance = [&](Cur& c) {
+    if (c.l >= P.nl) return;
+    if (++c.cs >= ncs_of(c.l)) {
+      c.cs = 0;
+      do { ++c.l; } while (c.l < P.nl && !active(c.l));
+    }
+  };
+  Cur fc{0, 0};
+  while (fc.l < P.nl && !active(fc.l)) ++fc.l;
+  int fi = 0, ci = 0;
+  for (; fi < 2 && fc.l < P.nl; ++fi) { fetch(fc, fi); advance(fc); }
+
+  const int g8 = lane >> 2, t4 = lane & 3;
+  for (int l = 0; l < P.nl; ++l) {
+    const Layer& L = P.l[l];
+    if (l > 0) grid_barrier(P.counter, (unsigned)l * gridDim.x);
+    if (!active(l)) continue;                            // (the whole cluster skips together)
+    const int kc = L.K / CL, k0 = cr * kc, kc4 = kc >> 2;
+    // activations slice [32][kc] (+ add), rounded to TF32; .cg loads: other CTAs wrote these buffers in this launch
+    for (int i = tid; i < 32 * kc4; i += THREADS) {
+      const int b = i / kc4, k4 = i - b * kc4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < B) {
+        v = __ldcg(reinterpret_cast<const float4*>(L.x + (size_t)b * L.xs + k0) + k4);
+        if (L.add) {
+          const float4 a = __ldcg(reinterpret_cast<const float4*>(L.add + (size_t)b * L.as + k0) + k4);
+          v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+      }
+      *reinterpret_cast<float4*>(s_x + b * XP + k4 * 4) =
+          make_float4(__uint_as_float(tf32_bits(v.x)), __uint_as_float(tf32_bits(v.y)), __uint_as_float(tf32_bits(v.z)),
+                      __uint_as_float(tf32_bits(v.w)));
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
+    const int ncs = (kc + CW - 1) / CW;
+    for (int cs = 0; cs < ncs; ++cs, ++ci) {
+      const int cw = min(CW, kc - cs * CW);
+      const int slot = (ci & 1) * 8 + w;
+      mbar_wait(bar0 + 8 * slot, (uint32_t)(ci >> 1) & 1u);
+      const float* wa = s_ring + slot * STAGE_FLOATS + g8 * WP + t4;     // rows g8 / g8+8 of this warp's 16 outputs
+      const float* xb = s_x + g8 * XP + cs * CW + t4;                    // shape g8 of each 8-shape tile
+#pragma unroll 4
+      for (int k = 0; k < cw; k += 8) {
+        const uint32_t a0 = __float_as_uint(wa[k]), a1 = __float_as_uint(wa[8 * WP + k]);
+        const uint32_t a2 = __float_as_uint(wa[k + 4]), a3 = __float_as_uint(wa[8 * WP + k + 4]);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const uint32_t b0 = __float_as_uint(xb[n * 8 * XP + k]), b1 = __float_as_uint(xb[n * 8 * XP + k + 4]);
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+      }
+      __syncwarp();
+      if (fc.l < P.nl) { fetch(fc, fi); advance(fc); ++fi; }             // refill the slot just consumed
+    }
+    // C fragment: c0,c1 -> (row g8, shapes 2*t4, 2*t4+1); c2,c3 -> (row g8+8, same shapes)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        s_part[(n * 8 + 2 * t4 + (i & 1)) * PP + w * 16 + g8 + (i >= 2 ? 8 : 0)] = acc[n][i];
+    cluster_sync_all();
+    {
+      // CTA cr: columns [16 cr, 16 cr + 16) of the cluster's tile; thread -> (shape b, two adjacent outputs)
+      const int b = tid >> 3, oc = cr * 16 + (tid & 7) * 2;
+      const uint32_t local = smem_u32(s_part + b * PP + oc);
+      float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+      for (int p = 0; p < CL; ++p) {
+        uint32_t remote;
+        float x0, x1;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(p));
+        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(remote) : "memory");
+        v0 += x0; v1 += x1;
+      }
+      const int o = cid * TO + oc;
+      if (b < B) {
+        if (L.bias) { v0 += __ldg(L.bias + o); v1 += __ldg(L.bias + o + 1); }
+        if (L.act == 1) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
+        else if (L.act == 2) { v0 = 1.0f / (1.0f + expf(-v0)); v1 = 1.0f / (1.0f + expf(-v1)); }
+        if (L.mul) { const float2 m = __ldcg(reinterpret_cast<const float2*>(L.mul + (size_t)b * L.ms + o)); v0 *= m.x; v1 *= m.y; }
+        if (L.res) { const float2 r = __ldcg(reinterpret_cast<const float2*>(L.res + (size_t)b * L.rs + o)); v0 += r.x; v1 += r.y; }
+        *reinterpret_cast<float2*>(L.out + (size_t)b * L.os + o) = make_float2(v0, v1);
+        if (L.out2) *reinterpret_cast<float2*>(L.out2 + (size_t)b * L.os2 + o) = make_float2(v0, v1);
+      }
+    }
+    // (the next layer's grid barrier also orders these s_part reads before anyone overwrites its tile)
+  }
+  cluster_sync_all();      // no CTA leaves while a peer may still read its shared memory
+}
+}  // namespace gpp
+
 // PositionalEmbedding (models/utils.py:16-31): fp32 frequencies exp(i * -log(1e4)/(half-1))
 __global__ void k_gp_posemb(const float* __restrict__ t, const float* __restrict__ freqs, float* __restrict__ out,
-                            int half, float scale) {
+                            int half, float scale, unsigned* __restrict__ zero_me) {
   pdl_prologue();
   int b = blockIdx.x, i = threadIdx.x;
+  if (zero_me && b == 0 && i == 0) *zero_me = 0u;      // grid-barrier counter of the persistent kernel that follows
   if (i >= half) return;
   float e = __fmul_rn(__fmul_rn(t[b], scale), freqs[i]);
   out[(size_t)b * 2 * half + i] = sinf(e);
@@ -264,7 +467,7 @@ static int global_prior_forward_layers(Model* m, const float* x, const float* t,
   float* a = c->alloc_n<float>((size_t)B * nf);
   float* bb = c->alloc_n<float>((size_t)B * nf);
   float* s0 = c->alloc_n<float>((size_t)B * nf / 8);
-  LION_LAUNCH(c, k_gp_posemb, B, 64, 0, t, g->d_freqs, pe, g->emb / 2, g->scale);
+  LION_LAUNCH(c, k_gp_posemb, B, 64, 0, t, g->d_freqs, pe, g->emb / 2, g->scale, (unsigned*)nullptr);
   // temb_layer: two 1x1 convs, no nonlinearity in between (resnet.py:181-184)
   LION_TRY(gp_linear(c, g->t0, pe, g->emb, nullptr, 0, t0, g->emb * 4, nullptr, 0, nullptr, 0, B, 0));
   if (g->clip) LION_TRY(memset_async(c, tadd, 0, sizeof(float) * B * tw));
@@ -291,6 +494,89 @@ static int global_prior_forward_layers(Model* m, const float* x, const float* t,
   return check_launch(c, "global_prior_forward");
 }
 
+// The persistent form is usable when every Linear fits the kernel's tiling and all 128 CTAs can be co-resident.
+static bool gp_persist_usable(const GlobalPriorBlk* g) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("LION_GP_PERSIST"); on = e ? atoi(e) : 1; }
+  if (!on) return false;
+  auto ok = [](const GPLin& l) {
+    return l.K % (gpp::CL * 8) == 0 && l.K / gpp::CL <= gpp::KC_MAX && l.O % gpp::TO == 0 && l.O <= gpp::NCL * gpp::TO;
+  };
+  bool all = ok(g->t0) && ok(g->t1) && ok(g->in) && ok(g->outl) && (!g->clip || ok(g->cmap));
+  for (auto& c : g->cells) all = all && ok(c.c1) && ok(c.c2) && ok(c.se0) && ok(c.se2);
+  if (!all || 4 + 4 * (int)g->cells.size() + (g->clip ? 1 : 0) > gpp::MAXL) return false;
+  // co-residency of the 16 clusters, per device (a grid barrier deadlocks otherwise)
+  static int resident[64];
+  static bool asked[64];
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return false;
+  if (!asked[d]) {
+    asked[d] = true;
+    resident[d] = 0;
+    if (cudaFuncSetAttribute(gpp::k_gp_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gpp::SMEM) == cudaSuccess) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(gpp::NCL * gpp::CL); cfg.blockDim = dim3(gpp::THREADS); cfg.dynamicSmemBytes = gpp::SMEM;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = gpp::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gpp::k_gp_persist, &cfg) == cudaSuccess) resident[d] = n;
+    }
+    (void)cudaGetLastError();
+    if (resident[d] < gpp::NCL)
+      fprintf(stderr, "lion_b200: global prior: %d of %d clusters co-resident on device %d -> two-kernel form\n", resident[d], gpp::NCL, d);
+  }
+  return resident[d] >= gpp::NCL;
+}
+
+// one chunk of <= 32 shapes through the persistent kernel (k_gp_posemb zeroes its barrier counter)
+static int global_prior_forward_persist(Model* m, const float* x, const float* t, const float* clip, float* out, int B) {
+  GlobalPriorBlk* g = m->gp;
+  Ctx* c = m->ctx;
+  const int nf = g->nf, tw = g->clip ? 2 * nf : nf;
+  float* pe = c->alloc_n<float>((size_t)B * g->emb);
+  float* t0 = c->alloc_n<float>((size_t)B * g->emb * 4);
+  float* tadd = c->alloc_n<float>((size_t)B * tw);     // [temb | 0]: what is added to the cell input
+  float* cat = c->alloc_n<float>((size_t)B * tw);      // [h | clip-mapped] (clip variant only)
+  float* h = c->alloc_n<float>((size_t)B * nf);
+  float* h2 = c->alloc_n<float>((size_t)B * nf);
+  float* a = c->alloc_n<float>((size_t)B * nf);
+  float* bb = c->alloc_n<float>((size_t)B * nf);
+  float* s0 = c->alloc_n<float>((size_t)B * nf / 8);
+  unsigned* counter = c->alloc_n<unsigned>(1);
+  LION_LAUNCH(c, k_gp_posemb, B, 64, 0, t, g->d_freqs, pe, g->emb / 2, g->scale, counter);
+  if (g->clip) LION_TRY(memset_async(c, tadd, 0, sizeof(float) * B * tw));
+  gpp::Prog P;
+  memset(&P, 0, sizeof(P));
+  P.B = B; P.counter = counter;
+  auto add = [&](const GPLin& l, const float* xin, int xs, const float* ad, int as, float* o, int os, float* o2, int os2,
+                 const float* mul, int ms, const float* res, int rs, int act) {
+    gpp::Layer& L = P.l[P.nl++];
+    L.w = l.w; L.bias = l.b; L.x = xin; L.add = ad; L.out = o; L.out2 = o2; L.mul = mul; L.res = res;
+    L.K = l.K; L.O = l.O; L.xs = xs; L.as = as; L.os = os; L.os2 = os2; L.ms = ms; L.rs = rs; L.act = act;
+  };
+  // same layer sequence as global_prior_forward_layers; the clip variant's copy of h into [h | clip] is a second store
+  add(g->t0, pe, g->emb, nullptr, 0, t0, g->emb * 4, nullptr, 0, nullptr, 0, nullptr, 0, 0);
+  add(g->t1, t0, g->emb * 4, nullptr, 0, tadd, tw, nullptr, 0, nullptr, 0, nullptr, 0, 0);
+  if (g->clip) add(g->cmap, clip, g->clip_dim, nullptr, 0, cat + nf, tw, nullptr, 0, nullptr, 0, nullptr, 0, 0);
+  add(g->in, x, g->D, nullptr, 0, h, nf, g->clip ? cat : nullptr, tw, nullptr, 0, nullptr, 0, 0);
+  for (auto& cell : g->cells) {
+    if (g->clip) add(cell.c1, cat, tw, tadd, tw, a, nf, nullptr, 0, nullptr, 0, nullptr, 0, 1);
+    else add(cell.c1, h, nf, tadd, tw, a, nf, nullptr, 0, nullptr, 0, nullptr, 0, 1);
+    add(cell.c2, a, nf, nullptr, 0, bb, nf, nullptr, 0, nullptr, 0, nullptr, 0, 1);
+    add(cell.se0, bb, nf, nullptr, 0, s0, nf / 8, nullptr, 0, nullptr, 0, nullptr, 0, 1);
+    add(cell.se2, s0, nf / 8, nullptr, 0, h2, nf, g->clip ? cat : nullptr, tw, bb, nf, h, nf, 2);   // sigmoid(.) * bb + h
+    float* tmp = h; h = h2; h2 = tmp;
+  }
+  add(g->outl, h, nf, nullptr, 0, out, g->D, nullptr, 0, nullptr, 0, nullptr, 0, 0);
+  if (!c->dry) {
+    gpp::k_gp_persist<<<gpp::NCL * gpp::CL, gpp::THREADS, gpp::SMEM, c->stream>>>(P);
+    c->launches++;
+  }
+  return check_launch(c, "global_prior_forward (persistent)");
+}
+
 int global_prior_forward(Model* m, const float* x, const float* t, const float* clip, float* out, int B) {
   GlobalPriorBlk* g = m->gp;
   Ctx* c = m->ctx;
@@ -302,7 +588,8 @@ int global_prior_forward(Model* m, const float* x, const float* t, const float* 
     const float* xc = x + (size_t)b0 * g->D;
     const float* cc = clip ? clip + (size_t)b0 * g->clip_dim : nullptr;
     float* oc = out + (size_t)b0 * g->D;
-    LION_TRY(global_prior_forward_layers(m, xc, t + b0, cc, oc, nb));
+    if (gp_persist_usable(g)) LION_TRY(global_prior_forward_persist(m, xc, t + b0, cc, oc, nb));
+    else LION_TRY(global_prior_forward_layers(m, xc, t + b0, cc, oc, nb));
     c->release(mk);
   }
   return 0;

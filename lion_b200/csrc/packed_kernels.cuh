@@ -615,10 +615,15 @@ __global__ void k_act_grid(const float4* __restrict__ in, float4* __restrict__ o
   const int p0 = blockIdx.x * (blockDim.x * ACT_U) + threadIdx.x;
   float4 v[ACT_U];
   bool interior[ACT_U];
+  // p -> (x, y, z) by multiply-high with m = ceil(2^32 / rp) (exact while p * rp < 2^32): the four positions of a thread
+  // cost one integer division instead of sixteen -- at 1 float4 per clock per SM this pass is instruction-bound, not
+  // HBM-bound, once the index arithmetic and an IEEE division per Swish are in the loop
+  const unsigned rp_m = 0xffffffffu / (unsigned)rp + 1u;
 #pragma unroll
   for (int u = 0; u < ACT_U; ++u) {
     int p = p0 + u * blockDim.x;
-    int z = p % rp, y = (p / rp) % rp, x = p / (rp * rp);
+    const int q = (int)__umulhi((unsigned)p, rp_m), x = (int)__umulhi((unsigned)q, rp_m);
+    const int z = p - q * rp, y = q - x * rp;
     interior[u] = p < P && z >= 1 && z <= rp - 2 && y >= 1 && y <= rp - 2 && x >= 1 && x <= rp - 2;
     v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (interior[u]) v[u] = __ldcs(src + p);          // read once: streaming
