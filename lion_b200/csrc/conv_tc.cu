@@ -325,34 +325,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
   //   sched 0: one contiguous range per CTA, cut into evenly sized items (9 tiles -> 3+3+3, not 4+4+1).  Balanced, but at
   //            r = 32 the 147 CTAs then stream 147 distant windows of a 268 MB input at once: the 3 x-plane sweeps of a tile
   //            (9 tiles apart) miss the L2 and the launch reads 975 MB from DRAM instead of 268 (ncu, profiles/).
-  //   sched 1: the same number of items per CTA, m = ceil(ceil(U / grid) / G), but the m * grid items are cut evenly from
-  //            the whole space and dealt round-robin (item j -> CTA j mod grid): at any moment the CTAs work on ~grid
-  //            ADJACENT items (a few shapes), so a tile's x-plane neighbours are in flight in a neighbouring CTA and hit L2.
+  //   sched 1: the same tiles per CTA T_i (= the contiguous range's size) and the same number of items m = ceil(max T / G), but
+  //            dealt in m ROUNDS: round k is one contiguous stretch of the tile space, cut into one item per CTA (CTA i's item
+  //            has floor(T_i (k+1) / m) - floor(T_i k / m) tiles).  At any moment the CTAs work on ~grid ADJACENT items
+  //            (a few shapes), so a tile's x-plane neighbours are in flight in a neighbouring CTA and hit the L2.
+  //            With T_i in {q, q+1} every offset has a closed form: A_k = floor(q k / m), B_k = floor((q+1) k / m),
+  //            c_i = CTAs before i that own q+1 tiles;  start(i, k) = n_q A_k + n_p B_k + (i - c_i)(A_k+1 - A_k) + c_i (B_k+1 - B_k).
   const int ntile_total = (P.p_end - P.p_begin + 127) / 128;
   const int n_nt = P.cout_pad / P.NT;
   const long long U = (long long)n_nt * P.B * ntile_total;
   const long long u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
-  const long long per_cta = (U + gridDim.x - 1) / gridDim.x;
-  const int n_items = (int)((per_cta + P.G - 1) / P.G) * (int)gridDim.x;      // sched 1: all items of the launch
   struct Items {
     long long u, u_end; int ntile_total, B, G;
-    int mode, U, I, j, stride;       // sched 1: [u, u_end) is the rest of the current item (an item is cut at an n-tile boundary)
+    int mode, m, q, n_p, n_q, c_i, i, big, k;   // sched 1: [u, u_end) is the rest of the current item (cut at n-tile boundaries)
     // next item: n-tile nt, first tile v0 in the n-tile's flat (shape, row tile) space, ntile tiles.  An item may run
     // across a shape boundary -- its tiles share the weight slabs whatever shape they belong to -- but not across n-tiles.
     __device__ __forceinline__ bool next(int& nt, long long& v0, int& ntile) {
       const long long per_nt = (long long)B * ntile_total;
       if (mode) {
         while (u >= u_end) {
-          if (j >= I) return false;
-          u = (long long)U * j / I;
-          u_end = (long long)U * (j + 1) / I;
-          j += stride;
+          if (k >= m) return false;
+          const int a0 = q * k / m, a1 = q * (k + 1) / m, b0 = (q + 1) * k / m, b1 = (q + 1) * (k + 1) / m;
+          u = (long long)n_q * a0 + (long long)n_p * b0 + (long long)(i - c_i) * (a1 - a0) + (long long)c_i * (b1 - b0);
+          u_end = u + (big ? b1 - b0 : a1 - a0);
+          ++k;
         }
         nt = (int)(u / per_nt);
         v0 = u - (long long)nt * per_nt;
         const long long lim = (long long)(nt + 1) * per_nt;
         const long long e = u_end < lim ? u_end : lim;
-        ntile = (int)(e - u);          // <= ceil(U / I) <= G
+        ntile = (int)(e - u);          // <= ceil((q + 1) / m) <= G
         u = e;
         return true;
       }
@@ -361,14 +363,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(Params P) {
       v0 = u - (long long)nt * per_nt;
       long long run = per_nt - v0;
       if (u_end - u < run) run = u_end - u;
-      const long long k = (run + G - 1) / G;
-      ntile = (int)((run + k - 1) / k);
+      const long long k2 = (run + G - 1) / G;
+      ntile = (int)((run + k2 - 1) / k2);
       u += ntile;
       return true;
     }
   };
-  const Items items0 = P.sched ? Items{0, 0, ntile_total, P.B, P.G, 1, (int)U, n_items, (int)blockIdx.x, (int)gridDim.x}
-                               : Items{u_begin, u_end, ntile_total, P.B, P.G, 0, 0, 0, 0, 0};
+  Items items0{u_begin, u_end, ntile_total, P.B, P.G, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (P.sched) {
+    const int grid = (int)gridDim.x, q = (int)(U / grid), n_p = (int)(U - (long long)q * grid);
+    const int tmax = q + (n_p ? 1 : 0);
+    items0.mode = 1; items0.u = 0; items0.u_end = 0;
+    items0.m = (tmax + P.G - 1) / P.G; items0.q = q; items0.n_p = n_p; items0.n_q = grid - n_p;
+    items0.i = (int)blockIdx.x; items0.c_i = (int)(u_begin - (long long)q * blockIdx.x);
+    items0.big = (int)(u_end - u_begin) > q; items0.k = 0;
+  }
 
   if (warp == 0) {
     // ===================== producer (whole warp; lane kg issues the copy of channel group kg) ====
@@ -794,7 +803,13 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   { static int ge = -1; if (ge < 0) { const char* e = getenv("LION_TC_G"); ge = e ? atoi(e) : 0; } if (ge > 0 && ge < G) G = ge; }
   P.G = G;
   P.B = B;
-  { static int sc = -1; if (sc < 0) { const char* e = getenv("LION_CONV_SCHED"); sc = e ? atoi(e) : 1; } P.sched = sc; }
+  // Round-based items (sched 1) where the input cannot stay in the L2 between a tile's three x-plane sweeps (> 96 MB: the
+  // 32-/64-channel grids at r = 32, B = 32): DRAM reads of the 64 -> 64 launch drop from 975 MB to 325 MB at equal or
+  // better time; the r = 16 / r = 8 launches are L2-resident either way and measured 5-14 % slower with it
+  // (gpurun call 32, profiles/r02_conv_sched_ab.txt), so they keep one contiguous range per CTA.  LION_CONV_SCHED=0|1 forces.
+  { static int sc = -2; if (sc == -2) { const char* e = getenv("LION_CONV_SCHED"); sc = e ? atoi(e) : -1; }
+    const double in_bytes = (double)B * Gin * geo.rows * 16.0;
+    P.sched = sc >= 0 ? sc : (w.ntaps == 27 && in_bytes > 96e6 ? 1 : 0); }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
   const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128 + tc::OCC_SMEM;

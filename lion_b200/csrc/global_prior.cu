@@ -174,32 +174,34 @@ __global__ void k_gp_reduce(const float* __restrict__ part, int nsplit, const fl
 // ---------------------------------------------------------------------------------------------------------------
 // The whole network as ONE persistent kernel (round 2, second design; the first -- no split-K, every CTA re-reading
 // the full activation matrix -- lost to the two-kernels-per-Linear form: profiles/r02_global_prior_persistent_ab.txt).
-//   * grid = 16 thread-block clusters x 8 CTAs, one CTA per SM.  Cluster c owns output rows [128c, 128c+128) of every
-//     Linear; its 8 CTAs split K eight ways (the SAME 256-wide slices and the same summation order as k_gp_partial /
-//     k_gp_reduce for K = 2048), so each CTA reads only its [32 shapes x K/8] slice of the activations.
-//   * split-K reduction through distributed shared memory: every CTA leaves its [32 x 128] partial tile in its own
-//     shared memory, one barrier.cluster, then CTA r sums columns [16r, 16r+16) over the 8 peers with ld.shared::cluster
-//     (fixed order -> bit-reproducible), applies bias / ReLU / sigmoid / SE gate / residual and stores the final values.
-//   * weights never wait for activations: warp w streams its own 16 rows of the CTA's weight tile with cp.async.bulk
-//     into two private ring slots ([16 rows x <= 128 columns] each) and refills a slot with the NEXT layer's rows the
-//     moment it has consumed it, so the HBM stream (309 MB per evaluation) runs ahead across the grid barriers.
+//   * grid = 128 CTAs in thread-block clusters of CL (8, 4 or 2; the largest size whose clusters are all co-resident:
+//     a B200 hosts only 15 clusters of 8 CTAs with this much shared memory, so CL = 4 is what runs there).  A cluster
+//     owns 16 * CL output rows of every Linear.  K is always split 8 ways -- the SAME 256-wide slices and summation
+//     order as k_gp_partial / k_gp_reduce for K = 2048 --: CL ways across the cluster's CTAs and HS = 8 / CL ways across
+//     the warp groups of a CTA, so each CTA reads only its [32 shapes x K / CL] slice of the activations.
+//   * warp w = (row group w % CL, k-part w / CL): 16 rows x K / 8 columns of the weight matrix, streamed with
+//     cp.async.bulk into two private ring slots ([16 rows x <= 128 columns] each); a slot is refilled with the warp's
+//     NEXT stage -- usually the next layer's rows -- the moment it has been consumed, so the HBM stream (309 MB per
+//     evaluation) runs ahead across the grid barriers: weights never wait for activations.
+//   * split-K reduction through distributed shared memory: every CTA leaves HS partial tiles [32 x 16 CL] in its own
+//     shared memory, one barrier.cluster, then CTA r sums columns [16r, 16r+16) over the 8 partials with
+//     ld.shared::cluster (fixed order -> bit-reproducible), applies bias / ReLU / sigmoid / SE gate / residual and
+//     stores the final values.
 //   * one grid barrier per Linear (monotonic counter, zeroed by k_gp_posemb): 36 instead of 73 kernel boundaries.
-// All 128 CTAs must be co-resident (checked once with cudaOccupancyMaxActiveClusters; otherwise the two-kernel form
-// runs).  LION_GP_PERSIST=0 selects the two-kernel form (A/B).
+// All 128 CTAs must be co-resident (checked once per device with cudaOccupancyMaxActiveClusters; otherwise the
+// two-kernel form runs).  LION_GP_PERSIST=0 selects the two-kernel form, LION_GP_PERSIST=8|4|2 pins the cluster size.
 namespace gpp {
-constexpr int CL = 8;                 // CTAs per cluster = K splits
-constexpr int NCL = 16;               // clusters = 128-row output tiles
-constexpr int TO = 128;               // output rows per cluster
+constexpr int NCTA = 128;             // 16 output rows x 8 K slices per CTA-warp; 8 warps per CTA
 constexpr int CW = 128;               // columns per weight stage
 constexpr int WP = CW + 4;            // stage row pitch in floats (bank = 4 * row + column: conflict-free fragments)
 constexpr int STAGE_FLOATS = 16 * WP; // one stage = one warp's 16 rows
 constexpr int NSLOT = 16;             // two per warp
-constexpr int KC_MAX = 512;           // K / 8 <= 512 (K <= 4096)
-constexpr int XP = KC_MAX + 4;
-constexpr int PP = TO + 4;
+constexpr int XW = 512;               // activation columns staged per pass (all k-parts of the CTA together)
+constexpr int XP = XW + 4;
 constexpr int THREADS = 256;
 constexpr int MAXL = 38;
-constexpr size_t SMEM = (size_t)(NSLOT * STAGE_FLOATS + 32 * XP + 32 * PP) * sizeof(float) + NSLOT * 8;
+constexpr int PART_FLOATS = 4 * 32 * (32 + 4);   // HS tiles of [32][16 CL + 4] floats: 4224 / 4352 / 4608 for CL = 8 / 4 / 2
+constexpr size_t SMEM = (size_t)(NSLOT * STAGE_FLOATS + 32 * XP + PART_FLOATS) * sizeof(float) + NSLOT * 8;
 
 struct Layer {
   const float* w; const float* bias; const float* x; const float* add; float* out; float* out2; const float* mul; const float* res;
@@ -245,16 +247,23 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned target) {
   __syncthreads();
 }
 
-struct Cur { int l, cs; };     // (layer, column stage) of a cluster's weight stream
+struct Cur { int l, cs; };     // (layer, column stage) of a warp's weight stream
 
+template <int CL>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) k_gp_persist(const __grid_constant__ Prog P) {
+  constexpr int HS = 8 / CL;            // k-parts per CTA
+  constexpr int TO = 16 * CL;           // output rows per cluster
+  constexpr int PP = TO + 4;            // partial-tile row pitch
+  constexpr int PW = XW / HS;           // activation columns per k-part and pass
   extern __shared__ __align__(128) float gsm[];
   float* s_ring = gsm;                                   // [NSLOT][16][WP]
-  float* s_x = s_ring + NSLOT * STAGE_FLOATS;            // [32][XP]  activations slice, TF32-rounded
-  float* s_part = s_x + 32 * XP;                         // [32][PP]  this CTA's partial sums [shape][output]
-  uint64_t* s_bar = (uint64_t*)(s_part + 32 * PP);       // [NSLOT]   "stage landed"
+  float* s_x = s_ring + NSLOT * STAGE_FLOATS;            // [32][XP]  activations slice of one pass: HS k-parts x PW columns, TF32-rounded
+  float* s_part = s_x + 32 * XP;                         // [HS][32][PP]  this CTA's partial sums [k-part][shape][output]
+  uint64_t* s_bar = (uint64_t*)(s_part + PART_FLOATS);   // [NSLOT]   "stage landed"
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int rw = w % CL, h = w / CL;                     // this warp's row group and k-part
   const int cr = blockIdx.x % CL, cid = blockIdx.x / CL;
+  const int ks = cr * HS + h;                            // this warp's K slice (0..7)
   const int B = P.B;
   const uint32_t bar0 = smem_u32(s_bar), ring0 = smem_u32(s_ring);
   if (tid == 0) {
@@ -264,11 +273,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) k_gp_pe
   __syncthreads();
 
   auto active = [&](int l) { return cid * TO < P.l[l].O; };
-  auto ncs_of = [&](int l) { return (P.l[l].K / CL + CW - 1) / CW; };
-  // warp-collective: start the copy of stage `c` (this warp's 16 rows) as fetch number fi of this warp
+  auto ncs_of = [&](int l) { return (P.l[l].K / 8 + CW - 1) / CW; };
+  // warp-collective: start the copy of stage `c` (this warp's 16 rows x <= 128 columns) as fetch number fi of this warp
   auto fetch = [&](Cur c, int fi) {
     const Layer& L = P.l[c.l];
-    const int kc = L.K / CL, cw = min(CW, kc - c.cs * CW);
+    const int kw = L.K / 8, cw = min(CW, kw - c.cs * CW);
     const int slot = (fi & 1) * 8 + w;
     const uint32_t bar = bar0 + 8 * slot;
     const uint32_t bytes = (uint32_t)cw * 4u;
@@ -276,7 +285,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) k_gp_pe
     if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * 16u) : "memory");
     __syncwarp();
     if (lane < 16) {
-      const float* src = L.w + (size_t)(cid * TO + w * 16 + lane) * L.K + cr * kc + c.cs * CW;
+      const float* src = L.w + (size_t)(cid * TO + rw * 16 + lane) * L.K + ks * kw + c.cs * CW;
       const uint32_t dst = ring0 + (uint32_t)(slot * STAGE_FLOATS + lane * WP) * 4u;
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                    ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -299,69 +308,80 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1) k_gp_pe
     const Layer& L = P.l[l];
     if (l > 0) grid_barrier(P.counter, (unsigned)l * gridDim.x);
     if (!active(l)) continue;                            // (the whole cluster skips together)
-    const int kc = L.K / CL, k0 = cr * kc, kc4 = kc >> 2;
-    // activations slice [32][kc] (+ add), rounded to TF32; .cg loads: other CTAs wrote these buffers in this launch
-    for (int i = tid; i < 32 * kc4; i += THREADS) {
-      const int b = i / kc4, k4 = i - b * kc4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < B) {
-        v = __ldcg(reinterpret_cast<const float4*>(L.x + (size_t)b * L.xs + k0) + k4);
-        if (L.add) {
-          const float4 a = __ldcg(reinterpret_cast<const float4*>(L.add + (size_t)b * L.as + k0) + k4);
-          v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-        }
-      }
-      *reinterpret_cast<float4*>(s_x + b * XP + k4 * 4) =
-          make_float4(__uint_as_float(tf32_bits(v.x)), __uint_as_float(tf32_bits(v.y)), __uint_as_float(tf32_bits(v.z)),
-                      __uint_as_float(tf32_bits(v.w)));
-    }
-    __syncthreads();
+    const int kw = L.K / 8;                              // columns per K slice
     float acc[4][4];
 #pragma unroll
     for (int n = 0; n < 4; ++n)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
-    const int ncs = (kc + CW - 1) / CW;
-    for (int cs = 0; cs < ncs; ++cs, ++ci) {
-      const int cw = min(CW, kc - cs * CW);
-      const int slot = (ci & 1) * 8 + w;
-      mbar_wait(bar0 + 8 * slot, (uint32_t)(ci >> 1) & 1u);
-      const float* wa = s_ring + slot * STAGE_FLOATS + g8 * WP + t4;     // rows g8 / g8+8 of this warp's 16 outputs
-      const float* xb = s_x + g8 * XP + cs * CW + t4;                    // shape g8 of each 8-shape tile
-#pragma unroll 4
-      for (int k = 0; k < cw; k += 8) {
-        const uint32_t a0 = __float_as_uint(wa[k]), a1 = __float_as_uint(wa[8 * WP + k]);
-        const uint32_t a2 = __float_as_uint(wa[k + 4]), a3 = __float_as_uint(wa[8 * WP + k + 4]);
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          const uint32_t b0 = __float_as_uint(xb[n * 8 * XP + k]), b1 = __float_as_uint(xb[n * 8 * XP + k + 4]);
-          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                       : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])
-                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    for (int p0 = 0; p0 < kw; p0 += PW) {                // passes: PW columns of every k-part at a time
+      const int pw = min(PW, kw - p0), pw4 = pw >> 2;
+      if (p0 > 0) __syncthreads();                       // the previous pass has been consumed
+      // activations [32][HS][pw] (+ add), rounded to TF32; .cg loads: other CTAs wrote these buffers in this launch
+      for (int i = tid; i < 32 * HS * pw4; i += THREADS) {
+        const int k4 = i % pw4, hb = i / pw4, hh = hb % HS, b = hb / HS;
+        const int col = (cr * HS + hh) * kw + p0;        // first column of k-part hh in this pass
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < B) {
+          v = __ldcg(reinterpret_cast<const float4*>(L.x + (size_t)b * L.xs + col) + k4);
+          if (L.add) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(L.add + (size_t)b * L.as + col) + k4);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+          }
         }
+        *reinterpret_cast<float4*>(s_x + b * XP + hh * PW + k4 * 4) =
+            make_float4(__uint_as_float(tf32_bits(v.x)), __uint_as_float(tf32_bits(v.y)), __uint_as_float(tf32_bits(v.z)),
+                        __uint_as_float(tf32_bits(v.w)));
       }
-      __syncwarp();
-      if (fc.l < P.nl) { fetch(fc, fi); advance(fc); ++fi; }             // refill the slot just consumed
+      __syncthreads();
+      for (int c0 = 0; c0 < pw; c0 += CW, ++ci) {
+        const int cw = min(CW, pw - c0);
+        const int slot = (ci & 1) * 8 + w;
+        mbar_wait(bar0 + 8 * slot, (uint32_t)(ci >> 1) & 1u);
+        const float* wa = s_ring + slot * STAGE_FLOATS + g8 * WP + t4;     // rows g8 / g8+8 of this warp's 16 outputs
+        const float* xb = s_x + g8 * XP + h * PW + c0 + t4;                // shape g8 of each 8-shape tile
+#pragma unroll 4
+        for (int k = 0; k < cw; k += 8) {
+          const uint32_t a0 = __float_as_uint(wa[k]), a1 = __float_as_uint(wa[8 * WP + k]);
+          const uint32_t a2 = __float_as_uint(wa[k + 4]), a3 = __float_as_uint(wa[8 * WP + k + 4]);
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const uint32_t b0 = __float_as_uint(xb[n * 8 * XP + k]), b1 = __float_as_uint(xb[n * 8 * XP + k + 4]);
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                         : "+f"(acc[n][0]), "+f"(acc[n][1]), "+f"(acc[n][2]), "+f"(acc[n][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+          }
+        }
+        __syncwarp();
+        if (fc.l < P.nl) { fetch(fc, fi); advance(fc); ++fi; }             // refill the slot just consumed
+      }
     }
     // C fragment: c0,c1 -> (row g8, shapes 2*t4, 2*t4+1); c2,c3 -> (row g8+8, same shapes)
+    {
+      float* sp = s_part + h * (32 * PP);
 #pragma unroll
-    for (int n = 0; n < 4; ++n)
+      for (int n = 0; n < 4; ++n)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        s_part[(n * 8 + 2 * t4 + (i & 1)) * PP + w * 16 + g8 + (i >= 2 ? 8 : 0)] = acc[n][i];
+        for (int i = 0; i < 4; ++i)
+          sp[(n * 8 + 2 * t4 + (i & 1)) * PP + rw * 16 + g8 + (i >= 2 ? 8 : 0)] = acc[n][i];
+    }
     cluster_sync_all();
     {
-      // CTA cr: columns [16 cr, 16 cr + 16) of the cluster's tile; thread -> (shape b, two adjacent outputs)
+      // CTA cr: columns [16 cr, 16 cr + 16) of the cluster's tile; thread -> (shape b, two adjacent outputs);
+      // the 8 partials are summed in K-slice order (peer CTA major, k-part minor)
       const int b = tid >> 3, oc = cr * 16 + (tid & 7) * 2;
       const uint32_t local = smem_u32(s_part + b * PP + oc);
       float v0 = 0.0f, v1 = 0.0f;
 #pragma unroll
       for (int p = 0; p < CL; ++p) {
         uint32_t remote;
-        float x0, x1;
         asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(p));
-        asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(remote) : "memory");
-        v0 += x0; v1 += x1;
+#pragma unroll
+        for (int hh = 0; hh < HS; ++hh) {
+          float x0, x1;
+          asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(x0), "=f"(x1) : "r"(remote + (uint32_t)(hh * 32 * PP * 4)) : "memory");
+          v0 += x0; v1 += x1;
+        }
       }
       const int o = cid * TO + oc;
       if (b < B) {
@@ -495,43 +515,51 @@ static int global_prior_forward_layers(Model* m, const float* x, const float* t,
 }
 
 // The persistent form is usable when every Linear fits the kernel's tiling and all 128 CTAs can be co-resident.
-static bool gp_persist_usable(const GlobalPriorBlk* g) {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("LION_GP_PERSIST"); on = e ? atoi(e) : 1; }
-  if (!on) return false;
-  auto ok = [](const GPLin& l) {
-    return l.K % (gpp::CL * 8) == 0 && l.K / gpp::CL <= gpp::KC_MAX && l.O % gpp::TO == 0 && l.O <= gpp::NCL * gpp::TO;
-  };
+// Returns the cluster size to launch (8, 4 or 2), or 0 for the two-kernel form.
+template <int CL>
+static int gp_clusters_resident() {
+  if (cudaFuncSetAttribute(gpp::k_gp_persist<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gpp::SMEM) != cudaSuccess) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gpp::NCTA); cfg.blockDim = dim3(gpp::THREADS); cfg.dynamicSmemBytes = gpp::SMEM;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gpp::k_gp_persist<CL>, &cfg) != cudaSuccess) n = 0;
+  return n;
+}
+static int gp_persist_cluster(const GlobalPriorBlk* g) {
+  static int want = -1;
+  if (want < 0) { const char* e = getenv("LION_GP_PERSIST"); want = e ? atoi(e) : 1; }
+  if (!want) return 0;
+  auto ok = [](const GPLin& l) { return l.K % 64 == 0 && l.K <= 8 * 4096 && l.O % 128 == 0 && l.O <= 2048; };
   bool all = ok(g->t0) && ok(g->t1) && ok(g->in) && ok(g->outl) && (!g->clip || ok(g->cmap));
   for (auto& c : g->cells) all = all && ok(c.c1) && ok(c.c2) && ok(c.se0) && ok(c.se2);
-  if (!all || 4 + 4 * (int)g->cells.size() + (g->clip ? 1 : 0) > gpp::MAXL) return false;
-  // co-residency of the 16 clusters, per device (a grid barrier deadlocks otherwise)
-  static int resident[64];
+  if (!all || 4 + 4 * (int)g->cells.size() + (g->clip ? 1 : 0) > gpp::MAXL) return 0;
+  // co-residency of all clusters, per device (a grid barrier deadlocks otherwise): the largest cluster size that fits
+  static int chosen[64];
   static bool asked[64];
   int d = 0;
-  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return false;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return 0;
   if (!asked[d]) {
     asked[d] = true;
-    resident[d] = 0;
-    if (cudaFuncSetAttribute(gpp::k_gp_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gpp::SMEM) == cudaSuccess) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(gpp::NCL * gpp::CL); cfg.blockDim = dim3(gpp::THREADS); cfg.dynamicSmemBytes = gpp::SMEM;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = gpp::CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, gpp::k_gp_persist, &cfg) == cudaSuccess) resident[d] = n;
-    }
+    chosen[d] = 0;
+    const int n8 = gp_clusters_resident<8>(), n4 = gp_clusters_resident<4>(), n2 = gp_clusters_resident<2>();
     (void)cudaGetLastError();
-    if (resident[d] < gpp::NCL)
-      fprintf(stderr, "lion_b200: global prior: %d of %d clusters co-resident on device %d -> two-kernel form\n", resident[d], gpp::NCL, d);
+    if (n8 >= gpp::NCTA / 8 && (want == 1 || want == 8)) chosen[d] = 8;
+    else if (n4 >= gpp::NCTA / 4 && (want == 1 || want == 4)) chosen[d] = 4;
+    else if (n2 >= gpp::NCTA / 2 && (want == 1 || want == 2)) chosen[d] = 2;
+    if (getenv("LION_VERBOSE") || !chosen[d])
+      fprintf(stderr, "lion_b200: global prior on device %d: co-resident clusters %d x8, %d x4, %d x2 -> %s\n", d, n8, n4, n2,
+              chosen[d] == 8 ? "persistent, clusters of 8" : chosen[d] == 4 ? "persistent, clusters of 4"
+              : chosen[d] == 2 ? "persistent, clusters of 2" : "two-kernel form");
   }
-  return resident[d] >= gpp::NCL;
+  return chosen[d];
 }
 
 // one chunk of <= 32 shapes through the persistent kernel (k_gp_posemb zeroes its barrier counter)
-static int global_prior_forward_persist(Model* m, const float* x, const float* t, const float* clip, float* out, int B) {
+static int global_prior_forward_persist(Model* m, const float* x, const float* t, const float* clip, float* out, int B, int CL) {
   GlobalPriorBlk* g = m->gp;
   Ctx* c = m->ctx;
   const int nf = g->nf, tw = g->clip ? 2 * nf : nf;
@@ -571,7 +599,9 @@ static int global_prior_forward_persist(Model* m, const float* x, const float* t
   }
   add(g->outl, h, nf, nullptr, 0, out, g->D, nullptr, 0, nullptr, 0, nullptr, 0, 0);
   if (!c->dry) {
-    gpp::k_gp_persist<<<gpp::NCL * gpp::CL, gpp::THREADS, gpp::SMEM, c->stream>>>(P);
+    if (CL == 8) gpp::k_gp_persist<8><<<gpp::NCTA, gpp::THREADS, gpp::SMEM, c->stream>>>(P);
+    else if (CL == 4) gpp::k_gp_persist<4><<<gpp::NCTA, gpp::THREADS, gpp::SMEM, c->stream>>>(P);
+    else gpp::k_gp_persist<2><<<gpp::NCTA, gpp::THREADS, gpp::SMEM, c->stream>>>(P);
     c->launches++;
   }
   return check_launch(c, "global_prior_forward (persistent)");
@@ -588,7 +618,8 @@ int global_prior_forward(Model* m, const float* x, const float* t, const float* 
     const float* xc = x + (size_t)b0 * g->D;
     const float* cc = clip ? clip + (size_t)b0 * g->clip_dim : nullptr;
     float* oc = out + (size_t)b0 * g->D;
-    if (gp_persist_usable(g)) LION_TRY(global_prior_forward_persist(m, xc, t + b0, cc, oc, nb));
+    const int CL = gp_persist_cluster(g);
+    if (CL) LION_TRY(global_prior_forward_persist(m, xc, t + b0, cc, oc, nb, CL));
     else LION_TRY(global_prior_forward_layers(m, xc, t + b0, cc, oc, nb));
     c->release(mk);
   }

@@ -92,3 +92,47 @@ def test_cuda_order_mean_emulation_is_a_mean():
         assert np.abs(m - ref).max() < 5e-7, (B, N)
     nc, vox = P.voxel_coords_cuda_order(torch.randn(2, 3, 256, generator=g).numpy(), 8)
     assert vox.dtype == torch.int32 and int(vox.min()) >= 0 and int(vox.max()) <= 7
+
+
+def _conv_items_sched1(U, per_nt, grid, G):
+    """Python model of the round-based work distribution of the convolution kernel (csrc/conv_tc.cu, `Items`, sched 1):
+    CTA i owns T_i = floor(U (i+1) / grid) - floor(U i / grid) tiles in m = ceil(max T / G) items; round k is one contiguous
+    stretch of the flat tile space holding every CTA's k-th item; an item is cut at n-tile boundaries."""
+    q, n_p = U // grid, U - (U // grid) * grid
+    n_q, m = grid - n_p, -(-(q + (1 if n_p else 0)) // G)
+    per = [[] for _ in range(grid)]
+    for i in range(grid):
+        u_begin, u_endr = U * i // grid, U * (i + 1) // grid
+        c_i, big = u_begin - q * i, (u_endr - u_begin) > q
+        k, u, u_end = 0, 0, 0
+        while True:
+            while u >= u_end and k < m:
+                a0, a1, b0, b1 = q * k // m, q * (k + 1) // m, (q + 1) * k // m, (q + 1) * (k + 1) // m
+                u = n_q * a0 + n_p * b0 + (i - c_i) * (a1 - a0) + c_i * (b1 - b0)
+                u_end = u + ((b1 - b0) if big else (a1 - a0))
+                k += 1
+            if u >= u_end:
+                break
+            nt = u // per_nt
+            e = min(u_end, (nt + 1) * per_nt)
+            per[i].append((nt, u - nt * per_nt, e - u))
+            u = e
+    return per
+
+
+def test_conv_interleaved_schedule_covers_every_tile_once():
+    # (tiles per shape, shapes, n-tiles, SMs, G): the step's shape classes at B = 32 plus ragged small cases
+    for ntile, B, n_nt, sms, G in ((307, 32, 1, 148, 8), (46, 32, 1, 148, 4), (8, 32, 1, 148, 4), (46, 32, 2, 148, 4),
+                                   (5, 3, 2, 148, 8), (1, 1, 1, 148, 8), (16, 32, 3, 148, 4), (307, 1, 1, 148, 8), (41, 32, 1, 148, 8), (9, 7, 1, 148, 2)):
+        per_nt, U = B * ntile, B * ntile * n_nt
+        per_cta = -(-U // sms)
+        grid = -(-U // per_cta)                       # conv_tc_run: fewest CTAs that reach the minimal maximum
+        per = _conv_items_sched1(U, per_nt, grid, G)
+        seen = []
+        for items in per:
+            for nt, v0, n in items:
+                assert 1 <= n <= G and v0 + n <= per_nt        # fits the TMEM accumulators, never crosses an n-tile
+                seen += [nt * per_nt + v0 + k for k in range(n)]
+        assert sorted(seen) == list(range(U))
+        totals = [sum(n for _, _, n in items) for items in per]
+        assert max(totals) == per_cta and max(totals) - min(totals) <= 1
