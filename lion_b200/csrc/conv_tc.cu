@@ -803,13 +803,13 @@ int conv_tc_run(Ctx* c, const ConvW& w, const float4* in, int Gin, float4* out, 
   { static int ge = -1; if (ge < 0) { const char* e = getenv("LION_TC_G"); ge = e ? atoi(e) : 0; } if (ge > 0 && ge < G) G = ge; }
   P.G = G;
   P.B = B;
-  // Round-based items (sched 1) where the input cannot stay in the L2 between a tile's three x-plane sweeps (> 96 MB: the
-  // 32-/64-channel grids at r = 32, B = 32): DRAM reads of the 64 -> 64 launch drop from 975 MB to 325 MB at equal or
-  // better time; the r = 16 / r = 8 launches are L2-resident either way and measured 5-14 % slower with it
-  // (gpurun call 32, profiles/r02_conv_sched_ab.txt), so they keep one contiguous range per CTA.  LION_CONV_SCHED=0|1 forces.
+  // Round-based items (sched 1) for the 64-channel grids at r = 32 (268 MB of input at B = 32, twice the L2): DRAM reads of
+  // the 64 -> 64 launch drop from 975 MB to 326 MB and it runs 2-3 % faster (0.400 vs 0.4125 ms).  Launches whose input is
+  // L2-resident (r = 16 / r = 8) measured 5-14 % slower with it and the 32-channel r = 32 grids (134 MB) 1-4 % slower
+  // (gpurun calls 32-33, profiles/r02_conv_sched_ab.txt): they keep one contiguous range per CTA.  LION_CONV_SCHED=0|1 forces.
   { static int sc = -2; if (sc == -2) { const char* e = getenv("LION_CONV_SCHED"); sc = e ? atoi(e) : -1; }
     const double in_bytes = (double)B * Gin * geo.rows * 16.0;
-    P.sched = sc >= 0 ? sc : (w.ntaps == 27 && in_bytes > 96e6 ? 1 : 0); }
+    P.sched = sc >= 0 ? sc : (w.ntaps == 27 && in_bytes > 200e6 ? 1 : 0); }
   P.occ = geo.occ; P.occ_stride = geo.occ_stride;
   { static int ns = -1; if (ns < 0) { const char* e = getenv("LION_TC_NOSKIP"); ns = e ? atoi(e) : 0; } if (ns) P.occ = nullptr; }
   const size_t fixed = 128 * 4 + 8 * 2 * 64 * 4 + 64 * 8 + 128 + tc::OCC_SMEM;

@@ -37,9 +37,10 @@ __device__ __forceinline__ float warp_transpose_sum32(float* v, int lane) {
 }
 
 // Split-K skinny GEMM, phase 1:  part[ks][b][o] = sum_{k in slice ks} W[o][k] * (x[b][k] + add[b][k])
-// grid = (O/128, K/256).  M = 32 shapes is far below a tcgen05 tile (M >= 128 rows of the SAME
-// operand), so this layer uses warp-level mma.sync.m16n8k8 TF32 (the reference's cuDNN 1x1
-// convolutions run TF32 as well): A = 16 weight rows x 8 k, B = 8 k x 8 shapes.
+// grid = (O/128, K/256).  Warp-level mma.sync.m16n8k8 TF32 (the reference's cuDNN 1x1 convolutions
+// run TF32 as well): A = 16 weight rows x 8 k, B = 8 k x 8 shapes.  With the operands swapped
+// (M = 128 weight rows, N = 32 shapes) this is a legal tcgen05 shape too, but the layer is bound by
+// launch latency and weight streaming (0.15 GFLOP per shape), not by the tensor pipe.
 //   * the block's weight tile [128 x 256] (128 KB) streams HBM -> shared memory with cp.async in
 //     four 64-column commit groups, so the tensor work on group g overlaps the arrival of g+1;
 //   * the activation slice [32 x 256] is staged once per block (rounded to TF32, round-to-nearest);
