@@ -481,18 +481,27 @@ def main():
                     self.waited.add(lo)
                 return dl[1 + t]
 
+        e2e_ev = []                                               # CUDA events at the phase boundaries of the last pass
+
         def e2e_pass():
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
             dg = hn_g.to(dev, non_blocking=True)
             dl[0].copy_(hn_l[0], non_blocking=True)               # x_T of the latent points
             zl = StreamedNoise()
+            ev[1].record()
             z_g, _ = diff.run_denoising_diffusion(dae[0], B, shape[0], given_noise=(dg[0], dg[1:]))
+            ev[2].record()
             z_l, _ = diff.run_denoising_diffusion(dae[1], B, shape[1], condition_input=vae.global2style(z_g),
                                                   given_noise=(dl[0], zl))
+            ev[3].record()
             pts = vae.sample(num_samples=B, decomposed_eps=vae.decompose_eps(vae.compose_eps([z_g, z_l])))
             if world > 1:
                 dist.all_gather(gathered[0], pts.contiguous())
             hout.copy_(pts, non_blocking=True)
+            ev[4].record()
             torch.cuda.synchronize(dev)
+            e2e_ev[:] = ev
 
         e2e_pass()                                          # warm-up
         barrier()
@@ -505,7 +514,10 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * n_e2e / dt.item(), "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "note": "x_T and every per-step noise tensor of both priors come from pinned host memory (the 1 GB of latent-point noise streams in 13 MB chunks on a copy stream, overlapped with the denoising steps); generated points are read back"}
+               "note": "x_T and every per-step noise tensor of both priors come from pinned host memory (the 1 GB of latent-point noise streams in 13 MB chunks on a copy stream, overlapped with the denoising steps); generated points are read back",
+               "seconds_per_pass_wall": dt.item() / n_e2e,
+               "phases_ms_last_pass": {"h2d_setup": e2e_ev[0].elapsed_time(e2e_ev[1]), "global_prior_loop": e2e_ev[1].elapsed_time(e2e_ev[2]),
+                                       "local_prior_loop": e2e_ev[2].elapsed_time(e2e_ev[3]), "decoder_gather_d2h": e2e_ev[3].elapsed_time(e2e_ev[4])}}
 
     # ---- phase breakdown (one extra pass, CUDA events; diagnostic only) -------------------------
     phases = None
