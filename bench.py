@@ -62,25 +62,29 @@ def parse():
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--clock-period-ms", type=int, default=1000, help="nvidia-smi sampling period during the timed region")
     ap.add_argument("--allow-knobs", action="store_true", help="run although LION_* performance knobs are set (they are recorded in the line)")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (one looping nvidia-smi process, 1 sample/s by default).
+    The query is kept light: at 5 samples/s with power.draw in it, rank 0 -- the only rank that samples -- ran its passes
+    2.2 % slower than rank 1 (profiles/r02_bench_n2_final.json: 6666 vs 6519 ms), every query takes the driver lock."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=1000):
         self.index = index
+        self.period_ms = int(period_ms)
         self.rows = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -104,7 +108,7 @@ class ClockSampler:
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
+                for n, v in zip(names, r[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
@@ -399,7 +403,7 @@ def main():
     barrier()
     launches["n"] = 0
     diff.total_gpu_launches = 0
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_period_ms)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
