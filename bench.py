@@ -461,6 +461,15 @@ def main():
         dl = torch.empty(hn_l.shape, device=dev)
         CH = 50                                                   # timesteps per chunk (13 MB)
 
+        class DeviceNoise:
+            """given_noise[1] already on the device: the captured step fetches row t itself (lion_ddpm_fetch_noise)"""
+
+            def __init__(self, block):
+                self.device_block = block
+
+            def __getitem__(self, t):
+                return self.device_block[t]
+
         class StreamedNoise:
             """given_noise[1]: z[t] -> device tensor, after making the current stream wait for its upload"""
 
@@ -478,11 +487,16 @@ def main():
                         self.events[lo] = ev
                 self.waited = set()
 
-            def __getitem__(self, t):
+            device_block = dl[1:]                                 # row t = z[t]: fetched inside the captured step
+
+            def ensure(self, t):
                 lo = 1 + ((t + 1 - 1) // CH) * CH
                 if lo not in self.waited:
                     torch.cuda.current_stream().wait_event(self.events[lo])
                     self.waited.add(lo)
+
+            def __getitem__(self, t):
+                self.ensure(t)
                 return dl[1 + t]
 
         e2e_ev = []                                               # CUDA events at the phase boundaries of the last pass
@@ -494,7 +508,7 @@ def main():
             dl[0].copy_(hn_l[0], non_blocking=True)               # x_T of the latent points
             zl = StreamedNoise()
             ev[1].record()
-            z_g, _ = diff.run_denoising_diffusion(dae[0], B, shape[0], given_noise=(dg[0], dg[1:]))
+            z_g, _ = diff.run_denoising_diffusion(dae[0], B, shape[0], given_noise=(dg[0], DeviceNoise(dg[1:])))
             ev[2].record()
             z_l, _ = diff.run_denoising_diffusion(dae[1], B, shape[1], condition_input=vae.global2style(z_g),
                                                   given_noise=(dl[0], zl))
@@ -518,7 +532,7 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * n_e2e / dt.item(), "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "note": "x_T and every per-step noise tensor of both priors come from pinned host memory (the 1 GB of latent-point noise streams in 13 MB chunks on a copy stream, overlapped with the denoising steps); generated points are read back",
+               "note": "x_T and every per-step noise tensor of both priors come from pinned host memory (the 1 GB of latent-point noise streams in 13 MB chunks on a copy stream, overlapped with the denoising steps; each captured step fetches its row of the uploaded block by the device-side step counter); generated points are read back",
                "seconds_per_pass_wall": dt.item() / n_e2e,
                "phases_ms_last_pass": {"h2d_setup": e2e_ev[0].elapsed_time(e2e_ev[1]), "global_prior_loop": e2e_ev[1].elapsed_time(e2e_ev[2]),
                                        "local_prior_loop": e2e_ev[2].elapsed_time(e2e_ev[3]), "decoder_gather_d2h": e2e_ev[3].elapsed_time(e2e_ev[4])}}

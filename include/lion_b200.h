@@ -170,6 +170,10 @@ int lion_ddpm_update(const float* x, const float* eps, const float* noise, float
 /* set / decrement the device-side step counter and write the model's timestep (t+1, 1..T) into t_out[B] */
 int lion_ddpm_set_step(int* step_ptr, float* t_out, int B, int t_index, void* stream);
 int lion_ddpm_next_step(int* step_ptr, float* t_out, int B, void* stream);
+/* dst[n] = block[t][n] with t = *step_ptr on the device: the noise of the current step out of a device-resident
+ * [T][n] block (the `given_noise` of run_denoising_diffusion, utils/diffusion_pvd.py:283-285, uploaded ahead of the
+ * loop), so that the copy is part of the captured step.  n % 4 == 0, 16-byte aligned pointers. */
+int lion_ddpm_fetch_noise(float* dst, const float* block, const int* step_ptr, size_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * One DDIM step (utils/diffusion_pvd.py:389-473, update at :450 and :464-465), elementwise:

@@ -65,6 +65,7 @@ def _proto(lib):
         "lion_ddpm_update": (P(vp, vp, vp, vp, vp, vp, f, sz, vp, i, vp), i),
         "lion_ddpm_set_step": (P(vp, vp, i, i, vp), i),
         "lion_ddpm_next_step": (P(vp, vp, i, vp), i),
+        "lion_ddpm_fetch_noise": (P(vp, vp, vp, sz, vp), i),
         "lion_conv3d_gn_fwd": (P(vp, vp, vp, vp, vp, i, vp), i),
         "lion_global_prior_step": (P(vp, vp, vp, vp, vp, i, vp), i),
         "lion_workspace_bytes": (P(vp), sz),

@@ -37,6 +37,16 @@ __global__ void k_ddpm_update(const float* x /* may alias xo (in-place update) *
   if (hist) hist[(size_t)(T - 1 - t) * n + i] = r;   // trajectory slot of this step (pred_x)
 }
 
+// Row `*step` of a device-resident noise block [rows][n] -> dst[n].  Lets a caller who supplies every step's noise
+// (given_noise: host noise uploaded ahead of the loop) keep the copy INSIDE the captured step graph, selected by the same
+// device-side step counter as the update's table row: no per-step host work besides the graph replay.
+__global__ void k_ddpm_fetch_noise(float4* __restrict__ dst, const float4* __restrict__ block, const int* __restrict__ step, size_t n4) {
+  pdl_prologue();
+  const int t = *step;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) dst[i] = block[(size_t)t * n4 + i];
+}
+
 __global__ void k_ddpm_set_step(int* step, float* t_out, int B, int t_index, int advance) {
   pdl_prologue();
   int t = advance ? (*step - 1) : t_index;
@@ -104,6 +114,14 @@ extern "C" int lion_ddpm_update(const float* x, const float* eps, const float* n
   c.stream = (cudaStream_t)stream;
   LION_LAUNCH(&c, k_ddpm_update, (unsigned)cdivz(n, 256), 256, 0, x, eps, noise ? noise : x, x_out, (const float4*)tables, step_ptr, temp, n, hist, T);
   return check_launch(&c, "lion_ddpm_update");
+}
+extern "C" int lion_ddpm_fetch_noise(float* dst, const float* block, const int* step_ptr, size_t n, void* stream) {
+  LION_REQUIRE(dst && block && step_ptr && n > 0 && n % 4 == 0, "lion_ddpm_fetch_noise: bad arguments (n must be a multiple of 4)");
+  LION_REQUIRE(((uintptr_t)dst | (uintptr_t)block) % 16 == 0, "lion_ddpm_fetch_noise: dst / block must be 16-byte aligned");
+  Ctx c;
+  c.stream = (cudaStream_t)stream;
+  LION_LAUNCH(&c, k_ddpm_fetch_noise, (unsigned)cdivz(n / 4, 256), 256, 0, (float4*)dst, (const float4*)block, step_ptr, n / 4);
+  return check_launch(&c, "lion_ddpm_fetch_noise");
 }
 extern "C" int lion_ddpm_set_step(int* step_ptr, float* t_out, int B, int t_index, void* stream) {
   LION_REQUIRE(step_ptr && t_out && B > 0 && t_index >= 0, "lion_ddpm_set_step: bad arguments");

@@ -109,9 +109,24 @@ class DiffusionDiscretized(object):
         lib = L.lib()
         launches = 0
 
+        # given_noise[1] may be a device-resident block: an object with `device_block` (contiguous fp32 CUDA tensor
+        # [T, *size], row t = the noise of timestep t) and optionally `ensure(t)` (called on the host before step t is
+        # enqueued, e.g. to make the stream wait for an upload still in flight).  The step then fetches its row inside the
+        # captured graph (lion_ddpm_fetch_noise, indexed by the device-side step counter) instead of one host-issued copy
+        # per step between graph replays.
+        block = getattr(given_noise[1], 'device_block', None) if given_noise is not None else None
+        if block is not None:
+            if not (block.is_cuda and block.dtype == torch.float32 and block.is_contiguous() and block.shape[0] >= T
+                    and block[0].numel() == n and n % 4 == 0 and block.data_ptr() % 16 == 0):
+                raise ValueError("lion_b200: given_noise device_block must be a contiguous fp32 CUDA tensor [T, *size]")
+        ensure = getattr(given_noise[1], 'ensure', None) if block is not None else None
+
         def draw_noise(t):
             if given_noise is None:
                 torch.randn(size, device=dev, out=noise)
+            elif block is not None:
+                if ensure is not None:
+                    ensure(t)
             else:
                 noise.copy_(given_noise[1][t].to(dev, torch.float32))
 
@@ -119,6 +134,8 @@ class DiffusionDiscretized(object):
             pred = model(x=x, t=tfl, condition_input=condition_input, clip_feat=clip_feat)
             if draw:
                 torch.randn(size, device=dev, out=noise)
+            elif block is not None:
+                L.check(lib.lion_ddpm_fetch_noise(L.ptr(noise), L.ptr(block), L.ptr(step), n, L.stream()), "ddpm_fetch_noise")
             L.check(lib.lion_ddpm_update(L.ptr(x), L.ptr(pred.contiguous()), L.ptr(noise), L.ptr(x), L.ptr(tables),
                                          L.ptr(step), float(temp), n, L.ptr(hist), T, L.stream()), "ddpm_update")
             L.check(lib.lion_ddpm_next_step(L.ptr(step), L.ptr(tfl), num_samples, L.stream()), "ddpm_next_step")
@@ -131,7 +148,7 @@ class DiffusionDiscretized(object):
             if given_noise is not None:
                 draw_noise(T - 1)
             body(given_noise is None)
-            per_step = L.last_launches(dev) + 2
+            per_step = L.last_launches(dev) + 2 + (1 if block is not None else 0)
             launches += per_step
             graph = None
             if graph_ok:

@@ -144,6 +144,40 @@ def test_ddpm10_config0_golden():
         assert rms_err(img, z["image"]) < 5e-2
 
 
+def test_given_noise_device_block_equals_per_step_copies():
+    """given_noise as a device-resident block (the step fetches its row inside the captured graph, indexed by the
+    device-side step counter: lion_ddpm_fetch_noise) must give the same bits as the per-step host-issued copies of the
+    reference-shaped hook (utils/diffusion_pvd.py:283-285), eagerly and under graph replay, B = 2 global prior."""
+    from lion_b200.utils.diffusion_pvd import DiffusionDiscretized
+    cfg = _cfg(num_steps=10)
+    diff = DiffusionDiscretized(cfg.sde, None, cfg)
+    gp = _global()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x_T = torch.randn(2, 128, 1, 1, device="cuda", generator=g)
+    zs = torch.randn(10, 2, 128, 1, 1, device="cuda", generator=g)
+
+    class Block:
+        def __init__(self, t):
+            self.device_block, self.seen = t, []
+
+        def ensure(self, t):
+            self.seen.append(t)
+
+        def __getitem__(self, t):
+            return self.device_block[t]
+
+    for use_graph in (False, True):
+        diff.use_cuda_graph = use_graph
+        a, la = diff.run_denoising_diffusion(gp, 2, [128, 1, 1], given_noise=(x_T, list(zs)))
+        blk = Block(zs)
+        b, lb = diff.run_denoising_diffusion(gp, 2, [128, 1, 1], given_noise=(x_T, blk))
+        assert torch.equal(a, b), "graph=%s" % use_graph
+        assert all(torch.equal(p, q) for p, q in zip(la["pred_x"], lb["pred_x"]))
+        assert blk.seen == list(range(9, -1, -1))            # every step announced on the host, last timestep first
+    with pytest.raises(ValueError):
+        diff.run_denoising_diffusion(gp, 2, [128, 1, 1], given_noise=(x_T, Block(zs.double())))
+
+
 def test_ddpm10_teacher_forced_per_step():
     """Every one of the 10 denoising steps of configs[0], started from the REFERENCE's own state
     at that step (tests/golden/ddpm10.npz: traj_full), must reproduce the reference's next state."""
