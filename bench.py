@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-extra-configs", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--e2e-upload", default="stream", choices=["stream", "first"],
+                    help="end-to-end leg: stream the per-step noise upload under the denoising loops, or finish it first")
+    ap.add_argument("--e2e-compare", action="store_true", help="(diagnostic) also time the other --e2e-upload mode")
     ap.add_argument("--clock-period-ms", type=int, default=1000, help="nvidia-smi sampling period during the timed region")
     ap.add_argument("--allow-knobs", action="store_true", help="run although LION_* performance knobs are set (they are recorded in the line)")
     return ap.parse_args()
@@ -507,6 +510,8 @@ def main():
             dg = hn_g.to(dev, non_blocking=True)
             dl[0].copy_(hn_l[0], non_blocking=True)               # x_T of the latent points
             zl = StreamedNoise()
+            if upload_first:
+                torch.cuda.current_stream().wait_stream(copy_stream)   # the whole upload precedes the first denoising step
             ev[1].record()
             z_g, _ = diff.run_denoising_diffusion(dae[0], B, shape[0], given_noise=(dg[0], DeviceNoise(dg[1:])))
             ev[2].record()
@@ -521,21 +526,36 @@ def main():
             torch.cuda.synchronize(dev)
             e2e_ev[:] = ev
 
-        e2e_pass()                                          # warm-up
-        barrier()
-        t0 = time.perf_counter()
+        def timed_e2e(first):
+            nonlocal upload_first
+            upload_first = first
+            e2e_pass()                                      # warm-up
+            barrier()
+            t0_ = time.perf_counter()
+            for _ in range(n_e2e):
+                e2e_pass()
+            barrier()
+            dt_ = torch.tensor([time.perf_counter() - t0_], device=dev)
+            if world > 1:
+                dist.all_reduce(dt_, op=dist.ReduceOp.MAX)
+            ph = {"h2d_setup": e2e_ev[0].elapsed_time(e2e_ev[1]), "global_prior_loop": e2e_ev[1].elapsed_time(e2e_ev[2]),
+                  "local_prior_loop": e2e_ev[2].elapsed_time(e2e_ev[3]), "decoder_gather_d2h": e2e_ev[3].elapsed_time(e2e_ev[4])}
+            return dt_, ph
+
         n_e2e = max(1, min(args.steps, 2))
-        for _ in range(n_e2e):
-            e2e_pass()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        upload_first = False
+        dt, e2e_phases = timed_e2e(args.e2e_upload == "first")
+        e2e_other = None
+        if args.e2e_compare:                                # diagnostic: the other upload mode on the same box
+            dt_o, ph_o = timed_e2e(args.e2e_upload != "first")
+            e2e_other = {"upload": "stream" if args.e2e_upload == "first" else "first",
+                         "value": world * B * n_e2e / dt_o.item(), "phases_ms_last_pass": ph_o}
         e2e = {"value": world * B * n_e2e / dt.item(), "unit": "shapes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "note": "x_T and every per-step noise tensor of both priors come from pinned host memory (the 1 GB of latent-point noise streams in 13 MB chunks on a copy stream, overlapped with the denoising steps; each captured step fetches its row of the uploaded block by the device-side step counter); generated points are read back",
                "seconds_per_pass_wall": dt.item() / n_e2e,
-               "phases_ms_last_pass": {"h2d_setup": e2e_ev[0].elapsed_time(e2e_ev[1]), "global_prior_loop": e2e_ev[1].elapsed_time(e2e_ev[2]),
-                                       "local_prior_loop": e2e_ev[2].elapsed_time(e2e_ev[3]), "decoder_gather_d2h": e2e_ev[3].elapsed_time(e2e_ev[4])}}
+               "upload": args.e2e_upload, "phases_ms_last_pass": e2e_phases}
+        if e2e_other:
+            e2e["other_upload_mode"] = e2e_other
 
     # ---- phase breakdown (one extra pass, CUDA events; diagnostic only) -------------------------
     phases = None
