@@ -5,7 +5,8 @@ num_train_timesteps, variance_type)`, :39-40 `set_timesteps(1000, device)` / `.t
 
 diffusers (pinned 0.11.1 in the reference's env.yaml) is not vendored in the reference and not
 installed here, so the published algorithm of its scheduling_ddpm.py is restated -- PARITY
-UNPINNED (SURVEY.md 8c iii): epsilon prediction, fp32 `linspace` betas, `cumprod` in fp32,
+UNPINNED by the letter (SURVEY.md 8c iii; the CPU restatement in oracle/scheduler.py reproduces the
+known-answer values of diffusers' own scheduler tests, tests/test_scheduler_route.py): epsilon prediction, fp32 `linspace` betas, `cumprod` in fp32,
   x0 = (x - sqrt(1-abar_t) eps) / sqrt(abar_t)
   prev = sqrt(abar_{t-1}) beta_t / (1-abar_t) * x0 + sqrt(alpha_t) (1-abar_{t-1}) / (1-abar_t) * x
   x' = prev + sqrt(var_t) z  (t > 0; z drawn with torch.randn on the sample's device), x' = prev (t = 0)
