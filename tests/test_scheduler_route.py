@@ -61,6 +61,29 @@ def test_scheduler_restatement_reproduces_diffusers_known_answers():
     assert abs(float(x.abs().mean()) - 0.3374) < 1e-3
 
 
+def test_product_scheduler_tables_reproduce_diffusers_known_answers():
+    """The same known answers through the PRODUCT's host side: `DDPMScheduler._get_variance` and the [T][8] table rows that
+    feed `lion_scheduler_step`, evaluated with the kernel's own expression (csrc/ddpm.cu: k_sched_step) on the CPU; the
+    clamp of x0 is the `clip_sample=True` of the diffusers test configuration, which LION itself switches off."""
+    from lion_b200.utils.ddpm_scheduler import DDPMScheduler
+    sc = DDPMScheduler(num_train_timesteps=1000, beta_start=1e-4, beta_end=0.02, beta_schedule="linear",
+                       variance_type="fixed_small", clip_sample=False)
+    for t, want in ((0, 0.0), (487, 0.00979), (999, 0.02)):
+        assert abs(float(sc._get_variance(t)) - want) < 1e-5
+    tab = sc.step_tables(torch.device("cpu"))
+    n = 4 * 3 * 8 * 8
+    x = (torch.arange(n).reshape(3, 8, 8, 4) / n).permute(3, 0, 1, 2)
+    g = torch.Generator().manual_seed(0)
+    for t in reversed(range(1000)):
+        eps = x * t / (t + 1)
+        r = tab[t]
+        x0 = torch.clamp((x - r[0] * eps) / r[1], -1, 1)
+        prev = r[2] * x0 + r[3] * x
+        x = prev + r[4] * torch.randn(eps.shape, generator=g, dtype=eps.dtype) if t > 0 else prev
+    assert abs(float(x.abs().sum()) - 258.9070) < 1e-2
+    assert abs(float(x.abs().mean()) - 0.3374) < 1e-3
+
+
 @pytest.mark.gpu
 def test_scheduler_step_kernel_matches_restatement():
     from lion_b200.utils.ddpm_scheduler import DDPMScheduler
