@@ -119,3 +119,19 @@ def test_vae_state_dict_loads_strict():
     vae = Model(default_prior_cfg())
     vae.load_state_dict(sd, strict=True)
     assert set(vae.state_dict()) == set(sd)
+
+
+def test_shipped_library_contains_blackwell_tensor_and_bulk_copy_sass():
+    """The built liblion_b200.so must carry the sm_100a-native instructions the design rests on -- tcgen05.mma (UTCHMMA),
+    tcgen05.ld (LDTM), tcgen05.commit (UTCBAR), cp.async.bulk (UBLKCP), mbarriers (SYNCS) -- so that a silent fallback to the
+    SIMT convolution (`LION_CONV_IMPL=simt` is a debugging knob, not a build mode) cannot ship.  cuobjdump needs no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    so = os.path.join(ROOT, "lion_b200", "csrc", "liblion_b200.so")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in sass
+    for op, least in (("UTCHMMA", 100), ("LDTM", 10), ("UTCBAR", 10), ("UBLKCP", 10), ("SYNCS", 50)):
+        n = len(re.findall(r"\b%s\b" % op, sass))
+        assert n >= least, "%s appears %d times in the SASS (expected >= %d)" % (op, n, least)
