@@ -436,11 +436,17 @@ __global__ void k_affine_prep(PrepJob j0, PrepJob j1) {
     __syncthreads();
     // squeeze: one warp per hidden unit, lanes stride the C inputs (coalesced, C / 32 independent loads per lane) -- a
     // thread per hidden unit walked 128 weights serially, ~5 us of the 12 us these launches took at C = 128
-    for (int o = (int)(threadIdx.x >> 5); o < H; o += (int)(blockDim.x >> 5)) {
+    if ((blockDim.x & 31) == 0) {
+      for (int o = (int)(threadIdx.x >> 5); o < H; o += (int)(blockDim.x >> 5)) {
+        float a = 0.0f;
+        for (int k = (int)(threadIdx.x & 31); k < C; k += 32) a = fmaf(J.se_w1[o * C + k], s_f[k], a);
+        a = warp_sum(a);
+        if ((threadIdx.x & 31) == 0) s_h[o] = fmaxf(a, 0.0f);
+      }
+    } else if (c < H) {      // channel counts that are not a multiple of the warp size (none in the shipped configs)
       float a = 0.0f;
-      for (int k = (int)(threadIdx.x & 31); k < C; k += 32) a = fmaf(J.se_w1[o * C + k], s_f[k], a);
-      a = warp_sum(a);
-      if ((threadIdx.x & 31) == 0) s_h[o] = fmaxf(a, 0.0f);
+      for (int k = 0; k < C; ++k) a = fmaf(J.se_w1[c * C + k], s_f[k], a);
+      s_h[c] = fmaxf(a, 0.0f);
     }
     __syncthreads();
     if (on) {
